@@ -1,0 +1,329 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-ends for (a) ``liboracle.so`` -- the independent CPU restatement of the hot path
+(``mdqt_oracle.c``) -- and (b) ``_ref/libref_*.so`` -- the UNMODIFIED reference programs compiled through
+the hijack harnesses (``ref_*_harness.cpp``).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+CPU-baseline legs of ``bench.py`` may import this module; the product package never does.
+
+All arrays are float64 numpy, C-contiguous: R, V, F, A are ``[3][n]``; psi is ``[n][S][2]``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+def _dp(a):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(c_double_p)
+
+
+def build(quiet=True):
+    """Build liboracle.so (always) and, when the reference sources are present, oracle/_ref/*.so."""
+    out = subprocess.run(["make", "-C", HERE, "all"], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + out.stdout + out.stderr)
+    if not quiet:
+        print(out.stdout)
+
+
+class QTParams(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_double) for k in (
+        "detuning", "detuningDP", "Om", "OmDP", "dR", "kRat", "vKick", "vKickDP", "g2E", "pv2qv", "dtq",
+        "fracOfSig", "Te", "sig0", "density")] + [("renorm", ctypes.c_int), ("quad", ctypes.c_int)]
+
+
+def su_params(Ge=0.1, density=2.0, sig0=4.0, Te=19.0, fracOfSig=0.0, detuning=-1.0, detuningDP=1.0, Om=1.0,
+              OmDP=1.0, renorm=0):
+    """Derived constants exactly as the reference evaluates them (SU:79-85, 146-149, 295-297)."""
+    import math
+    ratio = int(math.ceil(34.81 / math.sqrt(density)))
+    pv2qv = 1.1821 * math.pow(density, 1. / 6)
+    vKick = 0.001208 / pv2qv
+    kRat = 0.395
+    p = QTParams(detuning=detuning, detuningDP=detuningDP, Om=Om, OmDP=OmDP, dR=0.0617, kRat=kRat, vKick=vKick,
+                 vKickDP=vKick * kRat, g2E=174.07 / math.sqrt(density), pv2qv=pv2qv, dtq=0.002 / ratio,
+                 fracOfSig=fracOfSig, Te=Te, sig0=sig0, density=density, renorm=renorm, quad=0)
+    return p, ratio
+
+
+def mc408_params(n=2.0, detuning=-2.5, Om=0.7, quad=0, timeStep=0.005):
+    """Derived constants of the 7-level pump stage (MC408L:85-87, 115-122)."""
+    import math
+    ratio = int(round(87 / math.sqrt(n)))
+    pv2qv = 1.1821 * math.pow(n, 1. / 6)
+    p = QTParams(detuning=detuning, detuningDP=0.0, Om=Om, OmDP=0.0, dR=0.0617, kRat=0.0, vKick=0.001208 / pv2qv,
+                 vKickDP=0.0, g2E=174.07 / math.sqrt(n), pv2qv=pv2qv, dtq=timeStep / ratio, fracOfSig=0.0, Te=0.0,
+                 sig0=1.0, density=n, renorm=0, quad=quad)
+    return p, ratio
+
+
+class Oracle:
+    """The independent restatement (liboracle.so)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = self.lib = ctypes.CDLL(path)
+        L.orc_epot_su.restype = ctypes.c_double
+        L.orc_forces_su.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_double, c_double_p]
+        L.orc_forces_md.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_double_p]
+        L.orc_epot_su.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_double]
+        L.orc_step_su.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p] + [ctypes.c_double] * 3
+        L.orc_vv_positions.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double]
+        L.orc_vv_velocities.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double,
+                                        c_double_p, c_double_p, ctypes.c_int, ctypes.c_double, ctypes.c_double]
+        L.orc_qstep12.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p, ctypes.POINTER(QTParams),
+                                  c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_long), c_int_p]
+        L.orc_qstep7.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(QTParams), c_double_p, ctypes.c_int,
+                                 ctypes.POINTER(ctypes.c_long), c_int_p]
+        L.orc_uniforms5.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p]
+        L.orc_collision_draws.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p, c_double_p]
+
+    def philox(self, ctr, key):
+        c = (ctypes.c_uint32 * 4)(*ctr)
+        k = (ctypes.c_uint32 * 2)(*key)
+        o = (ctypes.c_uint32 * 4)()
+        self.lib.orc_philox4x32_10(c, k, o)
+        return list(o)
+
+    def uniforms5(self, seed, traj, n, substep):
+        """u[n][5] for ions 0..n-1 of trajectory `traj` at substep index `substep`."""
+        u = np.empty((n, 5))
+        for i in range(n):
+            self.lib.orc_uniforms5(seed, traj, i, substep, _dp(u[i]))
+        return u
+
+    def collision_draws(self, seed, traj, n, step):
+        u = np.empty(n)
+        nrm = np.empty((n, 3))
+        one = np.empty(1)
+        for i in range(n):
+            self.lib.orc_collision_draws(seed, traj, i, step, _dp(one), _dp(nrm[i]))
+            u[i] = one[0]
+        return u, nrm
+
+    def forces_su(self, R, L, lDeb):
+        F = np.empty_like(R)
+        self.lib.orc_forces_su(R.shape[1], _dp(R), L, lDeb, _dp(F))
+        return F
+
+    def forces_md(self, R, L, kappa, rCut):
+        A = np.empty_like(R)
+        self.lib.orc_forces_md(R.shape[1], _dp(R), L, kappa, rCut, _dp(A))
+        return A
+
+    def epot_su(self, R, L, lDeb):
+        return self.lib.orc_epot_su(R.shape[1], _dp(R), L, lDeb)
+
+    def step_su(self, R, V, F, L, dtq, t):
+        self.lib.orc_step_su(R.shape[1], _dp(R), _dp(V), _dp(F), L, dtq, t)
+
+    def vv_positions(self, R, V, A, L, dt):
+        self.lib.orc_vv_positions(R.shape[1], _dp(R), _dp(V), _dp(A), L, dt)
+
+    def vv_velocities(self, V, oldA, A, dt, collisionFreq=0.0, coll_u=None, coll_n=None, laser=0, beta=26000.0, dens=0.4):
+        self.lib.orc_vv_velocities(V.shape[1], _dp(V), _dp(oldA), _dp(A), dt, collisionFreq, _dp(coll_u), _dp(coll_n),
+                                   laser, beta, dens)
+
+    def qstep12(self, psi, Vx, tPart, t, p, u, sequential=False):
+        """One qstep() sweep in place; returns (new t, draws used per ion)."""
+        n = psi.shape[0]
+        tt = np.array([t], dtype=np.float64)
+        cur = ctypes.c_long(0)
+        used = np.zeros(n, dtype=np.int32)
+        self.lib.orc_qstep12(n, _dp(psi), _dp(Vx), _dp(tPart), _dp(tt), ctypes.byref(p), _dp(u), 1 if sequential else 0,
+                             ctypes.byref(cur), used.ctypes.data_as(c_int_p))
+        return float(tt[0]), used
+
+    def qstep7(self, psi, Vx, p, u, sequential=False):
+        n = psi.shape[0]
+        cur = ctypes.c_long(0)
+        used = np.zeros(n, dtype=np.int32)
+        self.lib.orc_qstep7(n, _dp(psi), _dp(Vx), ctypes.byref(p), _dp(u), 1 if sequential else 0, ctypes.byref(cur),
+                            used.ctypes.data_as(c_int_p))
+        return used
+
+
+def ref_available(name="su"):
+    return os.path.exists(os.path.join(HERE, "_ref", "libref_%s.so" % name))
+
+
+class RefSU:
+    """The unmodified reference SU program behind the hijack harness (oracle/_ref/libref_su.so)."""
+
+    def __init__(self, **kw):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_su.so"))
+        L.ref_su_epot.restype = ctypes.c_double
+        L.ref_su_get_t.restype = ctypes.c_double
+        L.ref_su_get_Epot0.restype = ctypes.c_double
+        L.ref_su_set_t.argtypes = [ctypes.c_double]
+        L.ref_su_set_Epot0.argtypes = [ctypes.c_double]
+        L.ref_su_set_box.argtypes = [ctypes.c_double, ctypes.c_double]
+        L.ref_su_init.argtypes = [ctypes.c_long]
+        L.ref_su_set_state.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p]
+        L.ref_su_get_state.argtypes = [c_double_p] * 5
+        L.ref_su_set_F.argtypes = [c_double_p]
+        L.ref_su_set_uniforms.argtypes = [c_double_p, ctypes.c_int]
+        L.ref_su_qstep_stream.argtypes = [c_double_p, c_int_p]
+        L.ref_su_get_tables.argtypes = [c_double_p] * 4
+        L.ref_su_set_savedir.argtypes = [ctypes.c_char_p]
+        L.ref_su_set_counters.argtypes = [ctypes.c_int, ctypes.c_uint]
+        L.ref_su_run_loop.argtypes = [ctypes.c_int] * 3
+        self.setup(**kw)
+
+    def setup(self, Ge=0.1, density=2.0, sig0=4.0, Te=19.0, fracOfSig=0.0, detuning=-1.0, detuningDP=1.0, Om=1.0,
+              OmDP=1.0, renorm=0):
+        p = (ctypes.c_double * 10)(Ge, density, sig0, Te, fracOfSig, detuning, detuningDP, Om, OmDP, renorm)
+        assert self.lib.ref_su_setup(p) == 0
+        c = (ctypes.c_double * 12)()
+        self.lib.ref_su_get_consts(c)
+        keys = ["L", "lDeb", "dtq", "g2E", "pv2qv", "vKick", "vKickDP", "ratio", "dR", "kRat", "TIMESTEP", "sampleFreq"]
+        self.consts = dict(zip(keys, list(c)))
+
+    def set_box(self, L, lDeb):
+        self.lib.ref_su_set_box(L, lDeb)
+        self.consts["L"], self.consts["lDeb"] = L, lDeb
+
+    def init(self, seed):
+        self.lib.ref_su_init(seed)
+        return self.lib.ref_su_get_N()
+
+    @property
+    def N(self):
+        return self.lib.ref_su_get_N()
+
+    def set_state(self, R=None, V=None, psi=None, tPart=None, t=None, n=None):
+        if n is None:
+            n = (R if R is not None else V if V is not None else None)
+            n = n.shape[1] if n is not None else (psi.shape[0] if psi is not None else tPart.shape[0])
+        self.lib.ref_su_set_state(n, _dp(R), _dp(V), _dp(psi), _dp(tPart))
+        if t is not None:
+            self.lib.ref_su_set_t(t)
+
+    def get_state(self):
+        n = self.N
+        R, V, F = np.empty((3, n)), np.empty((3, n)), np.empty((3, n))
+        psi, tp = np.empty((n, 12, 2)), np.empty(n)
+        self.lib.ref_su_get_state(_dp(R), _dp(V), _dp(F), _dp(psi), _dp(tp))
+        return dict(R=R, V=V, F=F, psi=psi, tPart=tp, t=self.lib.ref_su_get_t())
+
+    def set_F(self, F):
+        self.lib.ref_su_set_F(_dp(F))
+
+    def forces(self):
+        self.lib.ref_su_forces()
+
+    def step(self):
+        self.lib.ref_su_step()
+
+    def qstep(self, uniforms=None):
+        """qstep() with either the reference's own drand48 stream, or a sequential injected stream."""
+        if uniforms is not None:
+            self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+            self.lib.ref_su_set_uniforms(_dp(self._u), self._u.size)
+        self.lib.ref_su_qstep()
+        used = self.lib.ref_su_uniforms_used()
+        self.lib.ref_su_set_uniforms(None, 0)
+        return used
+
+    def qstep_stream(self, u5):
+        """qstep() sweep where ion i consumes u5[i][:]; returns draws used per ion."""
+        u5 = np.ascontiguousarray(u5, dtype=np.float64)
+        used = np.zeros(self.N, dtype=np.int32)
+        self.lib.ref_su_qstep_stream(_dp(u5), used.ctypes.data_as(c_int_p))
+        return used
+
+    def epot(self):
+        return self.lib.ref_su_epot()
+
+    def tables(self):
+        c, d, hd = np.empty((12, 12, 2)), np.empty((12, 12, 2)), np.empty((12, 12, 2))
+        gs = np.empty(18)
+        self.lib.ref_su_get_tables(_dp(c), _dp(d), _dp(hd), _dp(gs))
+        return c[..., 0] + 1j * c[..., 1], d[..., 0] + 1j * d[..., 1], hd[..., 0] + 1j * hd[..., 1], gs
+
+
+class RefMD:
+    """The unmodified reference MD-only program (oracle/_ref/libref_md.so); N=4096 fixed."""
+
+    def __init__(self):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_md.so"))
+        L.ref_md_set_controls.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        L.ref_md_set_state.argtypes = [c_double_p] * 3
+        L.ref_md_get_state.argtypes = [c_double_p] * 3
+        c = (ctypes.c_double * 7)()
+        L.ref_md_get_consts(c)
+        self.consts = dict(zip(["L", "rCut", "kappa", "Gamma", "n", "timeStep", "beta"], list(c)))
+        self.N = L.ref_md_N()
+
+    def seed(self, s):
+        self.lib.ref_md_seed(s)
+
+    def init(self):
+        self.lib.ref_md_init()
+
+    def set_controls(self, collisionFreq=0.0, laser=0, one_axis=0):
+        self.lib.ref_md_set_controls(collisionFreq, laser, one_axis)
+
+    def set_state(self, R=None, V=None, A=None):
+        self.lib.ref_md_set_state(_dp(R), _dp(V), _dp(A))
+
+    def get_state(self):
+        R, V, A = (np.empty((3, self.N)) for _ in range(3))
+        self.lib.ref_md_get_state(_dp(R), _dp(V), _dp(A))
+        return dict(R=R, V=V, A=A)
+
+    def accelerations(self):
+        self.lib.ref_md_accelerations()
+
+    def mdstep(self):
+        self.lib.ref_md_mdstep()
+
+
+class RefMC408L:
+    """The unmodified reference MC408L program (7-level pump; oracle/_ref/libref_mc408l.so); N=4096 fixed."""
+
+    def __init__(self, detuning=-2.5, Om=0.7, scratch="/tmp/mdqt_ref_scratch/"):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_mc408l.so"))
+        L.ref_mc_setup.argtypes = [c_double_p, ctypes.c_char_p]
+        L.ref_mc_set_state.argtypes = [c_double_p] * 4
+        L.ref_mc_get_state.argtypes = [c_double_p] * 4
+        L.ref_mc_set_uniforms.argtypes = [c_double_p, ctypes.c_long]
+        L.ref_mc_uniforms_used.restype = ctypes.c_long
+        L.ref_mc_set_controls.argtypes = [ctypes.c_double]
+        p = (ctypes.c_double * 2)(detuning, Om)
+        assert L.ref_mc_setup(p, scratch.encode()) == 0
+        c = (ctypes.c_double * 12)()
+        L.ref_mc_get_consts(c)
+        keys = ["L", "rCut", "kappa", "Gamma", "n", "timeStep", "g2E", "ratio", "dtq", "pv2qv", "dR", "pumpMDTimeSteps"]
+        self.consts = dict(zip(keys, list(c)))
+        self.N = L.ref_mc_N()
+
+    def set_state(self, R=None, V=None, A=None, psi=None):
+        self.lib.ref_mc_set_state(_dp(R), _dp(V), _dp(A), _dp(psi))
+
+    def get_state(self):
+        R, V, A = (np.empty((3, self.N)) for _ in range(3))
+        psi = np.empty((self.N, 7, 2))
+        self.lib.ref_mc_get_state(_dp(R), _dp(V), _dp(A), _dp(psi))
+        return dict(R=R, V=V, A=A, psi=psi)
+
+    def qstep(self, uniforms):
+        self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        self.lib.ref_mc_set_uniforms(_dp(self._u), self._u.size)
+        self.lib.ref_mc_qstep()
+        used = self.lib.ref_mc_uniforms_used()
+        self.lib.ref_mc_set_uniforms(None, 0)
+        return used
+
+    def mdstep(self):
+        self.lib.ref_mc_mdstep()
