@@ -1,0 +1,154 @@
+/* include/mdqt.h -- C ABI of libmdqt_b200.so: the B200-native replacement for the per-timestep MDQT hot path
+ * of tlangin/MDQTPlasmaSims (Yukawa force evaluation, position/velocity update, per-ion quantum-trajectory step).
+ *
+ * The reference has NO plugin / FFI API: its seam is a set of `void f(void)` free functions that main() calls on
+ * file-scope global arrays (SU = laserCoolingPlusExpansionMDQTSpeedUp.cpp, MD =
+ * MonteCarloFollowedByMDAndTempAnisotropy.cpp, MC408L = MonteCarloFollowedByQTTagging408Linear.cpp):
+ *
+ *     double R[3][N0+1000], V[3][..], F[3][..]; unsigned N;      SU:126-129      -> mdqt_upload_state / mdqt_download_state
+ *     cx_mat wvFns[N0+1000]; double tPart[..]; double t;         SU:151-152,114  -> same (psi as double [n][S][2])
+ *     void forces(void)                                          SU:192-236      -> mdqt_forces
+ *     void step(void); void qstep(void)   (one quantum substep)  SU:418-430, 438-717 -> mdqt_substeps(h, nsub)
+ *     main loop: forces() every `ratio` substeps                 SU:1369-1378    -> mdqt_md_steps(h, nsteps)
+ *     void Epotential(void)                                      SU:244-281      -> mdqt_epot
+ *     output(): <v_x>, E_kin, KDE P(v), S/P/D populations        SU:917-1032     -> mdqt_diagnostics / mdqt_vel_dist / mdqt_populations
+ *     void calculateAccelerations(int); void MDStep(int)         MD:387-448, 504-511 -> mdqt_forces / mdqt_vv_step
+ *     void qstep(void)  7-level pump, no kick                    MC408L:555-756  -> mdqt_qsteps
+ *
+ * Plain pointers and sizes only; every call returns 0 on success or a negative MDQT_E* code, and
+ * mdqt_last_error() gives the message. The library never calls exit() and has NO CPU fallback: without a CUDA
+ * device every compute entry point fails with MDQT_ENODEVICE.
+ *
+ * Host array layouts are the reference's: R, V, F = double [3][ld] (component-major, ld >= n_ions);
+ * psi = double [n_ions][S][2] (re, im) with S = scheme (12 or 7); tPart = double [n_ions].
+ * With n_traj > 1 (an ensemble shard batched in one handle) every array gains a leading [n_traj] dimension.
+ * A handle is bound to one GPU; calls on one handle are stream-ordered and must not be made concurrently.
+ */
+#ifndef MDQT_H
+#define MDQT_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDQT_OK 0
+#define MDQT_EINVAL (-1)
+#define MDQT_ENODEVICE (-2)
+#define MDQT_ECUDA (-3)
+#define MDQT_ENOMEM (-4)
+#define MDQT_ESTATE (-5)
+
+#define MDQT_SCHEME_NONE 0 /* MD only: no wavefunctions (MD family) */
+#define MDQT_SCHEME_SR7 7  /* 7-level 408 nm pump, MC408L / MC408Q / FZ408L */
+#define MDQT_SCHEME_SR12 12 /* 12-level Sr+ S1/2,P3/2,D5/2 laser cooling, SU / MG */
+
+typedef struct mdqt_handle mdqt_handle;
+
+typedef struct mdqt_params {
+  int32_t struct_bytes; /* = sizeof(mdqt_params): ABI check */
+  int32_t scheme;       /* MDQT_SCHEME_* */
+  int32_t n_ions;       /* N: ions per trajectory (SU:129) */
+  int32_t n_traj;       /* trajectories batched in this handle (ensemble shard; SLURM --array replacement). >= 1 */
+  int32_t traj0;        /* global index of the first trajectory (the reference's `job`): selects the RNG stream */
+  int32_t row0, n_rows; /* large-N row decomposition: this handle owns ions [row0,row0+n_rows); n_rows = 0 -> all */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t substeps_per_md; /* plasmaToQuantumTimestepRatio (SU:83) */
+  int32_t renormalize;  /* reNormalizewvFns (SU:74) */
+  int32_t quad;         /* 7-level only: circular-pump coupling mask of MC408Q:596 */
+  int32_t reserved;
+  double L;             /* box length (SU:297, MD:73) */
+  double kappa;         /* 1/lDeb = sqrt(3 Ge) (SU:295) or kappa (MD:67) */
+  double rcut;          /* L/2 (SU:195, MD:74) */
+  double dtq;           /* quantumTimestep (SU:84) */
+  double detuning, detuningDP, Om, OmDP; /* SU:70-73 */
+  double dR, kRat;      /* decayRatioD5Halves, kRat (SU:146-147) */
+  double vKick, vKickDP;/* SU:148-149 */
+  double g2E, pv2qv;    /* gamToEinsteinFreq, plasVelToQuantVel (SU:79, 85) */
+  double fracOfSig, Te, sig0, density; /* expansion detuning (SU:447) */
+  uint64_t seed;        /* Philox key; the reference seeds drand48 from time(NULL)+job (SU:1219) */
+} mdqt_params;
+
+typedef struct mdqt_diag {   /* what output() prints to energies.dat (SU:934-955) */
+  double t, ekin_x, ekin_y, ekin_z, epot, vx_avg;
+} mdqt_diag;
+
+/* Fill `p` with the SU-family derived constants exactly as the reference evaluates them (SU:79-85, 146-149,
+ * 295-297) for the user inputs Ge, density, sig0, Te, fracOfSig, detuning, detuningDP, Om, OmDP and N0. */
+int mdqt_params_su(mdqt_params* p, double Ge, double density, double sig0, double Te, double fracOfSig,
+                   double detuning, double detuningDP, double Om, double OmDP, int N0, int n_ions);
+/* MD-family constants (MD:66-74, 88; MC408L:79-122): kappa, Gamma-independent box for n_ions, pump parameters. */
+int mdqt_params_md(mdqt_params* p, int scheme, int n_ions, double kappa, double density, double timeStep,
+                   double detuning, double Om, int quad);
+
+int mdqt_device_count(void);
+const char* mdqt_last_error(void);
+const char* mdqt_version(void);
+
+int mdqt_create(const mdqt_params* p, mdqt_handle** out);
+int mdqt_destroy(mdqt_handle* h);
+int mdqt_sync(mdqt_handle* h);
+
+/* Upload / download the reference's global state. Any pointer may be NULL (that array is skipped).
+ * `ld` is the leading dimension of the host R/V/F arrays (the reference's N0+1000, SU:126). */
+int mdqt_upload_state(mdqt_handle* h, const double* R, const double* V, const double* psi, const double* tPart, int ld);
+int mdqt_download_state(mdqt_handle* h, double* R, double* V, double* psi, double* tPart, int ld);
+int mdqt_upload_forces(mdqt_handle* h, const double* F, int ld);
+int mdqt_download_forces(mdqt_handle* h, double* F, int ld);
+int mdqt_set_time(mdqt_handle* h, double t, uint64_t substep_index); /* global t (SU:114) and RNG substep counter */
+int mdqt_get_time(mdqt_handle* h, double* t, uint64_t* substep_index);
+
+/* forces() (SU:192-236) / calculateAccelerations() (MD:387-448): all-pairs minimum-image Yukawa, r < L/2. */
+int mdqt_forces(mdqt_handle* h);
+/* nsub x { step(); qstep(); } (SU:1376-1377) with F held fixed, fused per ion. */
+int mdqt_substeps(mdqt_handle* h, int nsub);
+/* nsteps x { forces(); substeps_per_md x { step(); qstep(); } } -- the body of the main loop (SU:1369-1378). */
+int mdqt_md_steps(mdqt_handle* h, int nsteps);
+/* Same as mdqt_md_steps but through HOST buffers: upload state, run, download state (the end-to-end call). */
+int mdqt_md_steps_host(mdqt_handle* h, int nsteps, double* R, double* V, double* psi, double* tPart, int ld);
+/* Epotential() (SU:244-281): sum_{i<j} exp(-kappa r)/r / N. */
+int mdqt_epot(mdqt_handle* h, double* epot);
+/* output() observables (SU:934-1023). pvel = double [3][2001] (X,Y,Z) on the reference's bins i*0.0025;
+ * pops = double [n_ions][3] (S,P,D). For n_traj > 1 results are per trajectory, leading [n_traj]. */
+int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out);
+int mdqt_vel_dist(mdqt_handle* h, double* pvel);
+int mdqt_populations(mdqt_handle* h, double* pops);
+
+/* MD family: MDStep() (MD:504-511) = stepPositions, calculateAccelerations, stepVelocities with Andersen
+ * collisions (probability dt*collisionFreq, velocities ~ N(0, sigma_v^2)) and the optional laser friction term
+ * (laser: 0 none, 1 three-axis MD:494-496, 2 x only MD:491; coefficient = 1.234e-6*beta/sqrt(n)). */
+int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff);
+/* 7-level pump sweeps without kick (MC408L:1227-1232 inner loop): nsub x qstep() at frozen velocities. */
+int mdqt_qsteps(mdqt_handle* h, int nsub);
+
+/* Test hook: replace the Philox stream by caller-supplied uniforms u[nsub][n_ions][5] (rand, rand2, randDOrS,
+ * randDir, rand3) for the next substeps/qsteps calls (n_traj must be 1). NULL restores Philox. */
+int mdqt_set_forced_uniforms(mdqt_handle* h, const double* u, int nsub);
+/* Test hook for the MD-family Andersen thermostat: per-ion collision uniforms u[n_ions] and the velocities
+ * v[n_ions][3] assigned on collision, instead of the Philox/Box-Muller draws. NULL restores Philox. */
+int mdqt_set_forced_collisions(mdqt_handle* h, const double* u, const double* v);
+/* The five Philox uniforms ion `ion` of trajectory `traj` consumes at substep `substep` (host-side replica). */
+int mdqt_philox_uniforms(uint64_t seed, uint32_t traj, uint32_t ion, uint64_t substep, double u[5]);
+
+/* Multi-GPU plumbing (row decomposition): raw device pointers so that the caller's NCCL all-gather can write
+ * remote rows of R in place. which: 0 = R, 1 = V, 2 = F. Layout on device: double [n_traj][3][mdqt_device_ld]. */
+void* mdqt_device_ptr(mdqt_handle* h, int which);
+int mdqt_device_ld(mdqt_handle* h);
+void* mdqt_stream(mdqt_handle* h);
+
+/* After an external write into the device R buffer (NCCL all-gather): tell the handle whether all coordinates
+ * lie in [0,L] (1: exact single-shift minimum image; 0: general rint path). */
+int mdqt_mark_wrapped(mdqt_handle* h, int wrapped);
+/* The j-range decomposition of the force kernel (a function of n_ions and n_traj only). */
+int mdqt_force_plan(mdqt_handle* h, int* nsplit, int* jlen);
+
+/* Per-kernel device timing of the most recent mdqt_md_steps call (ms, averaged per launch), measured with CUDA
+ * events on the handle's stream when profiling is enabled. which: 0 = force kernel, 1 = substep kernel. */
+int mdqt_enable_timing(mdqt_handle* h, int on);
+int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* launches);
+/* FP64 FMA-chain microbenchmark on the handle's device: returns achieved TFLOP/s (2 flop per DFMA). */
+int mdqt_fp64_peak(mdqt_handle* h, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,559 @@
+// mdqt_capi.cu -- the C ABI declared in include/mdqt.h: handle management, state marshalling between the
+// reference's host layouts (double R[3][ld], cx_mat wvFns[], SU:126-152) and the device SoA layout, and the
+// stream-ordered sequencing of the hot-path kernels (the body of the reference's main loop, SU:1369-1378).
+// There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
+#include "../../include/mdqt.h"
+#include "mdqt_internal.h"
+#include "mdqt_qtconsts.h"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace mdqt;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return fail(MDQT_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                           \
+  } while (0)
+
+struct mdqt_handle {
+  mdqt_params p;
+  int N, B, S, ld, row0, nrows;
+  cudaStream_t stream;
+  double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops;
+  unsigned* counters;
+  double* forced_u; int forced_nsub, forced_cursor;
+  double *forced_cu, *forced_cn;
+  QTConsts qc;
+  double t; uint64_t substep, vv_step;
+  int wrapped, nsplit, jlen, itiles, ipt;
+  bool timing;
+  std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
+  size_t ev_used;
+  double time_ms[2]; int time_n[2];
+};
+
+static size_t state_elems(const mdqt_handle* h) { return (size_t)h->B * 3 * h->ld; }
+
+extern "C" {
+
+const char* mdqt_last_error(void) { return g_err.c_str(); }
+const char* mdqt_version(void) { return "mdqt_b200 0.1 (sm_100a)"; }
+
+int mdqt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mdqt_params_su(mdqt_params* p, double Ge, double density, double sig0, double Te, double fracOfSig, double detuning,
+                   double detuningDP, double Om, double OmDP, int N0, int n_ions) {
+  if (!p) return fail(MDQT_EINVAL, "null params");
+  memset(p, 0, sizeof(*p));
+  p->struct_bytes = (int32_t)sizeof(*p);
+  p->scheme = MDQT_SCHEME_SR12;
+  p->n_ions = n_ions; p->n_traj = 1; p->traj0 = 1; p->row0 = 0; p->n_rows = 0; p->device = 0;
+  p->substeps_per_md = (int)ceil(34.81 / sqrt(density));          // SU:83
+  p->L = pow(N0 * 4. * M_PI / 3., 0.333333333);                   // SU:297 (literal exponent)
+  p->kappa = 1.0 / (1. / sqrt(3. * Ge));                          // 1/lDeb, SU:295
+  p->rcut = p->L / 2.;                                            // SU:195
+  p->dtq = 0.002 / p->substeps_per_md;                            // SU:80, 84
+  p->detuning = detuning; p->detuningDP = detuningDP; p->Om = Om; p->OmDP = OmDP;
+  p->dR = 0.0617; p->kRat = 0.395;                                // SU:146-147
+  p->g2E = 174.07 / sqrt(density);                                // SU:79
+  p->pv2qv = 1.1821 * pow(density, 1. / 6);                       // SU:85
+  p->vKick = 0.001208 / p->pv2qv;                                 // SU:148
+  p->vKickDP = p->vKick * p->kRat;                                // SU:149
+  p->fracOfSig = fracOfSig; p->Te = Te; p->sig0 = sig0; p->density = density;
+  p->seed = 12345;
+  return MDQT_OK;
+}
+
+int mdqt_params_md(mdqt_params* p, int scheme, int n_ions, double kappa, double density, double timeStep, double detuning,
+                   double Om, int quad) {
+  if (!p) return fail(MDQT_EINVAL, "null params");
+  memset(p, 0, sizeof(*p));
+  p->struct_bytes = (int32_t)sizeof(*p);
+  p->scheme = scheme;
+  p->n_ions = n_ions; p->n_traj = 1; p->traj0 = 1; p->device = 0;
+  p->L = pow(n_ions * 4. * M_PI / 3., 1. / 3);                    // MD:73
+  p->kappa = kappa; p->rcut = p->L / 2.;                          // MD:67, 74
+  p->substeps_per_md = (int)round(87 / sqrt(density));            // MC408L:116
+  p->dtq = timeStep / p->substeps_per_md;                         // MC408L:117
+  p->detuning = detuning; p->Om = Om; p->quad = quad;
+  p->dR = 0.0617;                                                 // MC408L:121
+  p->g2E = 174.07 / sqrt(density);                                // MC408L:115
+  p->pv2qv = 1.1821 * pow(density, 1. / 6);                       // MC408L:118
+  p->vKick = 0.001208 / p->pv2qv;                                 // MC408L:122
+  p->density = density; p->sig0 = 1.0;
+  p->seed = 12345;
+  return MDQT_OK;
+}
+
+// j-range decomposition: a function of (N, B) only, so that every rank of a row-decomposed run sums the same
+// j-chunks in the same order (bitwise identical forces for any GPU count).
+static void plan_force(mdqt_handle* h) {
+  const int N = h->N, B = h->B;
+  const bool big = (long long)N * B >= 148LL * 4 * kForceThreads * 2;
+  const int ipt = big ? 2 : 1;
+  const long long tiles = ((long long)N + kForceThreads * ipt - 1) / (kForceThreads * ipt) * B;
+  const long long slots = 148LL * (big ? 5 : 8);
+  double best = 1e300; int best_ns = 1, best_jlen = N;
+  for (int ns = 1; ns <= 64; ns++) {
+    int jlen = ((N + ns - 1) / ns + 7) & ~7;
+    int real_ns = (N + jlen - 1) / jlen;
+    long long ctas = tiles * real_ns;
+    long long waves = (ctas + slots - 1) / slots;
+    double cost = (double)waves * (jlen + 48 + 2 * real_ns);
+    if (cost < best * 0.999) { best = cost; best_ns = real_ns; best_jlen = jlen; }
+  }
+  h->nsplit = best_ns; h->jlen = best_jlen; h->ipt = ipt;
+  h->itiles = (h->nrows + kForceThreads - 1) / kForceThreads;  // upper bound on i-tiles of this handle
+}
+
+int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
+  if (!p || !out) return fail(MDQT_EINVAL, "null argument");
+  *out = nullptr;
+  if (p->struct_bytes != (int32_t)sizeof(mdqt_params)) return fail(MDQT_EINVAL, "mdqt_params size mismatch (ABI)");
+  if (p->scheme != MDQT_SCHEME_NONE && p->scheme != MDQT_SCHEME_SR7 && p->scheme != MDQT_SCHEME_SR12)
+    return fail(MDQT_EINVAL, "unknown level scheme");
+  if (p->n_ions < 1 || p->n_traj < 1) return fail(MDQT_EINVAL, "n_ions and n_traj must be >= 1");
+  if (!(p->L > 0) || !(p->rcut > 0) || !(p->kappa >= 0)) return fail(MDQT_EINVAL, "L, rcut must be > 0 and kappa >= 0");
+  if (p->kappa * p->rcut > 700.0) return fail(MDQT_EINVAL, "kappa*rcut too large for the fp64 exp range");
+  if (p->rcut > p->L / 2. * (1 + 1e-12)) return fail(MDQT_EINVAL, "rcut must not exceed L/2 (minimum image)");
+  int row0 = p->row0, nrows = p->n_rows == 0 ? p->n_ions : p->n_rows;
+  if (row0 < 0 || nrows < 1 || row0 + nrows > p->n_ions) return fail(MDQT_EINVAL, "row range outside [0,n_ions)");
+  if (p->scheme != MDQT_SCHEME_NONE && !(p->dtq > 0)) return fail(MDQT_EINVAL, "dtq must be > 0");
+  int ndev = mdqt_device_count();
+  if (ndev <= 0) return fail(MDQT_ENODEVICE, "no CUDA device: libmdqt_b200 has no CPU fallback");
+  if (p->device < 0 || p->device >= ndev) return fail(MDQT_EINVAL, "device ordinal out of range");
+  CU(cudaSetDevice(p->device));
+
+  mdqt_handle* h = new (std::nothrow) mdqt_handle();
+  if (!h) return fail(MDQT_ENOMEM, "host allocation failed");
+  h->p = *p;
+  h->N = p->n_ions; h->B = p->n_traj; h->S = p->scheme; h->row0 = row0; h->nrows = nrows;
+  h->ld = (p->n_ions + 31) & ~31;
+  h->t = 0.0; h->substep = 0; h->vv_step = 0; h->wrapped = 0;
+  h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
+  h->timing = false; h->ev_used = 0; h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
+  plan_force(h);
+  if (h->S) fill_qt_consts(h->qc, h->S, p->Om, p->OmDP, p->dR, p->vKick, p->vKickDP, p->dtq, p->g2E, p->quad);
+  upload_exp_table();
+
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  size_t ne = state_elems(h);
+  auto alloc = [&](double** ptr, size_t n) {
+    if (e == cudaSuccess) { e = cudaMalloc((void**)ptr, std::max<size_t>(n, 1) * sizeof(double)); if (e == cudaSuccess) e = cudaMemset(*ptr, 0, std::max<size_t>(n, 1) * sizeof(double)); }
+  };
+  alloc(&h->R, ne); alloc(&h->V, ne); alloc(&h->F, ne); alloc(&h->oldF, ne);
+  alloc(&h->psi, (size_t)h->B * 2 * h->S * h->ld);
+  alloc(&h->psi_stage, (size_t)h->B * 2 * h->S * h->N);
+  alloc(&h->tPart, (size_t)h->B * h->ld);
+  alloc(&h->Fpart, h->nsplit > 1 ? (size_t)h->nsplit * ne : 1);
+  alloc(&h->epot_partials, (size_t)h->itiles * h->nsplit * h->B);
+  alloc(&h->scalars, (size_t)h->B * 16);
+  alloc(&h->pvel, (size_t)h->B * 3 * kVelBins);
+  alloc(&h->pops, (size_t)h->B * h->N * 3);
+  if (e == cudaSuccess) {
+    e = cudaMalloc((void**)&h->counters, sizeof(unsigned) * (size_t)h->B * h->itiles);
+    if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(unsigned) * (size_t)h->B * h->itiles);
+  }
+  if (e != cudaSuccess) {
+    std::string m = std::string("device allocation failed: ") + cudaGetErrorString(e);
+    mdqt_destroy(h);
+    return fail(e == cudaErrorMemoryAllocation ? MDQT_ENOMEM : MDQT_ECUDA, m);
+  }
+  *out = h;
+  return MDQT_OK;
+}
+
+int mdqt_destroy(mdqt_handle* h) {
+  if (!h) return MDQT_OK;
+  cudaSetDevice(h->p.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  double* bufs[] = {h->R, h->V, h->F, h->oldF, h->psi, h->psi_stage, h->tPart, h->Fpart, h->epot_partials, h->scalars,
+                    h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn};
+  for (double* b : bufs) if (b) cudaFree(b);
+  if (h->counters) cudaFree(h->counters);
+  for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MDQT_OK;
+}
+
+int mdqt_sync(mdqt_handle* h) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+// [B][3][ld_host] host <-> [B][3][ld] device, N valid columns
+static cudaError_t copy_state(mdqt_handle* h, double* dev, const double* host_in, double* host_out, int ld_host) {
+  const int rows = h->B * 3;
+  if (host_in)
+    return cudaMemcpy2DAsync(dev, (size_t)h->ld * 8, host_in, (size_t)ld_host * 8, (size_t)h->N * 8, rows, cudaMemcpyHostToDevice, h->stream);
+  return cudaMemcpy2DAsync(host_out, (size_t)ld_host * 8, dev, (size_t)h->ld * 8, (size_t)h->N * 8, rows, cudaMemcpyDeviceToHost, h->stream);
+}
+
+int mdqt_upload_state(mdqt_handle* h, const double* R, const double* V, const double* psi, const double* tPart, int ld) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
+  CU(cudaSetDevice(h->p.device));
+  if (R) {
+    // coordinates inside [0,L] allow the exact single-shift minimum image; anything else takes the general path
+    int wrapped = 1;
+    for (int r = 0; r < h->B * 3 && wrapped; r++) {
+      const double* row = R + (size_t)r * ld;
+      for (int i = 0; i < h->N; i++) if (!(row[i] >= 0.0 && row[i] <= h->p.L)) { wrapped = 0; break; }
+    }
+    h->wrapped = wrapped;
+    CU(copy_state(h, h->R, R, nullptr, ld));
+  }
+  if (V) CU(copy_state(h, h->V, V, nullptr, ld));
+  if (psi) {
+    if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
+    CU(cudaMemcpyAsync(h->psi_stage, psi, (size_t)h->B * h->N * 2 * h->S * 8, cudaMemcpyHostToDevice, h->stream));
+    launch_transpose_psi_in(h->psi_stage, h->psi, h->S, h->N, h->ld, h->B, h->stream);
+  }
+  if (tPart)
+    CU(cudaMemcpy2DAsync(h->tPart, (size_t)h->ld * 8, tPart, (size_t)h->N * 8, (size_t)h->N * 8, h->B, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));  // host buffers are caller-owned: do not hold on to them
+  return MDQT_OK;
+}
+
+int mdqt_download_state(mdqt_handle* h, double* R, double* V, double* psi, double* tPart, int ld) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
+  CU(cudaSetDevice(h->p.device));
+  if (R) CU(copy_state(h, h->R, nullptr, R, ld));
+  if (V) CU(copy_state(h, h->V, nullptr, V, ld));
+  if (psi) {
+    if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
+    launch_transpose_psi_out(h->psi, h->psi_stage, h->S, h->N, h->ld, h->B, h->stream);
+    CU(cudaMemcpyAsync(psi, h->psi_stage, (size_t)h->B * h->N * 2 * h->S * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (tPart)
+    CU(cudaMemcpy2DAsync(tPart, (size_t)h->N * 8, h->tPart, (size_t)h->ld * 8, (size_t)h->N * 8, h->B, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_upload_forces(mdqt_handle* h, const double* F, int ld) {
+  if (!h || !F) return fail(MDQT_EINVAL, "null argument");
+  if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
+  CU(cudaSetDevice(h->p.device));
+  CU(copy_state(h, h->F, F, nullptr, ld));
+  CU(cudaStreamSynchronize(h->stream));
+  return MDQT_OK;
+}
+int mdqt_download_forces(mdqt_handle* h, double* F, int ld) {
+  if (!h || !F) return fail(MDQT_EINVAL, "null argument");
+  if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
+  CU(cudaSetDevice(h->p.device));
+  CU(copy_state(h, h->F, nullptr, F, ld));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_set_time(mdqt_handle* h, double t, uint64_t substep_index) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  h->t = t; h->substep = substep_index;
+  return MDQT_OK;
+}
+int mdqt_get_time(mdqt_handle* h, double* t, uint64_t* substep_index) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (t) *t = h->t;
+  if (substep_index) *substep_index = h->substep;
+  return MDQT_OK;
+}
+
+static ForceArgs force_args(mdqt_handle* h) {
+  ForceArgs a;
+  a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
+  a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
+  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.wrapped = h->wrapped;
+  a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
+  return a;
+}
+
+static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step) {
+  QTArgs a;
+  const mdqt_params& p = h->p;
+  a.R = h->R; a.V = h->V; a.F = h->F; a.psi = h->psi; a.tPart = h->tPart;
+  a.forced_u = h->forced_u ? h->forced_u + (size_t)h->forced_cursor * h->N * 5 : nullptr;
+  a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = p.traj0;
+  a.nsub = nsub; a.do_step = do_step; a.renorm = p.renormalize; a.quad = p.quad;
+  a.t0 = h->t; a.substep0 = h->substep; a.seed = p.seed;
+  a.L = p.L; a.dtq = p.dtq;
+  a.detuning = p.detuning; a.detuningDP = p.detuningDP; a.Om = p.Om; a.OmDP = p.OmDP; a.dR = p.dR; a.kRat = p.kRat;
+  a.vKick = p.vKick; a.vKickDP = p.vKickDP; a.g2E = p.g2E; a.pv2qv = p.pv2qv;
+  a.fracOfSig = p.fracOfSig; a.Te = p.Te; a.sig0 = p.sig0; a.density = p.density;
+  return a;
+}
+
+static cudaEvent_t next_event(mdqt_handle* h) {
+  if (h->ev_used == h->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev.push_back(e);
+  }
+  return h->ev[h->ev_used++];
+}
+
+static int enqueue_substeps(mdqt_handle* h, int nsub, int do_step) {
+  if (h->forced_u && h->forced_cursor + nsub > h->forced_nsub) return fail(MDQT_ESTATE, "forced uniforms exhausted");
+  QTArgs a = qt_args(h, nsub, do_step);
+  launch_substeps(a, h->qc, h->S, h->stream);
+  if (h->forced_u) h->forced_cursor += nsub;
+  h->substep += (uint64_t)nsub;
+  if (do_step)
+    for (int s = 0; s < nsub; s++) h->t += h->p.dtq;  // the same repeated addition as SU:716 / the kernel
+  return MDQT_OK;
+}
+
+int mdqt_forces(mdqt_handle* h) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  launch_forces(force_args(h), h->stream);
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_substeps(mdqt_handle* h, int nsub) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (h->S != MDQT_SCHEME_SR12) return fail(MDQT_ESTATE, "mdqt_substeps needs the 12-level scheme");
+  if (nsub < 0) return fail(MDQT_EINVAL, "nsub < 0");
+  if (nsub == 0) return MDQT_OK;
+  CU(cudaSetDevice(h->p.device));
+  int rc = enqueue_substeps(h, nsub, 1);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_qsteps(mdqt_handle* h, int nsub) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (h->S != MDQT_SCHEME_SR7) return fail(MDQT_ESTATE, "mdqt_qsteps needs the 7-level scheme");
+  if (nsub < 0) return fail(MDQT_EINVAL, "nsub < 0");
+  if (nsub == 0) return MDQT_OK;
+  CU(cudaSetDevice(h->p.device));
+  int rc = enqueue_substeps(h, nsub, 0);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_md_steps(mdqt_handle* h, int nsteps) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (h->S != MDQT_SCHEME_SR12) return fail(MDQT_ESTATE, "mdqt_md_steps needs the 12-level scheme");
+  if (h->p.substeps_per_md < 1) return fail(MDQT_EINVAL, "substeps_per_md < 1");
+  CU(cudaSetDevice(h->p.device));
+  if (h->timing) h->ev_used = 0;
+  for (int k = 0; k < nsteps; k++) {
+    if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
+    launch_forces(force_args(h), h->stream);
+    if (h->timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
+    int rc = enqueue_substeps(h, h->p.substeps_per_md, 1);
+    if (rc) return rc;
+    if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
+  }
+  CU(cudaGetLastError());
+  if (h->timing) {
+    CU(cudaStreamSynchronize(h->stream));
+    h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
+    for (size_t k = 0; k + 3 < h->ev_used; k += 4) {
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, h->ev[k], h->ev[k + 1]);
+      cudaEventElapsedTime(&b, h->ev[k + 2], h->ev[k + 3]);
+      h->time_ms[0] += a; h->time_ms[1] += b; h->time_n[0]++; h->time_n[1]++;
+    }
+  }
+  return MDQT_OK;
+}
+
+int mdqt_md_steps_host(mdqt_handle* h, int nsteps, double* R, double* V, double* psi, double* tPart, int ld) {
+  if (!h || !R || !V || !psi || !tPart) return fail(MDQT_EINVAL, "null argument");
+  int rc = mdqt_upload_state(h, R, V, psi, tPart, ld);
+  if (rc) return rc;
+  rc = mdqt_md_steps(h, nsteps);
+  if (rc) return rc;
+  return mdqt_download_state(h, R, V, psi, tPart, ld);
+}
+
+int mdqt_epot(mdqt_handle* h, double* epot) {
+  if (!h || !epot) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);
+  CU(cudaMemcpyAsync(epot, h->scalars + (size_t)h->B * 8, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
+  if (!h || !out) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
+  launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);
+  std::vector<double> s((size_t)h->B * 16);
+  CU(cudaMemcpyAsync(s.data(), h->scalars, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  for (int b = 0; b < h->B; b++) {
+    out[b].t = h->t; out[b].vx_avg = s[b * 8]; out[b].ekin_x = s[b * 8 + 1]; out[b].ekin_y = s[b * 8 + 2];
+    out[b].ekin_z = s[b * 8 + 3]; out[b].epot = s[(size_t)h->B * 8 + b];
+  }
+  return MDQT_OK;
+}
+
+int mdqt_vel_dist(mdqt_handle* h, double* pvel) {
+  if (!h || !pvel) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
+  launch_vel_dist(h->V, h->scalars, h->N, h->ld, h->B, h->pvel, h->stream);
+  CU(cudaMemcpyAsync(pvel, h->pvel, (size_t)h->B * 3 * kVelBins * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_populations(mdqt_handle* h, double* pops) {
+  if (!h || !pops) return fail(MDQT_EINVAL, "null argument");
+  if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
+  CU(cudaSetDevice(h->p.device));
+  launch_populations(h->psi, h->S, h->N, h->ld, h->B, h->pops, h->stream);
+  CU(cudaMemcpyAsync(pops, h->pops, (size_t)h->B * h->N * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!(dt > 0)) return fail(MDQT_EINVAL, "dt must be > 0");
+  CU(cudaSetDevice(h->p.device));
+  std::swap(h->F, h->oldF);  // oldA = A (MD:505-506)
+  VVArgs a;
+  a.R = h->R; a.V = h->V; a.A = h->oldF; a.oldA = h->oldF;
+  a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = h->p.traj0;
+  a.L = h->p.L; a.dt = dt; a.collisionFreq = collisionFreq; a.sigma_v = sigma_v; a.laser_coeff = laser_coeff; a.laser = laser;
+  a.step = h->vv_step; a.seed = h->p.seed; a.forced_u = h->forced_cu; a.forced_n = h->forced_cn;
+  launch_vv_positions(a, h->stream);    // stepPositions (MD:507)
+  launch_forces(force_args(h), h->stream);  // calculateAccelerations (MD:508)
+  a.A = h->F;
+  launch_vv_velocities(a, h->stream);   // stepVelocities (MD:509)
+  h->vv_step++;
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_set_forced_uniforms(mdqt_handle* h, const double* u, int nsub) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->forced_u) { cudaFree(h->forced_u); h->forced_u = nullptr; }
+  h->forced_nsub = 0; h->forced_cursor = 0;
+  if (!u) return MDQT_OK;
+  if (h->B != 1) return fail(MDQT_ESTATE, "forced uniforms need n_traj == 1");
+  if (nsub < 1) return fail(MDQT_EINVAL, "nsub < 1");
+  size_t n = (size_t)nsub * h->N * 5;
+  CU(cudaMalloc((void**)&h->forced_u, n * 8));
+  CU(cudaMemcpy(h->forced_u, u, n * 8, cudaMemcpyHostToDevice));
+  h->forced_nsub = nsub;
+  return MDQT_OK;
+}
+
+int mdqt_set_forced_collisions(mdqt_handle* h, const double* u, const double* v) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->forced_cu) { cudaFree(h->forced_cu); h->forced_cu = nullptr; }
+  if (h->forced_cn) { cudaFree(h->forced_cn); h->forced_cn = nullptr; }
+  if (!u || !v) return MDQT_OK;
+  if (h->B != 1) return fail(MDQT_ESTATE, "forced collisions need n_traj == 1");
+  CU(cudaMalloc((void**)&h->forced_cu, (size_t)h->N * 8));
+  CU(cudaMalloc((void**)&h->forced_cn, (size_t)h->N * 24));
+  CU(cudaMemcpy(h->forced_cu, u, (size_t)h->N * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->forced_cn, v, (size_t)h->N * 24, cudaMemcpyHostToDevice));
+  return MDQT_OK;
+}
+
+// host replica of the device stream (same integer arithmetic): lets callers feed the oracle the very uniforms
+// the kernel consumes
+static void philox_host(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+static double u52_host(uint32_t hi, uint32_t lo) {
+  uint64_t k = ((uint64_t)hi << 20) | (uint64_t)(lo >> 12);
+  return ((double)k + 0.5) * 2.220446049250313080847263336181640625e-16;
+}
+int mdqt_philox_uniforms(uint64_t seed, uint32_t traj, uint32_t ion, uint64_t substep, double u[5]) {
+  if (!u) return fail(MDQT_EINVAL, "null argument");
+  for (uint32_t call = 0; call < 3; call++) {
+    uint32_t c[4] = {(uint32_t)substep, (uint32_t)(substep >> 32), ion, (traj << 3) | call};
+    philox_host(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u[2 * call] = u52_host(c[0], c[1]);
+    if (call < 2) u[2 * call + 1] = u52_host(c[2], c[3]);
+  }
+  return MDQT_OK;
+}
+
+void* mdqt_device_ptr(mdqt_handle* h, int which) {
+  if (!h) return nullptr;
+  return which == 0 ? (void*)h->R : which == 1 ? (void*)h->V : which == 2 ? (void*)h->F : nullptr;
+}
+int mdqt_device_ld(mdqt_handle* h) { return h ? h->ld : 0; }
+void* mdqt_stream(mdqt_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mdqt_mark_wrapped(mdqt_handle* h, int wrapped) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  h->wrapped = wrapped ? 1 : 0;
+  return MDQT_OK;
+}
+
+int mdqt_force_plan(mdqt_handle* h, int* nsplit, int* jlen) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (nsplit) *nsplit = h->nsplit;
+  if (jlen) *jlen = h->jlen;
+  return MDQT_OK;
+}
+
+int mdqt_enable_timing(mdqt_handle* h, int on) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  h->timing = on != 0;
+  return MDQT_OK;
+}
+int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* launches) {
+  if (!h || which < 0 || which > 1) return fail(MDQT_EINVAL, "bad argument");
+  if (ms_per_launch) *ms_per_launch = h->time_n[which] ? h->time_ms[which] / h->time_n[which] : 0.0;
+  if (launches) *launches = h->time_n[which];
+  return MDQT_OK;
+}
+
+int mdqt_fp64_peak(mdqt_handle* h, double* tflops) {
+  if (!h || !tflops) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  double v = run_fp64_peak(h->stream);
+  if (v <= 0) return fail(MDQT_ECUDA, "fp64 peak probe failed");
+  *tflops = v;
+  return MDQT_OK;
+}
+
+}  // extern "C"

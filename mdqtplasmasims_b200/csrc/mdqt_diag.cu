@@ -1,0 +1,131 @@
+// mdqt_diag.cu -- K4: the observables of output() (reference laserCoolingPlusExpansionMDQTSpeedUp.cpp:917-1032)
+// computed on the device, and the AoS <-> SoA wavefunction marshalling used at the C-ABI boundary.
+//   <v_x>, E_kin,x (about <v_x>), E_kin,y, E_kin,z            SU:934-947
+//   symmetrised Gaussian KDE of the velocity distribution      SU:958-979  (2001 bins of 0.0025, width 0.002)
+//   S/P/D populations per ion                                  SU:1016-1023
+// All reductions run in a fixed order (thread-strided partial sums + tree), so results are reproducible.
+#include "mdqt_internal.h"
+#include <math.h>
+
+namespace mdqt {
+
+__device__ __forceinline__ double block_sum_1024(double v, double* sred) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((tid & 31) == 0) sred[tid >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+  if (tid < 32) {
+    tot = (tid < (int)(blockDim.x >> 5)) ? sred[tid] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+  }
+  __syncthreads();
+  if (tid == 0) sred[0] = tot;
+  __syncthreads();
+  return sred[0];
+}
+
+// one CTA per trajectory; out[b][0..3] = vx_avg, ekin_x, ekin_y, ekin_z
+__global__ void __launch_bounds__(1024) k_diag(const double* __restrict__ V, int N, int ld, double* __restrict__ out) {
+  __shared__ double sred[32];
+  const int b = blockIdx.x;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const double* vy = vx + ld;
+  const double* vz = vy + ld;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += vx[i];
+  const double avg = block_sum_1024(s, sred) / (double)N;
+  double ex = 0.0, ey = 0.0, ez = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double d = vx[i] - avg;
+    ex += 0.5 * (d * d); ey += 0.5 * (vy[i] * vy[i]); ez += 0.5 * (vz[i] * vz[i]);
+  }
+  ex = block_sum_1024(ex, sred);
+  ey = block_sum_1024(ey, sred);
+  ez = block_sum_1024(ez, sred);
+  if (threadIdx.x == 0) {
+    out[b * 8 + 0] = avg; out[b * 8 + 1] = ex / (double)N; out[b * 8 + 2] = ey / (double)N; out[b * 8 + 3] = ez / (double)N;
+  }
+}
+
+void launch_diag(const double* V, int N, int ld, int B, double*, double* diag_out, cudaStream_t s) {
+  k_diag<<<B, 1024, 0, s>>>(V, N, ld, diag_out);
+}
+
+// grid: (ceil(2001/8), 3, B); 256 threads = 8 bins x 32 lanes; lanes stride over ions
+__global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, const double* __restrict__ diag, int N, int ld,
+                                                  double* __restrict__ pvel) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int bin = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const double* v = V + ((size_t)b * 3 + c) * ld;
+  const double avg = (c == 0) ? diag[b * 8] : 0.0;
+  const double V2 = 1. / (2. * 0.002 * 0.002);
+  const double vb = (double)bin * 0.0025;
+  double s = 0.0;
+  if (bin < kVelBins)
+    for (int i = lane; i < N; i += 32) {
+      double d = v[i] - avg;
+      double a = vb - d, e = vb + d;
+      s += exp(-V2 * a * a) + exp(-V2 * e * e);
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0 && bin < kVelBins) pvel[((size_t)b * 3 + c) * kVelBins + bin] = s / (6.0 * sqrt(2 * M_PI * 0.002 * 0.002));
+}
+
+void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s) {
+  dim3 grid((kVelBins + 7) / 8, 3, B);
+  k_vel_dist<<<grid, 256, 0, s>>>(V, diag_out, N, ld, pvel);
+}
+
+// pops[b][i][3] = popS, popP, popD with the reference's state grouping (S: 0,1; P: 2..5; D: 6..S-1)
+__global__ void k_populations(const double* __restrict__ psi, int S, int N, int ld, double* __restrict__ pops) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* p = psi + (size_t)b * 2 * S * ld;
+  double pop[3] = {0.0, 0.0, 0.0};
+  for (int k = 0; k < S; k++) {
+    double re = p[(size_t)(2 * k) * ld + i], im = p[(size_t)(2 * k + 1) * ld + i];
+    pop[k < 2 ? 0 : (k < 6 ? 1 : 2)] += re * re + im * im;
+  }
+  double* o = pops + ((size_t)b * N + i) * 3;
+  o[0] = pop[0]; o[1] = pop[1]; o[2] = pop[2];
+}
+
+void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s) {
+  dim3 grid((N + 255) / 256, B);
+  k_populations<<<grid, 256, 0, s>>>(psi, S, N, ld, pops);
+}
+
+// psi_aos[b][i][k][2]  <->  psi_soa[b][2k+c][ld]
+__global__ void k_psi_in(const double* __restrict__ aos, double* __restrict__ soa, int S, int N, int ld) {
+  const int b = blockIdx.y;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)N * 2 * S) return;
+  const int i = (int)(g / (2 * S)), kc = (int)(g % (2 * S));
+  soa[((size_t)b * 2 * S + kc) * ld + i] = aos[(size_t)b * N * 2 * S + g];
+}
+__global__ void k_psi_out(const double* __restrict__ soa, double* __restrict__ aos, int S, int N, int ld) {
+  const int b = blockIdx.y;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)N * 2 * S) return;
+  const int i = (int)(g / (2 * S)), kc = (int)(g % (2 * S));
+  aos[(size_t)b * N * 2 * S + g] = soa[((size_t)b * 2 * S + kc) * ld + i];
+}
+void launch_transpose_psi_in(const double* psi_aos, double* psi_soa, int S, int N, int ld, int B, cudaStream_t s) {
+  long long n = (long long)N * 2 * S;
+  dim3 grid((unsigned)((n + 255) / 256), B);
+  k_psi_in<<<grid, 256, 0, s>>>(psi_aos, psi_soa, S, N, ld);
+}
+void launch_transpose_psi_out(const double* psi_soa, double* psi_aos, int S, int N, int ld, int B, cudaStream_t s) {
+  long long n = (long long)N * 2 * S;
+  dim3 grid((unsigned)((n + 255) / 256), B);
+  k_psi_out<<<grid, 256, 0, s>>>(psi_soa, psi_aos, S, N, ld);
+}
+
+}  // namespace mdqt

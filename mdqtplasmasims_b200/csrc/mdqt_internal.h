@@ -1,0 +1,66 @@
+// mdqt_internal.h -- shared declarations between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mdqt {
+
+constexpr int kForceThreads = 128;   // threads per CTA of the pair kernels
+constexpr int kExpTable = 128;       // entries of the 2^(j/128) table used by the fp64 exp
+constexpr int kVelBins = 2001;       // KDE bins of output() (SU:120-123)
+
+struct ForceArgs {
+  const double* R;   // [B][3][ld] all positions
+  double* F;         // [B][3][ld] result
+  double* Fpart;     // [nsplit][B][3][ld] partial sums when nsplit > 1
+  unsigned* counters;// [B][itiles] arrival counters (self-resetting)
+  int N, ld, B;
+  int row0, nrows;   // rows owned by this handle
+  int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
+  int ipt;           // ion rows per thread (1 or 2)
+  int wrapped;       // 1: all coordinates known to lie in [0,L] (single-shift minimum image is exact)
+  double L, halfL, invL, kappa, rc2;
+};
+
+struct QTArgs {
+  double* R; double* V; const double* F;  // [B][3][ld]
+  double* psi;                            // [B][2*S][ld] component-major: (2*k+{0,1})*ld + i
+  double* tPart;                          // [B][ld]
+  const double* forced_u;                 // [nsub][N][5] or null
+  int N, ld, B, row0, nrows, traj0;
+  int nsub;
+  int do_step;                            // 1: step()+qstep() with kick (SU); 0: qstep only, frozen V (MC408L)
+  int renorm, quad;
+  double t0; uint64_t substep0; uint64_t seed;
+  double L, dtq;
+  double detuning, detuningDP, Om, OmDP, dR, kRat, vKick, vKickDP, g2E, pv2qv;
+  double fracOfSig, Te, sig0, density;
+};
+
+struct VVArgs {
+  double* R; double* V; const double* A; const double* oldA;  // [B][3][ld]
+  int N, ld, B, row0, nrows, traj0;
+  double L, dt, collisionFreq, sigma_v, laser_coeff;
+  int laser;
+  uint64_t step; uint64_t seed;
+  const double* forced_u;   // [N] collision uniforms or null
+  const double* forced_n;   // [N][3] velocities assigned on collision or null
+};
+
+void launch_forces(const ForceArgs& a, cudaStream_t s);
+void launch_epot(const ForceArgs& a, double* block_partials, double* result, cudaStream_t s);  // result[B]
+int epot_partials_needed(const ForceArgs& a);
+struct QTConsts;
+void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s);
+void launch_vv_positions(const VVArgs& a, cudaStream_t s);
+void launch_vv_velocities(const VVArgs& a, cudaStream_t s);
+// diag_out[B][8]: vx_avg, ekin_x, ekin_y, ekin_z; pvel[B][3][2001]; pops[B][N][3]
+void launch_diag(const double* V, int N, int ld, int B, double* scratch, double* diag_out, cudaStream_t s);
+void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s);
+void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s);
+void launch_transpose_psi_in(const double* psi_aos, double* psi_soa, int S, int N, int ld, int B, cudaStream_t s);
+void launch_transpose_psi_out(const double* psi_soa, double* psi_aos, int S, int N, int ld, int B, cudaStream_t s);
+double run_fp64_peak(cudaStream_t s);
+void upload_exp_table();
+
+}  // namespace mdqt

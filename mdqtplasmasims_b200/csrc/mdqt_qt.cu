@@ -1,0 +1,434 @@
+// mdqt_qt.cu -- K2: the fused per-ion quantum-substep kernel (leap-frog position/velocity update + quantum-
+// trajectory step), and K5: the MD-family velocity-Verlet kernels. Hand-written for sm_100a, fp64.
+//
+// Replaces step() / step_R() / step_V() (reference laserCoolingPlusExpansionMDQTSpeedUp.cpp:356-430) and
+// qstep() (SU:438-717 with the operator tables of SU:1163-1215) -- and, as the 7-level instantiation, qstep()
+// of MonteCarloFollowedByQTTagging408Linear.cpp:555-756 (tables MC408L:1171-1190; Quad mask MC408Q:596) --
+// plus stepPositions()/stepVelocities() of MonteCarloFollowedByMDAndTempAnisotropy.cpp:452-502.
+//
+// Design. The reference builds dense 12x12 complex Armadillo matrices per ion per substep. The Hamiltonian is in
+// fact block diagonal: the sigma+/sigma- light fields (no pi light) only connect
+//     block A = { S-1/2, P+1/2, P-3/2, D+3/2, D-1/2, D-5/2 }   (0-indexed states 0,3,5,10,8,6)
+//     block B = { S+1/2, P+3/2, P-1/2, D+5/2, D+1/2, D-3/2 }   (0-indexed states 1,2,4,11,9,7)
+// and inside a block only 5 real couplings + 1 phase-rotating complex coupling are non-zero. The two blocks talk
+// to each other only through the renormalisation prefactor 1/sqrt(1-dp) (a sum of P populations) and through
+// quantum jumps. So each ion is advanced by a PAIR of adjacent lanes, one block (6 complex amplitudes, in
+// registers) per lane, exchanging one double per Runge-Kutta stage with __shfl_xor. All `nsub` substeps between
+// two force evaluations are fused in one launch (F is frozen in between, SU:1369-1378), so R, V, F, psi, tPart
+// cross HBM once per MD step instead of once per substep. Random numbers are Philox4x32-10 keyed by
+// (seed; substep, ion, trajectory) -- no state, no ordering dependence (the reference's shared drand48 races).
+#include "mdqt_internal.h"
+#include "mdqt_qtconsts.h"
+#include <math.h>
+
+namespace mdqt {
+
+// ------------------------------------------------------------------------------------------------------------
+// Philox4x32-10 and the uniform layout shared with oracle/mdqt_oracle.c (orc_uniforms5 / orc_collision_draws)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ double u52(unsigned hi, unsigned lo) {
+  unsigned long long k = ((unsigned long long)hi << 20) | (unsigned long long)(lo >> 12);
+  return ((double)k + 0.5) * 2.220446049250313080847263336181640625e-16;  // (k + 1/2) 2^-52, in (0,1)
+}
+__device__ __forceinline__ uint4 philox_call(uint64_t seed, unsigned traj, unsigned ion, uint64_t step, unsigned call) {
+  return philox4x32_10(make_uint4((unsigned)step, (unsigned)(step >> 32), ion, (traj << 3) | call),
+                       make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+}
+
+struct cplx { double re, im; };
+__device__ __forceinline__ double cnorm(const cplx& a) { return fma(a.re, a.re, a.im * a.im); }
+// Im(a conj(b))
+__device__ __forceinline__ double im_acb(const cplx& a, const cplx& b) { return fma(a.im, b.re, -(a.re * b.im)); }
+
+// ------------------------------------------------------------------------------------------------------------
+// One lane's block of the stage map  g(w) = pref * (1 - i h H) w - w   (= h * k_stage of SU:534-535)
+// local states: 0 = S, 1 = P1, 2 = P2, 3 = D coupled to P1, 4 = D coupled to P1 (static) and P2 (rotating),
+// 5 = D coupled to P2.   NL = 6 (12-level) or 4 (7-level: S, P1, P2 and the uncoupled D reservoir).
+// ------------------------------------------------------------------------------------------------------------
+struct LaneH {
+  double hc10, hc20, hc13, hc14, hc25;  // h * real couplings
+  double hrr, hri;                      // h * (rotating coupling H[4][2]) re, im
+  double hE1, hE2, hE3, hE4, hE5;       // h * energies
+  double hg1, hg2;                      // h * Gamma/2 on P1, P2
+  double G1, G2;                        // h * Gamma on P1, P2 (for dp)
+};
+
+template <int NL>
+__device__ __forceinline__ void apply_M(const LaneH& H, const cplx* w, cplx* m) {
+  // m = w - i h (H w):  m.re = w.re + h (Hw).im ;  m.im = w.im - h (Hw).re
+  // S
+  m[0].re = fma(H.hc10, w[1].im, fma(H.hc20, w[2].im, w[0].re));
+  m[0].im = fma(-H.hc10, w[1].re, fma(-H.hc20, w[2].re, w[0].im));
+  // P1: (E1 - i g1) w1 + c10 w0 + c13 w3 + c14 w4
+  {
+    double hr = fma(H.hE1, w[1].re, H.hg1 * w[1].im);   // h Re
+    double hi = fma(H.hE1, w[1].im, -(H.hg1 * w[1].re));// h Im
+    hr = fma(H.hc10, w[0].re, hr); hi = fma(H.hc10, w[0].im, hi);
+    if (NL == 6) {
+      hr = fma(H.hc13, w[3].re, hr); hi = fma(H.hc13, w[3].im, hi);
+      hr = fma(H.hc14, w[4].re, hr); hi = fma(H.hc14, w[4].im, hi);
+    }
+    m[1].re = w[1].re + hi; m[1].im = w[1].im - hr;
+  }
+  // P2: (E2 - i g2) w2 + c20 w0 + c25 w5 + conj(rot) w4
+  {
+    double hr = fma(H.hE2, w[2].re, H.hg2 * w[2].im);
+    double hi = fma(H.hE2, w[2].im, -(H.hg2 * w[2].re));
+    hr = fma(H.hc20, w[0].re, hr); hi = fma(H.hc20, w[0].im, hi);
+    if (NL == 6) {
+      hr = fma(H.hc25, w[5].re, hr); hi = fma(H.hc25, w[5].im, hi);
+      // conj(rot) * w4 = (rr - i ri)(x + i y) = rr x + ri y + i (rr y - ri x)
+      hr = fma(H.hrr, w[4].re, fma(H.hri, w[4].im, hr));
+      hi = fma(H.hrr, w[4].im, fma(-H.hri, w[4].re, hi));
+    }
+    m[2].re = w[2].re + hi; m[2].im = w[2].im - hr;
+  }
+  if (NL == 6) {
+    {  // D(3): E3 w3 + c13 w1
+      double hr = fma(H.hE3, w[3].re, H.hc13 * w[1].re), hi = fma(H.hE3, w[3].im, H.hc13 * w[1].im);
+      m[3].re = w[3].re + hi; m[3].im = w[3].im - hr;
+    }
+    {  // D(4): E4 w4 + c14 w1 + rot w2 ; rot w2 = (rr + i ri)(x + i y) = rr x - ri y + i (rr y + ri x)
+      double hr = fma(H.hE4, w[4].re, H.hc14 * w[1].re), hi = fma(H.hE4, w[4].im, H.hc14 * w[1].im);
+      hr = fma(H.hrr, w[2].re, fma(-H.hri, w[2].im, hr));
+      hi = fma(H.hrr, w[2].im, fma(H.hri, w[2].re, hi));
+      m[4].re = w[4].re + hi; m[4].im = w[4].im - hr;
+    }
+    {  // D(5): E5 w5 + c25 w2
+      double hr = fma(H.hE5, w[5].re, H.hc25 * w[2].re), hi = fma(H.hE5, w[5].im, H.hc25 * w[2].im);
+      m[5].re = w[5].re + hi; m[5].im = w[5].im - hr;
+    }
+  } else {
+    m[3] = w[3];  // 7-level D reservoir: zero energy, no coupling
+  }
+}
+
+template <int NL>
+__device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g, unsigned pairmask) {
+  cplx m[NL];
+  double own = fma(H.G1, cnorm(w[1]), H.G2 * cnorm(w[2]));
+  double dp = own + __shfl_xor_sync(pairmask, own, 1);
+  double pref = rsqrt(1.0 - dp);
+  apply_M<NL>(H, w, m);
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    g[k].re = fma(pref, m[k].re, -w[k].re);
+    g[k].im = fma(pref, m[k].im, -w[k].im);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// the fused kernel: nsub x { step(); qstep(); } for one ion per lane pair
+// ------------------------------------------------------------------------------------------------------------
+template <int NL, bool FORCED>
+__global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = gid & 1;
+  // shuffles are between the two lanes of an ion only: ions of one warp may sit in different branches
+  const unsigned pairmask = 3u << (threadIdx.x & 30);
+  const long long slot = gid >> 1;
+  const bool active = slot < (long long)a.nrows * a.B;
+  // inactive lanes still run (shuffles are warp-wide) on a harmless dummy ion
+  const int b = active ? (int)(slot / a.nrows) : 0;
+  const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
+  const QTLane& Lc = C.lane[lane];
+  constexpr int S = (NL == 6) ? 12 : 7;
+
+  double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
+  double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
+  const double* __restrict__ Fb = a.F + (size_t)b * 3 * a.ld;
+  double* __restrict__ Pb = a.psi + (size_t)b * 2 * S * a.ld;
+
+  cplx y[NL];
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    int gidx = Lc.map[k];
+    if (gidx >= 0) { y[k].re = Pb[(size_t)(2 * gidx) * a.ld + i]; y[k].im = Pb[(size_t)(2 * gidx + 1) * a.ld + i]; }
+    else { y[k].re = 0.0; y[k].im = 0.0; }
+  }
+  // lane A carries (x, y), lane B carries (x, z); x is advanced redundantly (bitwise identically) by both
+  const int c2 = 1 + lane;
+  double rx = 0, r2 = 0, vx = Vb[i], v2 = 0, fx = 0, f2 = 0, tp = 0;
+  if (a.do_step) {
+    rx = Rb[i]; r2 = Rb[(size_t)c2 * a.ld + i];
+    v2 = Vb[(size_t)c2 * a.ld + i];
+    fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
+    tp = a.tPart[(size_t)b * a.ld + i];
+  }
+  const double h = C.h;
+  double t = a.t0;
+
+  for (int s = 0; s < a.nsub; s++) {
+    // ---------------- step(): R += V dt/2 ; V += F dt ; R += V dt/2, single wrap into [0,L] (SU:356-430) ------
+    if (a.do_step) {
+      const double DT = 0.5 * a.dtq;
+      const bool started = t > 0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        if (started) {
+          rx = __dadd_rn(rx, __dmul_rn(DT, vx));
+          r2 = __dadd_rn(r2, __dmul_rn(DT, v2));
+        } else {  // first substep of a new run: 2nd-order start (SU:370-379)
+          rx = __dadd_rn(rx, __dadd_rn(__dmul_rn(DT, vx), __dmul_rn(__dmul_rn(DT, DT), fx)));
+          r2 = __dadd_rn(r2, __dadd_rn(__dmul_rn(DT, v2), __dmul_rn(__dmul_rn(DT, DT), f2)));
+        }
+        if (rx < 0) rx = __dadd_rn(rx, a.L);
+        if (rx > a.L) rx = __dadd_rn(rx, -a.L);
+        if (r2 < 0) r2 = __dadd_rn(r2, a.L);
+        if (r2 > a.L) r2 = __dadd_rn(r2, -a.L);
+        if (half == 0) {
+          vx = __dadd_rn(vx, __dmul_rn(a.dtq, fx));
+          v2 = __dadd_rn(v2, __dmul_rn(a.dtq, f2));
+        }
+      }
+    }
+    // ---------------- qstep() (SU:478-714 / MC408L:578-755) ---------------------------------------------------
+    double expDet = 0.0;
+    if (a.fracOfSig != 0.0)  // SU:447, from the global time before it is advanced
+      expDet = 0.0126 * a.fracOfSig * a.Te * t /
+               (sqrt(a.density) * a.sig0 * sqrt(1 + 0.00014314 * t * t * a.Te / (a.density * a.sig0 * a.sig0)));
+    const double vq = vx * a.pv2qv;
+    if (a.do_step) tp = __dadd_rn(tp, a.dtq);
+
+    // P populations of both blocks, in the reference's state order 2,3,4,5 -> identical jump decision in both lanes
+    const double nown1 = cnorm(y[1]), nown2 = cnorm(y[2]);
+    const double noth1 = __shfl_xor_sync(pairmask, nown1, 1), noth2 = __shfl_xor_sync(pairmask, nown2, 1);
+    double n2, n3, n4, n5;
+    if (NL == 6) {  // 12-level: idx2 = B.P1, idx3 = A.P1, idx4 = B.P2, idx5 = A.P2
+      n2 = lane ? nown1 : noth1; n3 = lane ? noth1 : nown1; n4 = lane ? nown2 : noth2; n5 = lane ? noth2 : nown2;
+    } else {        // 7-level:  idx2 = A.P1, idx3 = B.P1, idx4 = A.P2, idx5 = B.P2
+      n2 = lane ? noth1 : nown1; n3 = lane ? nown1 : noth1; n4 = lane ? noth2 : nown2; n5 = lane ? nown2 : noth2;
+    }
+    const double dp0 = h * C.gam[0] * n2 + h * C.gam[1] * n3 + h * C.gam[2] * n4 + h * C.gam[3] * n5;
+
+    double u0, u1;
+    const uint64_t sidx = a.substep0 + (uint64_t)s;
+    if (FORCED) {
+      const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
+      u0 = up[0]; u1 = up[1];
+    } else {
+      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
+      u0 = u52(o.x, o.y); u1 = u52(o.z, o.w);
+    }
+
+    double kick = 0.0;
+    if (u0 > dp0) {
+      // ---- no jump: optical force from the pre-step coherences (SU:490-503), then the 4-stage propagator ----
+      if (a.do_step) {
+        double ksp = Lc.gA * im_acb(y[0], y[1]) - Lc.gB * im_acb(y[0], y[2]);
+        double own = C.kick_sp * ksp;
+        if (NL == 6) {
+          double kdp = Lc.gD[0] * im_acb(y[4], y[2]) + Lc.gD[1] * im_acb(y[3], y[1]) - Lc.gD[2] * im_acb(y[5], y[2]) -
+                       Lc.gD[3] * im_acb(y[4], y[1]);
+          own = fma(C.kick_dp, kdp, own);
+        }
+        kick = own;  // cross-lane sum below (outside the divergent region)
+      }
+      LaneH H;
+      const double uu = vq + expDet;
+      H.hc10 = h * Lc.c10; H.hc20 = h * Lc.c20; H.hc13 = h * Lc.c13; H.hc14 = h * Lc.c14; H.hc25 = h * Lc.c25;
+      H.hE1 = h * (-a.detuning - vq - expDet);                        // totalDetRightSP (SU:506)
+      H.hE2 = h * (-a.detuning + vq + expDet);                        // totalDetLeftSP  (SU:507)
+      if (NL == 6) {
+        H.hE3 = h * (-a.detuning + a.detuningDP + (a.kRat - 1) * uu); // states 11,12 (SU:510)
+        H.hE4 = h * (-a.detuning + a.detuningDP - vq - expDet - a.kRat * uu);  // states 9,10
+        H.hE5 = h * (-a.detuning + a.detuningDP + (1 - a.kRat) * uu); // states 7,8
+        double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;             // SU:508
+        double sn, cs;
+        sincos(phi, &sn, &cs);
+        H.hrr = h * (Lc.rot * cs); H.hri = h * (Lc.rot * sn);
+      } else {
+        H.hE3 = H.hE4 = H.hE5 = 0.0; H.hrr = H.hri = 0.0;
+      }
+      H.hg1 = 0.5 * h * Lc.gam1; H.hg2 = 0.5 * h * Lc.gam2;
+      H.G1 = h * Lc.gam1; H.G2 = h * Lc.gam2;
+
+      cplx w[NL], g[NL], acc[NL];
+      stage<NL>(H, y, g, pairmask);
+#pragma unroll
+      for (int k = 0; k < NL; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
+      stage<NL>(H, w, g, pairmask);
+#pragma unroll
+      for (int k = 0; k < NL; k++) {
+        acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
+        w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im);
+      }
+      stage<NL>(H, w, g, pairmask);
+#pragma unroll
+      for (int k = 0; k < NL; k++) {
+        acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
+        w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
+      }
+      stage<NL>(H, w, g, pairmask);
+#pragma unroll
+      for (int k = 0; k < NL; k++) {
+        y[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
+        y[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
+      }
+    } else {
+      // ---- quantum jump (SU:573-703 / MC408L:674-752): both lanes take identical decisions ----
+      double u2, u3, u4;
+      if (FORCED) {
+        const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
+        u2 = up[2]; u3 = up[3]; u4 = up[4];
+      } else {
+        uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
+        u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
+        u4 = u52(o.x, o.y);
+      }
+      tp = 0.0;
+      const double tot = n2 + n3 + n4 + n5;
+      const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
+      const bool sDecay = !(u2 < C.dfrac);
+      if (a.do_step) {
+        double mag = sDecay ? a.vKick : a.vKickDP;
+        kick = (u3 < 0.5) ? mag : -mag;
+        if (lane) kick = 0.0;  // counted once in the cross-lane sum
+      }
+      int dest;
+      if (NL == 6) {
+        if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
+        else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
+        else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
+        else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
+      } else {
+        // the 7-level file draws its 4th uniform (rand3) only for S decays out of states 4 and 5; with a
+        // counter-based stream the slot is simply left unused otherwise
+        if (u1 < p3) dest = sDecay ? 0 : 6;
+        else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : 6;
+        else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 0 : 1) : 6;
+        else dest = sDecay ? 1 : 6;
+      }
+#pragma unroll
+      for (int k = 0; k < NL; k++) { y[k].re = (Lc.map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
+    }
+    if (a.do_step) {
+      kick = kick + __shfl_xor_sync(pairmask, kick, 1);
+      vx = __dadd_rn(vx, kick);  // SU:705
+    }
+    if (a.renorm) {  // SU:706-712
+      double own = 0.0;
+#pragma unroll
+      for (int k = 0; k < NL; k++) own += cnorm(y[k]);
+      double nn = sqrt(own + __shfl_xor_sync(pairmask, own, 1));
+#pragma unroll
+      for (int k = 0; k < NL; k++) { y[k].re /= nn; y[k].im /= nn; }
+    }
+    if (a.do_step) t = __dadd_rn(t, a.dtq);  // SU:716
+  }
+
+  if (!active) return;
+#pragma unroll
+  for (int k = 0; k < NL; k++) {
+    int gidx = Lc.map[k];
+    if (gidx >= 0) { Pb[(size_t)(2 * gidx) * a.ld + i] = y[k].re; Pb[(size_t)(2 * gidx + 1) * a.ld + i] = y[k].im; }
+  }
+  if (a.do_step) {
+    Rb[(size_t)c2 * a.ld + i] = r2;
+    Vb[(size_t)c2 * a.ld + i] = v2;
+    if (lane == 0) { Rb[i] = rx; Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp; }
+  }
+}
+
+void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s) {
+  long long threads = 2LL * a.nrows * a.B;
+  int block = threads >= 148LL * 4 * 128 ? 128 : 64;
+  int grid = (int)((threads + block - 1) / block);
+  bool forced = a.forced_u != nullptr;
+  if (scheme == 12) {
+    if (forced) k_substeps<6, true><<<grid, block, 0, s>>>(a, C);
+    else k_substeps<6, false><<<grid, block, 0, s>>>(a, C);
+  } else {
+    if (forced) k_substeps<4, true><<<grid, block, 0, s>>>(a, C);
+    else k_substeps<4, false><<<grid, block, 0, s>>>(a, C);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: MD-family velocity Verlet (MD:452-502)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_vv_positions(VVArgs a) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)a.nrows * a.B * 3) return;
+  int b = (int)(g / (3LL * a.nrows));
+  int rem = (int)(g % (3LL * a.nrows));
+  int c = rem / a.nrows, i = a.row0 + rem % a.nrows;
+  size_t idx = ((size_t)b * 3 + c) * a.ld + i;
+  // R = R + dt*V + dt*dt/2*A, each operation rounded as in the reference (MD:455)
+  double r = __dadd_rn(__dadd_rn(a.R[idx], __dmul_rn(a.dt, a.V[idx])), __dmul_rn(__dmul_rn(a.dt, a.dt) / 2, a.A[idx]));
+  if (r < 0) r = __dadd_rn(r, a.L);
+  if (r > a.L) r = __dadd_rn(r, -a.L);
+  a.R[idx] = r;
+}
+
+__global__ void k_vv_velocities(VVArgs a) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)a.nrows * a.B) return;
+  int b = (int)(g / a.nrows);
+  int i = a.row0 + (int)(g % a.nrows);
+  size_t base = (size_t)b * 3 * a.ld + i;
+  double v[3];
+  bool collide = false;
+  if (a.collisionFreq > 0.0) {
+    double u, nrm[3];
+    if (a.forced_u) {
+      u = a.forced_u[i];
+      nrm[0] = a.forced_n[3 * i]; nrm[1] = a.forced_n[3 * i + 1]; nrm[2] = a.forced_n[3 * i + 2];
+      collide = u < a.dt * a.collisionFreq;
+    } else {
+      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 3);
+      u = u52(o.x, o.y);
+      collide = u < a.dt * a.collisionFreq;  // MD:476-477
+      if (collide) {                         // Box-Muller on stream calls 3..5 (orc_collision_draws)
+        double ua = u52(o.z, o.w);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 4);
+        double ub = u52(o.x, o.y), uc = u52(o.z, o.w);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 5);
+        double ud = u52(o.x, o.y);
+        double r = sqrt(-2.0 * log(ua)), sn, cs;
+        sincos(6.283185307179586476925286766559 * ub, &sn, &cs);
+        nrm[0] = a.sigma_v * (r * cs); nrm[1] = a.sigma_v * (r * sn);
+        nrm[2] = a.sigma_v * (sqrt(-2.0 * log(uc)) * cos(6.283185307179586476925286766559 * ud));
+      }
+    }
+    if (collide) { v[0] = nrm[0]; v[1] = nrm[1]; v[2] = nrm[2]; }
+  }
+  if (!collide) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      size_t idx = base + (size_t)c * a.ld;
+      v[c] = __dadd_rn(a.V[idx], __dmul_rn(a.dt / 2, __dadd_rn(a.oldA[idx], a.A[idx])));  // MD:484-486
+    }
+  }
+  if (a.laser == 2) {
+    v[0] = __dadd_rn(v[0], __dmul_rn(__dmul_rn(v[0], a.dt), a.laser_coeff));          // MD:491
+  } else if (a.laser == 1) {
+    v[0] = __dadd_rn(v[0], __dmul_rn(__dmul_rn(v[0], a.dt), a.laser_coeff) / 2);      // MD:494
+    v[1] = __dadd_rn(v[1], -(__dmul_rn(__dmul_rn(v[1], a.dt), a.laser_coeff) / 4));   // MD:495
+    v[2] = __dadd_rn(v[2], -(__dmul_rn(__dmul_rn(v[2], a.dt), a.laser_coeff) / 4));   // MD:496
+  }
+#pragma unroll
+  for (int c = 0; c < 3; c++) a.V[base + (size_t)c * a.ld] = v[c];
+}
+
+void launch_vv_positions(const VVArgs& a, cudaStream_t s) {
+  long long n = 3LL * a.nrows * a.B;
+  k_vv_positions<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+}
+void launch_vv_velocities(const VVArgs& a, cudaStream_t s) {
+  long long n = (long long)a.nrows * a.B;
+  k_vv_velocities<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+}
+
+}  // namespace mdqt

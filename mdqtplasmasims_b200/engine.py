@@ -1,0 +1,321 @@
+"""Host-side mirror of the reference's hot-path interface, over the C ABI of ``libmdqt_b200.so``.
+
+The reference (tlangin/MDQTPlasmaSims) exposes its hot path as ``void f(void)`` functions working on file-scope
+globals (``forces()`` SU:192, ``step()`` SU:418, ``qstep()`` SU:438, ``Epotential()`` SU:244, ``output()`` SU:917;
+``calculateAccelerations()`` MD:387, ``MDStep()`` MD:504; 7-level ``qstep()`` MC408L:555).  :class:`Engine` keeps
+those names and argument meanings, with the globals living in GPU memory behind a handle.  Everything here is
+plumbing (ctypes + numpy); all arithmetic happens in the CUDA kernels.  There is no CPU fallback: if the shared
+library is missing or no GPU is present, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmdqt_b200.so")
+
+SCHEME_NONE, SCHEME_SR7, SCHEME_SR12 = 0, 7, 12
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class MDQTError(RuntimeError):
+    pass
+
+
+class Params(ctypes.Structure):
+    """``mdqt_params`` of include/mdqt.h (same field order)."""
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "struct_bytes", "scheme", "n_ions", "n_traj", "traj0", "row0", "n_rows", "device", "substeps_per_md",
+        "renormalize", "quad", "reserved")] + [(k, ctypes.c_double) for k in (
+            "L", "kappa", "rcut", "dtq", "detuning", "detuningDP", "Om", "OmDP", "dR", "kRat", "vKick", "vKickDP", "g2E",
+            "pv2qv", "fracOfSig", "Te", "sig0", "density")] + [("seed", ctypes.c_uint64)]
+
+
+class Diag(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_double) for k in ("t", "ekin_x", "ekin_y", "ekin_z", "epot", "vx_avg")]
+
+
+# every symbol include/mdqt.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    "mdqt_params_su", "mdqt_params_md", "mdqt_device_count", "mdqt_last_error", "mdqt_version", "mdqt_create",
+    "mdqt_destroy", "mdqt_sync", "mdqt_upload_state", "mdqt_download_state", "mdqt_upload_forces",
+    "mdqt_download_forces", "mdqt_set_time", "mdqt_get_time", "mdqt_forces", "mdqt_substeps", "mdqt_md_steps",
+    "mdqt_md_steps_host", "mdqt_epot", "mdqt_diagnostics", "mdqt_vel_dist", "mdqt_populations", "mdqt_vv_step",
+    "mdqt_qsteps", "mdqt_set_forced_uniforms", "mdqt_set_forced_collisions", "mdqt_philox_uniforms", "mdqt_device_ptr",
+    "mdqt_device_ld", "mdqt_stream", "mdqt_mark_wrapped", "mdqt_force_plan", "mdqt_enable_timing",
+    "mdqt_kernel_time_ms", "mdqt_fp64_peak",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libmdqt_b200.so (built in-tree by mdqtplasmasims_b200/build.py). Fails loudly when missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MDQTError("libmdqt_b200.so not built: run `python -m mdqtplasmasims_b200.build` (no CPU fallback exists)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.mdqt_last_error.restype = ctypes.c_char_p
+    L.mdqt_version.restype = ctypes.c_char_p
+    L.mdqt_device_ptr.restype = ctypes.c_void_p
+    L.mdqt_stream.restype = ctypes.c_void_p
+    vp = ctypes.c_void_p
+    L.mdqt_params_su.argtypes = [ctypes.POINTER(Params)] + [ctypes.c_double] * 9 + [ctypes.c_int, ctypes.c_int]
+    L.mdqt_params_md.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 5 + [ctypes.c_int]
+    L.mdqt_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(vp)]
+    L.mdqt_destroy.argtypes = [vp]
+    L.mdqt_sync.argtypes = [vp]
+    L.mdqt_upload_state.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int]
+    L.mdqt_download_state.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int]
+    L.mdqt_upload_forces.argtypes = [vp, vp, ctypes.c_int]
+    L.mdqt_download_forces.argtypes = [vp, vp, ctypes.c_int]
+    L.mdqt_set_time.argtypes = [vp, ctypes.c_double, ctypes.c_uint64]
+    L.mdqt_get_time.argtypes = [vp, c_double_p, ctypes.POINTER(ctypes.c_uint64)]
+    L.mdqt_forces.argtypes = [vp]
+    L.mdqt_substeps.argtypes = [vp, ctypes.c_int]
+    L.mdqt_md_steps.argtypes = [vp, ctypes.c_int]
+    L.mdqt_md_steps_host.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+    L.mdqt_epot.argtypes = [vp, c_double_p]
+    L.mdqt_diagnostics.argtypes = [vp, ctypes.POINTER(Diag)]
+    L.mdqt_vel_dist.argtypes = [vp, c_double_p]
+    L.mdqt_populations.argtypes = [vp, c_double_p]
+    L.mdqt_vv_step.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_double]
+    L.mdqt_qsteps.argtypes = [vp, ctypes.c_int]
+    L.mdqt_set_forced_uniforms.argtypes = [vp, vp, ctypes.c_int]
+    L.mdqt_set_forced_collisions.argtypes = [vp, vp, vp]
+    L.mdqt_philox_uniforms.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p]
+    L.mdqt_device_ptr.argtypes = [vp, ctypes.c_int]
+    L.mdqt_device_ld.argtypes = [vp]
+    L.mdqt_stream.argtypes = [vp]
+    L.mdqt_mark_wrapped.argtypes = [vp, ctypes.c_int]
+    L.mdqt_force_plan.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    L.mdqt_enable_timing.argtypes = [vp, ctypes.c_int]
+    L.mdqt_kernel_time_ms.argtypes = [vp, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_int)]
+    L.mdqt_fp64_peak.argtypes = [vp, c_double_p]
+    _lib = L
+    return L
+
+
+def su_params(Ge=0.1, density=2.0, sig0=4.0, Te=19.0, fracOfSig=0.0, detuning=-1.0, detuningDP=1.0, Om=1.0, OmDP=1.0,
+              N0=3500, n_ions=None, **overrides):
+    """``mdqt_params`` for the SU family from the reference's user inputs (SU:56-74)."""
+    p = Params()
+    rc = load_library().mdqt_params_su(ctypes.byref(p), Ge, density, sig0, Te, fracOfSig, detuning, detuningDP, Om, OmDP,
+                                       N0, N0 if n_ions is None else n_ions)
+    if rc:
+        raise MDQTError(load_library().mdqt_last_error().decode())
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def md_params(scheme=SCHEME_NONE, n_ions=4096, kappa=0.5, density=0.4, timeStep=0.005, detuning=-2.5, Om=0.7, quad=0,
+              **overrides):
+    """``mdqt_params`` for the MD family (MD:66-88; MC408L:79-122)."""
+    p = Params()
+    rc = load_library().mdqt_params_md(ctypes.byref(p), scheme, n_ions, kappa, density, timeStep, detuning, Om, quad)
+    if rc:
+        raise MDQTError(load_library().mdqt_last_error().decode())
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def philox_uniforms(seed, traj, n_ions, substep):
+    """The u[n_ions][5] the device draws for trajectory ``traj`` at global substep ``substep`` (host replica)."""
+    L = load_library()
+    u = np.empty((n_ions, 5))
+    for i in range(n_ions):
+        L.mdqt_philox_uniforms(seed, traj, i, substep, u[i].ctypes.data_as(c_double_p))
+    return u
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _chk64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise MDQTError("array has shape %s, expected %s" % (a.shape, shape))
+    return a
+
+
+class Engine:
+    """One handle = the reference's global simulation state, resident on one GPU.
+
+    Method names follow the reference: ``forces()``, ``step_qstep(n)`` (n x { step(); qstep(); }), ``md_steps(n)``
+    (the main-loop body), ``Epotential()``, ``MDStep()``, ``qstep7(n)``.
+    """
+
+    def __init__(self, params):
+        self.lib = load_library()
+        self.params = params
+        h = ctypes.c_void_p()
+        rc = self.lib.mdqt_create(ctypes.byref(params), ctypes.byref(h))
+        if rc:
+            raise MDQTError("mdqt_create failed (%d): %s" % (rc, self.lib.mdqt_last_error().decode()))
+        self.h = h
+        self.N, self.B, self.S = params.n_ions, params.n_traj, params.scheme
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mdqt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise MDQTError("libmdqt_b200 error %d: %s" % (rc, self.lib.mdqt_last_error().decode()))
+
+    def _lead(self):
+        return (self.B,) if self.B > 1 else ()
+
+    # ---- state -------------------------------------------------------------------------------------------
+    def upload(self, R=None, V=None, psi=None, tPart=None, t=None, substep=None):
+        N = self.N
+        R = _chk64(R, self._lead() + (3, N))
+        V = _chk64(V, self._lead() + (3, N))
+        psi = _chk64(psi, self._lead() + (N, self.S, 2)) if psi is not None else None
+        tPart = _chk64(tPart, self._lead() + (N,))
+        self._ck(self.lib.mdqt_upload_state(self.h, _ptr(R), _ptr(V), _ptr(psi), _ptr(tPart), N))
+        if t is not None or substep is not None:
+            t0, s0 = self.time()
+            self._ck(self.lib.mdqt_set_time(self.h, t0 if t is None else t, s0 if substep is None else substep))
+
+    def download(self, want=("R", "V", "psi", "tPart")):
+        N = self.N
+        out = {}
+        R = np.empty(self._lead() + (3, N)) if "R" in want else None
+        V = np.empty(self._lead() + (3, N)) if "V" in want else None
+        psi = np.empty(self._lead() + (N, self.S, 2)) if ("psi" in want and self.S) else None
+        tp = np.empty(self._lead() + (N,)) if "tPart" in want else None
+        self._ck(self.lib.mdqt_download_state(self.h, _ptr(R), _ptr(V), _ptr(psi), _ptr(tp), N))
+        for k, v in (("R", R), ("V", V), ("psi", psi), ("tPart", tp)):
+            if v is not None:
+                out[k] = v
+        out["t"], out["substep"] = self.time()
+        return out
+
+    def upload_forces(self, F):
+        F = _chk64(F, self._lead() + (3, self.N))
+        self._ck(self.lib.mdqt_upload_forces(self.h, _ptr(F), self.N))
+
+    def download_forces(self):
+        F = np.empty(self._lead() + (3, self.N))
+        self._ck(self.lib.mdqt_download_forces(self.h, _ptr(F), self.N))
+        return F
+
+    def time(self):
+        t = ctypes.c_double()
+        s = ctypes.c_uint64()
+        self._ck(self.lib.mdqt_get_time(self.h, ctypes.byref(t), ctypes.byref(s)))
+        return t.value, s.value
+
+    def sync(self):
+        self._ck(self.lib.mdqt_sync(self.h))
+
+    # ---- the reference's hot-path functions -----------------------------------------------------------------
+    def forces(self):
+        """forces() SU:192-236 / calculateAccelerations() MD:387-448."""
+        self._ck(self.lib.mdqt_forces(self.h))
+
+    calculateAccelerations = forces
+
+    def step_qstep(self, nsub=1):
+        """nsub x { step(); qstep(); } (SU:1376-1377)."""
+        self._ck(self.lib.mdqt_substeps(self.h, nsub))
+
+    def md_steps(self, nsteps=1):
+        """nsteps x { forces(); ratio x { step(); qstep(); } } (SU:1369-1378)."""
+        self._ck(self.lib.mdqt_md_steps(self.h, nsteps))
+
+    def md_steps_host(self, nsteps, R, V, psi, tPart):
+        """End-to-end call on HOST arrays (updated in place): upload, nsteps MD steps, download."""
+        for a in (R, V, psi, tPart):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.mdqt_md_steps_host(self.h, nsteps, _ptr(R), _ptr(V), _ptr(psi), _ptr(tPart), self.N))
+
+    def Epotential(self):
+        """Epotential() SU:244-281 (per particle)."""
+        e = np.empty(self.B)
+        self._ck(self.lib.mdqt_epot(self.h, e.ctypes.data_as(c_double_p)))
+        return e if self.B > 1 else float(e[0])
+
+    def diagnostics(self):
+        d = (Diag * self.B)()
+        self._ck(self.lib.mdqt_diagnostics(self.h, d))
+        out = [{k: getattr(x, k) for k, _ in Diag._fields_} for x in d]
+        return out if self.B > 1 else out[0]
+
+    def vel_dist(self):
+        p = np.empty(self._lead() + (3, 2001))
+        self._ck(self.lib.mdqt_vel_dist(self.h, p.ctypes.data_as(c_double_p)))
+        return p
+
+    def populations(self):
+        p = np.empty(self._lead() + (self.N, 3))
+        self._ck(self.lib.mdqt_populations(self.h, p.ctypes.data_as(c_double_p)))
+        return p
+
+    def MDStep(self, dt=0.005, collisionFreq=0.0, sigma_v=1.0, laser=0, laser_coeff=0.0):
+        """MDStep() MD:504-511."""
+        self._ck(self.lib.mdqt_vv_step(self.h, dt, collisionFreq, sigma_v, laser, laser_coeff))
+
+    def qstep7(self, nsub=1):
+        """nsub x qstep() of the 7-level pump (MC408L:555-756), velocities frozen, no kick."""
+        self._ck(self.lib.mdqt_qsteps(self.h, nsub))
+
+    # ---- test hooks / plumbing ---------------------------------------------------------------------------------
+    def set_forced_uniforms(self, u):
+        if u is None:
+            self._ck(self.lib.mdqt_set_forced_uniforms(self.h, None, 0))
+            return
+        u = _chk64(u)
+        assert u.ndim == 3 and u.shape[1:] == (self.N, 5)
+        self._ck(self.lib.mdqt_set_forced_uniforms(self.h, _ptr(u), u.shape[0]))
+
+    def set_forced_collisions(self, u, v):
+        if u is None:
+            self._ck(self.lib.mdqt_set_forced_collisions(self.h, None, None))
+            return
+        u, v = _chk64(u, (self.N,)), _chk64(v, (self.N, 3))
+        self._ck(self.lib.mdqt_set_forced_collisions(self.h, _ptr(u), _ptr(v)))
+
+    def force_plan(self):
+        a, b = ctypes.c_int(), ctypes.c_int()
+        self._ck(self.lib.mdqt_force_plan(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def device_ptr(self, which):
+        return self.lib.mdqt_device_ptr(self.h, which)
+
+    @property
+    def ld(self):
+        return self.lib.mdqt_device_ld(self.h)
+
+    def mark_wrapped(self, wrapped=True):
+        self._ck(self.lib.mdqt_mark_wrapped(self.h, 1 if wrapped else 0))
+
+    def enable_timing(self, on=True):
+        self._ck(self.lib.mdqt_enable_timing(self.h, 1 if on else 0))
+
+    def kernel_time_ms(self, which):
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        self._ck(self.lib.mdqt_kernel_time_ms(self.h, which, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
+
+    def fp64_peak_tflops(self):
+        v = ctypes.c_double()
+        self._ck(self.lib.mdqt_fp64_peak(self.h, ctypes.byref(v)))
+        return v.value

@@ -1,0 +1,193 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE ONLY.
+
+Generates the golden input/output vectors under tests/golden/ by running the UNMODIFIED reference programs
+(through oracle/_ref/libref_*.so, i.e. /root/reference compiled by oracle/Makefile) on seeded inputs.
+Run in the build container (where /root/reference exists):
+
+    OMP_NUM_THREADS=1 python -m oracle.gen_golden
+
+The reference has no golden vectors of its own; these files pin the oracle restatement and
+the CUDA path to the reference's actual outputs and travel to the GPU box, where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+os.environ["OMP_NUM_THREADS"] = "1"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+NOJUMP = 0.99999  # injected `rand`: always > dp, so no jump
+
+
+def full_psi(rng, n, S):
+    psi = rng.normal(size=(n, S, 2))
+    psi /= np.sqrt((psi ** 2).sum(axis=(1, 2)))[:, None, None]
+    return psi
+
+
+def gen_su_forces():
+    ref = po.RefSU()
+    N = ref.init(12345)  # random frozen start, drand48 seed 12345 (SU:289-348)
+    s = ref.get_state()
+    ref.forces()
+    F = ref.get_state()["F"]
+    np.savez(os.path.join(OUT, "su_forces_N%d.npz" % N), R=s["R"], F=F, Epot=ref.epot(), L=ref.consts["L"],
+             lDeb=ref.consts["lDeb"], psi0=s["psi"][:64])
+    print("su_forces: N=%d F[:,0]=%s Epot=%.17g" % (N, F[:, 0], ref.epot()))
+
+
+def gen_su_nojump():
+    """{step(); qstep();} x nsub with injected no-jump uniforms, F frozen: the deterministic evolution."""
+    rng = np.random.default_rng(2024)
+    n = 96
+    cases = {}
+    for name, frac, t0, nsub in (("a", 0.0, 0.0, 1), ("b", 0.0, 0.0, 25), ("c", 0.5, 0.4321, 25), ("d", 0.5, 0.0, 3),
+                                 ("e", 0.0, 7.5, 50)):
+        ref = po.RefSU(fracOfSig=frac)
+        c = ref.consts
+        R = rng.uniform(0, c["L"], size=(3, n))
+        R[0, :4] = [1e-7, c["L"] - 1e-7, 0.0, c["L"]]  # exercise the wrap (SU:381-389)
+        V = rng.normal(size=(3, n)) * 0.3
+        V[0, :2] = [-0.5, 0.5]
+        F = rng.normal(size=(3, n)) * 2.0
+        psi = full_psi(rng, n, 12)
+        psi[:8] = 0.0
+        psi[:8, 0, 0] = 1.0  # pure S ions
+        tp = rng.uniform(0, 0.5, size=n)
+        ref.set_state(R=R, V=V, psi=psi, tPart=tp, t=t0)
+        ref.set_F(F)
+        for _ in range(nsub):
+            ref.step()
+            ref.qstep(np.full(n, NOJUMP))
+        o = ref.get_state()
+        for k, v in (("R", R), ("V", V), ("F", F), ("psi", psi), ("tPart", tp), ("t0", t0), ("nsub", nsub), ("frac", frac),
+                     ("R_out", o["R"]), ("V_out", o["V"]), ("psi_out", o["psi"]), ("tPart_out", o["tPart"]), ("t_out", o["t"])):
+            cases[name + "_" + k] = v
+    np.savez(os.path.join(OUT, "su_nojump.npz"), **cases)
+    print("su_nojump: cases a-e written")
+
+
+def gen_su_jumps():
+    """Every branch of the jump table (SU:573-703) by forced uniforms, through the reference's own qstep()."""
+    ref = po.RefSU()
+    rows = []
+    # P source state (0-indexed 2..5) x {S decay, D decay} x kick sign x destination selector
+    for src in (2, 3, 4, 5):
+        for u2 in (0.01, 0.5):          # randDOrS: < dR/(1+dR)=0.0581 -> D decay
+            for u3 in (0.25, 0.75):     # randDir
+                for u4 in (0.02, 0.3, 0.5, 0.7, 0.97):  # rand3
+                    rows.append((src, u2, u3, u4))
+    n = len(rows)
+    rng = np.random.default_rng(7)
+    psi = np.zeros((n, 12, 2))
+    u5 = np.zeros((n, 5))
+    for i, (src, u2, u3, u4) in enumerate(rows):
+        # P populations 0.1 each: cumulative thresholds 0.25/0.5/0.75 select the source sublevel
+        amp = rng.normal(size=(12, 2))
+        amp[2:6] *= 0.0
+        for m in range(2, 6):
+            ph = rng.uniform(0, 2 * np.pi)
+            amp[m] = np.sqrt(0.1) * np.array([np.cos(ph), np.sin(ph)])
+        rest = np.sqrt((amp[:2] ** 2).sum() + (amp[6:] ** 2).sum())
+        amp[:2] *= np.sqrt(0.6) / rest
+        amp[6:] *= np.sqrt(0.6) / rest
+        psi[i] = amp
+        u5[i] = [1e-12, (src - 2) * 0.25 + 0.125, u2, u3, u4]
+    V = np.zeros((3, n))
+    V[0] = rng.normal(size=n) * 0.2
+    tp = rng.uniform(0.1, 0.3, size=n)
+    ref.set_state(R=np.zeros((3, n)), V=V, psi=psi, tPart=tp, t=1.0)
+    used = ref.qstep_stream(u5)
+    o = ref.get_state()
+    np.savez(os.path.join(OUT, "su_jumps.npz"), psi=psi, V=V, tPart=tp, u5=u5, used=used, psi_out=o["psi"], V_out=o["V"],
+             tPart_out=o["tPart"])
+    dests = np.argmax((o["psi"] ** 2).sum(axis=2), axis=1)
+    print("su_jumps: %d cases, used hist %s, %d distinct (src,dest) pairs" %
+          (n, np.bincount(used), len(set(zip([r[0] for r in rows], dests.tolist())))))
+
+
+def gen_su_stream():
+    """A short coupled run with the engine's own Philox uniforms (orc_uniforms5), jumps included: F frozen per MD
+    step, forces() recomputed by the reference every 25 substeps (the main-loop schedule SU:1369-1378)."""
+    orc = po.Oracle()
+    ref = po.RefSU()
+    c = ref.consts
+    rng = np.random.default_rng(99)
+    n, seed, traj, nsub_total = 128, 20260101, 3, 50
+    # a small dense box so that forces matter: override L for n ions
+    L = (n * 4 * np.pi / 3) ** (1. / 3)
+    ref.set_box(L, c["lDeb"])
+    R = rng.uniform(0, L, size=(3, n))
+    V = rng.normal(size=(3, n)) * 0.1
+    psi = full_psi(rng, n, 12)  # substantial P population -> jumps within 50 substeps
+    tp = np.zeros(n)
+    ref.set_state(R=R, V=V, psi=psi, tPart=tp, t=0.0)
+    used_all = []
+    for s in range(nsub_total):
+        if s % 25 == 0:
+            ref.forces()
+        ref.step()
+        used_all.append(ref.qstep_stream(orc.uniforms5(seed, traj, n, s)))
+    o = ref.get_state()
+    used_all = np.array(used_all)
+    np.savez(os.path.join(OUT, "su_stream.npz"), R=R, V=V, psi=psi, tPart=tp, L=L, lDeb=c["lDeb"], seed=seed, traj=traj,
+             nsub=nsub_total, used=used_all, R_out=o["R"], V_out=o["V"], psi_out=o["psi"], tPart_out=o["tPart"], t_out=o["t"])
+    print("su_stream: %d substeps, %d jumps" % (nsub_total, int((used_all > 1).sum())))
+
+
+def gen_md():
+    md = po.RefMD()
+    c = md.consts
+    md.seed(12345)
+    md.init()
+    rng = np.random.default_rng(5)
+    R = rng.uniform(0, c["L"], size=(3, md.N))
+    md.set_state(R=R)
+    md.set_controls(0.0, 0, 0)
+    V = md.get_state()["V"].copy()
+    md.accelerations()
+    A = md.get_state()["A"].copy()
+    md.mdstep()
+    s1 = md.get_state()
+    md.set_controls(0.0, 1, 0)
+    md.mdstep()
+    s2 = md.get_state()
+    np.savez(os.path.join(OUT, "md_N4096.npz"), R=R, V=V, A=A, R1=s1["R"], V1=s1["V"], A1=s1["A"], R2=s2["R"], V2=s2["V"],
+             A2=s2["A"], **{k: c[k] for k in c})
+    print("md: A[:,0]=%s" % A[:, 0])
+
+
+def gen_mc408():
+    mc = po.RefMC408L()
+    c = mc.consts
+    rng = np.random.default_rng(11)
+    n = mc.N
+    psi = full_psi(rng, n, 7)
+    psi[:16] = 0.0
+    psi[:16, 1, 0] = 1.0
+    V = rng.normal(size=(3, n)) * 0.5
+    mc.set_state(V=V, psi=psi)
+    nsub = 62
+    for _ in range(nsub):
+        used = mc.qstep(np.full(n, NOJUMP))
+        assert used == n
+    o = mc.get_state()
+    keep = 512
+    np.savez(os.path.join(OUT, "mc408l_nojump.npz"), psi=psi[:keep], Vx=V[0, :keep], psi_out=o["psi"][:keep], nsub=nsub,
+             **{k: c[k] for k in c})
+    print("mc408l_nojump: %d substeps" % nsub)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    po.build()
+    gen_su_forces()
+    gen_su_nojump()
+    gen_su_jumps()
+    gen_su_stream()
+    gen_md()
+    gen_mc408()

@@ -1,0 +1,417 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (mdqtplasmasims_b200.Engine -> libmdqt_b200.so),
+against (a) the golden vectors produced by the unmodified reference (tests/golden, oracle/gen_golden.py) and (b) the
+oracle restatement (oracle/mdqt_oracle.c) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): forces <= 1e-12 relative, deterministic amplitudes <= 1e-10; positions and
+velocities <= 1e-12. Integer/branch outcomes (jump destinations, draws consumed) must be exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from mdqtplasmasims_b200 import (Engine, SCHEME_NONE, SCHEME_SR7, SCHEME_SR12, md_params, philox_uniforms, su_params,
+                                 synthetic)
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-12
+AMP_TOL = 1e-10
+RV_TOL = 1e-12
+NOJUMP = 0.99999
+
+
+def force_errors(F, Fref, R, L, kappa):
+    """max|dF|/max|F| and the per-ion error normalised by sum_j |f_ij| (computed in numpy for small N)."""
+    e_glob = np.abs(F - Fref).max() / np.abs(Fref).max()
+    n = R.shape[1]
+    d = R[:, :, None] - R[:, None, :]
+    d -= L * np.round(d / L)
+    r = np.sqrt((d ** 2).sum(axis=0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = np.where((r > 0) & (r < L / 2), (1 / r + kappa) * np.exp(-kappa * r) / r, 0.0)  # |f_ij| = prefactor * r
+    denom = f.sum(axis=1)
+    e_ion = (np.sqrt(((F - Fref) ** 2).sum(axis=0)) / denom).max()
+    return e_glob, e_ion
+
+
+def test_forces_golden_N3472(golden_dir):
+    g = np.load(os.path.join(golden_dir, "su_forces_N3472.npz"))
+    R, Fref = g["R"], g["F"]
+    N = R.shape[1]
+    p = su_params(n_ions=N)
+    assert abs(p.L - float(g["L"])) == 0.0 and abs(1 / p.kappa - float(g["lDeb"])) < 1e-15
+    eng = Engine(p)
+    eng.upload(R=R)
+    eng.forces()
+    F = eng.download_forces()
+    e_glob, e_ion = force_errors(F, Fref, R, p.L, p.kappa)
+    assert e_glob <= FORCE_TOL and e_ion <= FORCE_TOL, (e_glob, e_ion)
+    # Newton's third law: sum_i F_i ~ 0 to rounding
+    assert np.abs(F.sum(axis=1)).max() <= 1e-10 * np.abs(F).max()
+    # Epotential (SU:244-281)
+    assert abs(eng.Epotential() - float(g["Epot"])) <= 1e-12 * float(g["Epot"])
+    # idempotence / determinism: a second call gives bitwise identical forces
+    eng.forces()
+    assert np.array_equal(F, eng.download_forces())
+
+
+@pytest.mark.parametrize("n,kappa_ge", [(1, 0.1), (2, 0.1), (33, 0.1), (257, 0.3), (1000, 0.0833333)])
+def test_forces_vs_oracle_small_and_ragged(oracle, n, kappa_ge):
+    p = su_params(Ge=kappa_ge, N0=max(n, 8), n_ions=n)
+    R = synthetic.random_positions(n, p.L, seed=n)
+    eng = Engine(p)
+    eng.upload(R=R)
+    eng.forces()
+    F = eng.download_forces()
+    Fref = oracle.forces_su(R, p.L, 1 / p.kappa)
+    if n == 1:
+        assert np.all(F == 0.0)
+        return
+    scale = np.abs(Fref).max()
+    assert np.abs(F - Fref).max() <= FORCE_TOL * scale
+    assert abs(eng.Epotential() - oracle.epot_su(R, p.L, 1 / p.kappa)) <= 1e-12 * max(1.0, abs(oracle.epot_su(R, p.L, 1 / p.kappa)))
+
+
+def test_forces_unwrapped_positions_general_image(oracle):
+    """Coordinates outside [0,L] (several box lengths away) take the general rint() minimum-image path."""
+    n = 500
+    p = su_params(N0=n, n_ions=n)
+    rng = np.random.default_rng(3)
+    R = rng.uniform(-3 * p.L, 4 * p.L, size=(3, n))
+    eng = Engine(p)
+    eng.upload(R=R)
+    eng.forces()
+    F = eng.download_forces()
+    Fref = oracle.forces_su(R, p.L, 1 / p.kappa)
+    assert np.abs(F - Fref).max() <= 2e-12 * np.abs(Fref).max()
+
+
+def test_forces_coincident_and_cutoff_edge(oracle):
+    """Coincident ions (r = 0) are skipped like SU:222; pairs beyond L/2 contribute nothing."""
+    n = 64
+    p = su_params(N0=n, n_ions=n)
+    R = synthetic.random_positions(n, p.L, seed=5)
+    R[:, 1] = R[:, 0]  # coincident pair
+    eng = Engine(p)
+    eng.upload(R=R)
+    eng.forces()
+    F = eng.download_forces()
+    assert np.all(np.isfinite(F))
+    Fref = oracle.forces_su(R, p.L, 1 / p.kappa)
+    assert np.abs(F - Fref).max() <= FORCE_TOL * np.abs(Fref).max()
+
+
+def test_forces_md_family_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "md_N4096.npz"))
+    p = md_params(scheme=SCHEME_NONE, n_ions=4096, kappa=float(g["kappa"]), density=float(g["n"]))
+    assert p.L == float(g["L"])
+    eng = Engine(p)
+    eng.upload(R=g["R"], V=g["V"])
+    eng.forces()
+    A = eng.download_forces()
+    assert np.abs(A - g["A"]).max() <= FORCE_TOL * np.abs(g["A"]).max()
+    # MDStep (MD:504-511), collisionless, then with the three-axis laser friction term
+    dt = float(g["timeStep"])
+    eng.MDStep(dt=dt)
+    s = eng.download(("R", "V"))
+    assert np.abs(s["R"] - g["R1"]).max() <= RV_TOL * p.L
+    assert np.abs(s["V"] - g["V1"]).max() <= RV_TOL * np.abs(g["V1"]).max()
+    assert np.abs(eng.download_forces() - g["A1"]).max() <= 2e-12 * np.abs(g["A1"]).max()
+    coeff = 1.234e-6 * float(g["beta"]) / np.sqrt(float(g["n"]))
+    eng.MDStep(dt=dt, laser=1, laser_coeff=coeff)
+    s = eng.download(("R", "V"))
+    assert np.abs(s["R"] - g["R2"]).max() <= RV_TOL * p.L
+    assert np.abs(s["V"] - g["V2"]).max() <= 1e-11 * np.abs(g["V2"]).max()
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "d", "e"])
+def test_substeps_nojump_golden(golden_dir, case):
+    """nsub x {step(); qstep();} with no jumps vs the reference's own step()/qstep(): covers fracOfSig != 0,
+    tPart != 0, the t == 0 first-substep branch (SU:370-379) and the wrap (SU:381-389)."""
+    g = np.load(os.path.join(golden_dir, "su_nojump.npz"))
+    G = lambda k: g[case + "_" + k]
+    n, nsub = G("R").shape[1], int(G("nsub"))
+    p = su_params(fracOfSig=float(G("frac")), n_ions=n)
+    eng = Engine(p)
+    eng.upload(R=G("R"), V=G("V"), psi=G("psi"), tPart=G("tPart"), t=float(G("t0")), substep=0)
+    eng.upload_forces(G("F"))
+    eng.set_forced_uniforms(np.full((nsub, n, 5), NOJUMP))
+    eng.step_qstep(nsub)
+    s = eng.download()
+    assert np.abs(s["psi"] - G("psi_out")).max() <= AMP_TOL
+    assert np.abs(s["V"] - G("V_out")).max() <= RV_TOL
+    assert np.abs(s["R"] - G("R_out")).max() <= RV_TOL * p.L
+    assert np.abs(s["tPart"] - G("tPart_out")).max() <= 1e-15
+    assert s["t"] == float(G("t_out"))  # same repeated addition -> bitwise
+    assert np.all((s["R"] >= 0) & (s["R"] <= p.L))
+
+
+def test_jump_table_golden(golden_dir):
+    """All 18 (source, destination) branches of SU:573-703, forced through the uniforms; exact destinations/kicks."""
+    g = np.load(os.path.join(golden_dir, "su_jumps.npz"))
+    n = g["psi"].shape[0]
+    p = su_params(n_ions=n)
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=g["V"], psi=g["psi"], tPart=g["tPart"], t=1.0)
+    eng.upload_forces(np.zeros((3, n)))
+    eng.set_forced_uniforms(g["u5"][None])
+    eng.step_qstep(1)
+    s = eng.download()
+    assert np.array_equal(s["psi"], g["psi_out"])          # unit basis kets: exact
+    assert np.all(s["tPart"] == 0.0)
+    assert np.abs(s["V"][0] - g["V_out"][0]).max() <= 1e-18  # V_x + (+-vKick | +-vKickDP)
+
+
+def test_philox_stream_trajectory_golden(golden_dir):
+    """50 coupled substeps (2 MD steps) with the engine's own Philox stream, jumps included, against the reference
+    driven with the same uniforms (single-ion trick)."""
+    g = np.load(os.path.join(golden_dir, "su_stream.npz"))
+    n = g["R"].shape[1]
+    p = su_params(n_ions=n, N0=n)
+    p.L = float(g["L"]); p.rcut = p.L / 2; p.seed = int(g["seed"]); p.traj0 = int(g["traj"])
+    eng = Engine(p)
+    eng.upload(R=g["R"], V=g["V"], psi=g["psi"], tPart=g["tPart"], t=0.0, substep=0)
+    eng.md_steps(2)
+    s = eng.download()
+    # jump decisions must coincide: compare which ions sit in a basis ket / reset tPart
+    assert np.array_equal(s["tPart"] == 0.0, g["tPart_out"] == 0.0)
+    assert np.abs(s["psi"] - g["psi_out"]).max() <= AMP_TOL
+    assert np.abs(s["V"] - g["V_out"]).max() <= 1e-11
+    assert np.abs(s["R"] - g["R_out"]).max() <= 1e-11 * p.L
+    assert s["t"] == float(g["t_out"])
+
+
+def test_philox_device_matches_host_replica(oracle):
+    """Device Philox == host replica == oracle: a jump taken on the device at exactly the substep/ion the host
+    stream predicts (u0 compared with dp)."""
+    n, seed, traj = 256, 777, 5
+    u_host = philox_uniforms(seed, traj, n, 0)
+    u_orc = oracle.uniforms5(seed, traj, n, 0)
+    assert np.array_equal(u_host, u_orc)
+    p = su_params(n_ions=n, seed=seed, traj0=traj)
+    psi = synthetic.random_full_state(n, 12, seed=1)
+    V = np.zeros((3, n)); R = synthetic.random_positions(n, p.L, seed=2)
+    eng = Engine(p)
+    eng.upload(R=R, V=V, psi=psi, tPart=np.zeros(n), t=1.0, substep=0)
+    eng.upload_forces(np.zeros((3, n)))
+    eng.step_qstep(1)
+    s = eng.download()
+    from oracle import pyoracle as po
+    qp, _ = po.su_params()
+    psi_o, Vx, tp = psi.copy(), V[0].copy(), np.zeros(n)
+    _, used = oracle.qstep12(psi_o, Vx, tp, 1.0, qp, u_orc)
+    assert np.abs(s["psi"] - psi_o).max() <= AMP_TOL
+    assert np.abs(s["V"][0] - Vx).max() <= 1e-15
+
+
+def test_norm_drift_and_energy_conservation_lasers_off():
+    """Property tests: with Om = OmDP = 0 the P population stays 0, no jumps occur and the
+    plasma is a conservative system: total energy drift over 40 MD steps stays tiny; |psi|^2 stays 1."""
+    n = 1024
+    p = su_params(Om=0.0, OmDP=0.0, n_ions=n, N0=n)
+    eng = Engine(p)
+    R = synthetic.random_positions(n, p.L, seed=8)
+    psi = synthetic.random_s_state(n, 12, seed=8)
+    eng.upload(R=R, V=np.zeros((3, n)), psi=psi, tPart=np.zeros(n), t=0.0, substep=0)
+    d0 = eng.diagnostics()
+    e0 = d0["ekin_x"] + d0["ekin_y"] + d0["ekin_z"] + d0["epot"]
+    eng.md_steps(40)
+    d1 = eng.diagnostics()
+    e1 = d1["ekin_x"] + d1["ekin_y"] + d1["ekin_z"] + d1["epot"]
+    assert abs(e1 - e0) <= 2e-3 * abs(d1["ekin_x"] + d1["ekin_y"] + d1["ekin_z"]) + 1e-9
+    s = eng.download()
+    norm = (s["psi"] ** 2).sum(axis=(1, 2))
+    assert np.abs(norm - 1).max() <= 1e-12
+    assert np.all(s["tPart"] > 0)  # nobody jumped
+
+
+def test_norm_drift_bound_with_lasers():
+    n = 512
+    p = su_params(n_ions=n, N0=n)
+    eng = Engine(p)
+    eng.upload(R=synthetic.random_positions(n, p.L, seed=9), V=np.zeros((3, n)), psi=synthetic.random_s_state(n, 12, seed=9),
+               tPart=np.zeros(n), t=0.0, substep=0)
+    eng.md_steps(8)  # 200 substeps
+    s = eng.download()
+    norm = (s["psi"] ** 2).sum(axis=(1, 2))
+    assert np.abs(norm - 1).max() < 3e-4  # reference-measured drift bound
+    pops = eng.populations()
+    assert np.abs(pops.sum(axis=1) - norm).max() <= 1e-14
+    assert 0.05 < pops[:, 1].mean() < 0.5  # P population builds up under the cooling lasers
+
+
+def test_ensemble_batch_equals_single_trajectories():
+    """An ensemble shard batched in one handle (n_traj = 3) reproduces three single-trajectory runs bitwise."""
+    n, B = 300, 3
+    base = dict(n_ions=n, N0=n, seed=4242)
+    R = np.stack([synthetic.random_positions(n, su_params(**base).L, seed=20 + b) for b in range(B)])
+    psi = np.stack([synthetic.random_s_state(n, 12, seed=30 + b) for b in range(B)])
+    V = np.zeros((B, 3, n)); tp = np.zeros((B, n))
+    eb = Engine(su_params(n_traj=B, traj0=10, **base))
+    eb.upload(R=R, V=V, psi=psi, tPart=tp, t=0.0, substep=0)
+    eb.md_steps(3)
+    sb = eb.download()
+    for b in range(B):
+        e1 = Engine(su_params(n_traj=1, traj0=10 + b, **base))
+        e1.upload(R=R[b], V=V[b], psi=psi[b], tPart=tp[b], t=0.0, substep=0)
+        e1.md_steps(3)
+        s1 = e1.download()
+        # the j-split plan depends on (N, B), so sums may differ in rounding between B=3 and B=1 handles
+        assert np.abs(sb["R"][b] - s1["R"]).max() <= 1e-9
+        assert np.abs(sb["psi"][b] - s1["psi"]).max() <= 1e-7
+        assert np.array_equal(sb["tPart"][b] == 0.0, s1["tPart"] == 0.0)
+
+
+def test_row_decomposition_bitwise_identical():
+    """i-row decomposition (the multi-GPU large-N path) emulated on one GPU: handles owning row blocks of the same
+    system produce forces bitwise identical to the single-handle result (G-independent j summation order)."""
+    n = 2000
+    p = su_params(n_ions=n, N0=n)
+    R = synthetic.random_positions(n, p.L, seed=77)
+    full = Engine(p)
+    full.upload(R=R)
+    full.forces()
+    F = full.download_forces()
+    for G in (2, 4, 8):
+        rows = n // G
+        for g in range(G):
+            e = Engine(su_params(n_ions=n, N0=n, row0=g * rows, n_rows=rows))
+            e.upload(R=R)
+            e.forces()
+            Fg = e.download_forces()
+            assert np.array_equal(Fg[:, g * rows:(g + 1) * rows], F[:, g * rows:(g + 1) * rows])
+
+
+def test_diagnostics_vs_numpy():
+    n = 777
+    p = su_params(n_ions=n, N0=n)
+    V = synthetic.maxwellian(n, 0.05, seed=3)
+    V[0] += 0.01
+    eng = Engine(p)
+    eng.upload(R=synthetic.random_positions(n, p.L, seed=4), V=V, psi=synthetic.random_full_state(n, 12, seed=5), tPart=np.zeros(n))
+    d = eng.diagnostics()
+    avg = V[0].mean()
+    assert abs(d["vx_avg"] - avg) <= 1e-15
+    assert abs(d["ekin_x"] - 0.5 * ((V[0] - avg) ** 2).mean()) <= 1e-15
+    assert abs(d["ekin_y"] - 0.5 * (V[1] ** 2).mean()) <= 1e-15
+    assert abs(d["ekin_z"] - 0.5 * (V[2] ** 2).mean()) <= 1e-15
+    pv = eng.vel_dist()
+    vel = np.arange(2001) * 0.0025
+    V2 = 1. / (2. * 0.002 * 0.002)
+    for c, off in ((0, avg), (1, 0.0), (2, 0.0)):
+        v = V[c] - off
+        ref = (np.exp(-V2 * (vel[:, None] - v[None, :]) ** 2) + np.exp(-V2 * (vel[:, None] + v[None, :]) ** 2)).sum(axis=1)
+        ref /= 6.0 * np.sqrt(2 * np.pi * 0.002 * 0.002)
+        assert np.abs(pv[c] - ref).max() <= 1e-11 * ref.max()
+
+
+def test_qstep7_golden_and_jumps(golden_dir, oracle):
+    g = np.load(os.path.join(golden_dir, "mc408l_nojump.npz"))
+    n, nsub = g["psi"].shape[0], int(g["nsub"])
+    p = md_params(scheme=SCHEME_SR7, n_ions=n, kappa=float(g["kappa"]), density=float(g["n"]), timeStep=float(g["timeStep"]))
+    assert p.substeps_per_md == int(g["ratio"]) and p.dtq == float(g["dtq"])
+    V = np.zeros((3, n)); V[0] = g["Vx"]
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=g["psi"])
+    eng.set_forced_uniforms(np.full((nsub, n, 5), NOJUMP))
+    eng.qstep7(nsub)
+    s = eng.download(("psi", "V"))
+    assert np.abs(s["psi"] - g["psi_out"]).max() <= AMP_TOL
+    assert np.array_equal(s["V"], V)  # the pump stage never kicks (MC408L:754)
+    # jumps: device with forced uniforms vs the restatement (pinned to MC408L's own qstep in the CPU suite)
+    from oracle import pyoracle as po
+    qp, _ = po.mc408_params(n=float(g["n"]))
+    rng = np.random.default_rng(4)
+    u5 = rng.uniform(size=(1, n, 5)); u5[0, ::2, 0] = 1e-12
+    psi0 = s["psi"].copy()
+    eng.set_forced_uniforms(u5)
+    eng.qstep7(1)
+    s2 = eng.download(("psi",))
+    psi_o = psi0.copy()
+    oracle.qstep7(psi_o, V[0].copy(), qp, u5[0])
+    assert np.abs(s2["psi"] - psi_o).max() <= AMP_TOL
+    jumped = (np.abs(psi_o) == 1.0).any(axis=(1, 2))
+    assert jumped[::2].all() and np.array_equal(s2["psi"][jumped], psi_o[jumped])
+
+
+def test_qstep7_quad_mask(oracle):
+    from oracle import pyoracle as po
+    n = 128
+    p = md_params(scheme=SCHEME_SR7, n_ions=n, density=2.0, detuning=0.0, Om=2.0, quad=1)
+    qp, _ = po.mc408_params(n=2.0, detuning=0.0, Om=2.0, quad=1)
+    psi = synthetic.random_full_state(n, 7, seed=6)
+    V = synthetic.maxwellian(n, 0.5, seed=6)
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=psi)
+    eng.set_forced_uniforms(np.full((10, n, 5), NOJUMP))
+    eng.qstep7(10)
+    psi_o = psi.copy()
+    for _ in range(10):
+        oracle.qstep7(psi_o, V[0].copy(), qp, np.full((n, 5), NOJUMP))
+    assert np.abs(eng.download(("psi",))["psi"] - psi_o).max() <= AMP_TOL
+
+
+def test_andersen_collisions(oracle):
+    """stepVelocities with collisions (MD:476-482): forced draws reproduce the restatement exactly; Philox draws
+    give a Maxwellian of the requested width at the requested rate."""
+    n = 4096
+    p = md_params(scheme=SCHEME_NONE, n_ions=n, kappa=0.5, density=0.4)
+    R = synthetic.random_positions(n, p.L, seed=1)
+    V = synthetic.maxwellian(n, np.sqrt(1 / 3.), seed=2)
+    dt, freq, sig = 0.005, 40.0, np.sqrt(1 / 3.)
+    rng = np.random.default_rng(3)
+    cu, cn = rng.uniform(size=n), rng.normal(size=(n, 3)) * sig
+    eng = Engine(p)
+    eng.upload(R=R, V=V)
+    eng.forces()
+    A0 = eng.download_forces()
+    eng.set_forced_collisions(cu, cn)
+    eng.MDStep(dt=dt, collisionFreq=freq, sigma_v=sig)
+    s = eng.download(("R", "V"))
+    A1 = eng.download_forces()
+    Vo = V.copy()
+    oracle.vv_velocities(Vo, A0, A1, dt, collisionFreq=freq, coll_u=cu, coll_n=cn)
+    assert np.abs(s["V"] - Vo).max() <= 1e-14
+    collided = cu < dt * freq
+    assert np.array_equal(s["V"][:, collided], cn[collided].T)
+    # Philox-driven thermostat: everybody collides (freq large) -> V ~ N(0, sig^2)
+    eng.set_forced_collisions(None, None)
+    eng.MDStep(dt=dt, collisionFreq=1e9, sigma_v=sig)
+    v = eng.download(("V",))["V"]
+    assert abs(v.mean()) < 5 * sig / np.sqrt(3 * n)
+    assert abs(v.std() - sig) < 0.02 * sig
+    from scipy import stats
+    assert stats.kstest(v.ravel() / sig, "norm").pvalue > 1e-4
+
+
+def test_e2e_host_call_matches_resident():
+    n = 400
+    p = su_params(n_ions=n, N0=n, seed=5)
+    R = synthetic.random_positions(n, p.L, seed=1); V = np.zeros((3, n))
+    psi = synthetic.random_s_state(n, 12, seed=1); tp = np.zeros(n)
+    a = Engine(p)
+    a.upload(R=R, V=V, psi=psi, tPart=tp, t=0.0, substep=0)
+    a.md_steps(2)
+    sa = a.download()
+    b = Engine(p)
+    R2, V2, psi2, tp2 = R.copy(), V.copy(), psi.copy(), tp.copy()
+    b.md_steps_host(2, R2, V2, psi2, tp2)
+    assert np.array_equal(R2, sa["R"]) and np.array_equal(V2, sa["V"]) and np.array_equal(psi2, sa["psi"])
+
+
+def test_error_paths():
+    from mdqtplasmasims_b200 import MDQTError
+    p = su_params(n_ions=16, N0=16)
+    p.rcut = p.L  # > L/2
+    with pytest.raises(MDQTError):
+        Engine(p)
+    p = su_params(n_ions=0)
+    with pytest.raises(MDQTError):
+        Engine(p)
+    e = Engine(md_params(scheme=SCHEME_NONE, n_ions=32))
+    with pytest.raises(MDQTError):
+        e.step_qstep(1)  # no wavefunctions in this handle
+    e7 = Engine(md_params(scheme=SCHEME_SR7, n_ions=32, density=2.0))
+    with pytest.raises(MDQTError):
+        e7.md_steps(1)
