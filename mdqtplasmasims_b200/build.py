@@ -25,21 +25,22 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    if not force and not needs_build() and out is None:
         return LIB
+    out = out or LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++",
-           "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+           "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"] + ["-D" + d for d in defines] + [
+           "-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
-    out = subprocess.run(cmd, capture_output=True, text=True)
-    if out.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + out.stdout + out.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(out.stderr)
-    return LIB
+        print(res.stderr)
+    return out
 
 
 if __name__ == "__main__":

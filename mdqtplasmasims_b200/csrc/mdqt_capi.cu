@@ -7,6 +7,7 @@
 #include "mdqt_qtconsts.h"
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -116,6 +117,13 @@ static void plan_force(mdqt_handle* h) {
     if (cost < best * 0.999) { best = cost; best_ns = real_ns; best_jlen = jlen; }
   }
   h->nsplit = best_ns; h->jlen = best_jlen; h->ipt = ipt;
+  // developer tuning knobs (kernel A/B runs): override the plan
+  if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("MDQT_FORCE_NSPLIT")) {
+    int ns = std::max(1, std::min(1024, atoi(e)));
+    h->jlen = ((N + ns - 1) / ns + 7) & ~7;
+    h->nsplit = (N + h->jlen - 1) / h->jlen;
+  }
   h->itiles = (h->nrows + kForceThreads - 1) / kForceThreads;  // upper bound on i-tiles of this handle
 }
 

@@ -15,6 +15,10 @@
 #include "mdqt_internal.h"
 #include <math.h>
 
+#ifndef MDQT_PAIR_VARIANT
+#define MDQT_PAIR_VARIANT 2
+#endif
+
 namespace mdqt {
 
 __constant__ double c_exp2tab[kExpTable];
@@ -26,7 +30,7 @@ void upload_exp_table() {
 }
 
 struct PairConsts {
-  double L, halfL, invL, kappa, negkappa, nk_scale, negc;
+  double L, halfL, invL, kappa, negkappa, nk_scale, negc, rc2;
   long long rc2bits_m1;
 };
 
@@ -35,7 +39,7 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a) {
   c.L = a.L; c.halfL = a.halfL; c.invL = a.invL; c.kappa = a.kappa; c.negkappa = -a.kappa;
   c.nk_scale = -a.kappa * 184.66496523378731614207035916824219;  // 128 * log2(e)
   c.negc = -0.0054152123481245727298221259488920044;     // -ln2 / 128
-  c.rc2bits_m1 = __double_as_longlong(a.rc2) - 1;
+  c.rc2bits_m1 = __double_as_longlong(a.rc2) - 1; c.rc2 = a.rc2;
   return c;
 }
 
@@ -43,7 +47,7 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a) {
 
 template <bool WRAPPED>
 __device__ __forceinline__ double min_image(double d, const PairConsts& c) {
-  if (WRAPPED) {
+  if (WRAPPED && MDQT_PAIR_VARIANT == 0) {
     // coordinates in [0,L] => |d| <= L => round(d/L) is -1, 0 or +1 (SU:218): one conditional shift is exact
     return (fabs(d) > c.halfL) ? d - copysign(c.L, d) : d;
   } else {
@@ -57,7 +61,11 @@ __device__ __forceinline__ double min_image(double d, const PairConsts& c) {
 __device__ __forceinline__ void pair_core(double dx, double dy, double dz, const PairConsts& c, const double* tab,
                                           double& rinv, double& ef, bool& valid) {
   double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+#if MDQT_PAIR_VARIANT >= 2
+  valid = (r2 < c.rc2) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0)
+#else
   valid = (unsigned long long)(__double_as_longlong(r2) - 1) < (unsigned long long)c.rc2bits_m1;
+#endif
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));  // MUFU.RSQ64H: ~2^-20 relative
   double t = r2 * y;

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmdqt_b200.so")
+LIB_PATH = os.environ.get("MDQT_LIB_PATH") or os.path.join(HERE, "libmdqt_b200.so")  # env: kernel A/B builds
 
 SCHEME_NONE, SCHEME_SR7, SCHEME_SR12 = 0, 7, 12
 c_double_p = ctypes.POINTER(ctypes.c_double)
