@@ -239,9 +239,10 @@ def run_ours(args):
 
     # ---- extra: large-N row decomposition with an NCCL all-gather of positions per MD step (config 5 shape) -----------------
     if args.large_n > 0:
+        from mdqtplasmasims_b200 import sharding
         NL = (args.large_n // world) * world
-        rows = NL // world
-        pl = su_params(n_ions=NL, N0=NL, row0=rank * rows, n_rows=rows, seed=777, device=local)
+        row0, rows = sharding.row_block(NL, world, rank)
+        pl = su_params(n_ions=NL, N0=NL, row0=row0, n_rows=rows, seed=777, device=local)
         el = Engine(pl)
         from mdqtplasmasims_b200 import synthetic
         Rl = synthetic.random_positions(NL, pl.L, seed=777)
@@ -257,9 +258,8 @@ def run_ours(args):
             el.forces()
             el.step_qstep(25)
             if world > 1:
-                with torch.cuda.stream(ls):
-                    for c in range(3):
-                        dist.all_gather_into_tensor(Rdev[c, :NL], Rdev[c, rank * rows:(rank + 1) * rows])
+                with torch.cuda.stream(ls):  # the collective is ordered after the substep kernel on the engine's stream
+                    sharding.allgather_positions(Rdev, NL, world, rank, dist)
 
         md_step_large(); el.sync(); torch.cuda.synchronize(); barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

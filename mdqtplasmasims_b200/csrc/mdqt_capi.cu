@@ -102,20 +102,25 @@ int mdqt_params_md(mdqt_params* p, int scheme, int n_ions, double kappa, double 
 // j-range decomposition: a function of (N, B) only, so that every rank of a row-decomposed run sums the same
 // j-chunks in the same order (bitwise identical forces for any GPU count).
 static void plan_force(mdqt_handle* h) {
+  // Cost model (fitted to B200 timings, profiles/): the kernel is issue-bound, so an SM's time is the work of the
+  // CTAs assigned to it -- ceil(ctas/148) x (jlen + fixed CTA overhead) x rows per thread -- as long as >= 4 CTAs
+  // are co-resident; two rows per thread amortise the shared-memory reads (~3 % fewer issue slots per pair).
   const int N = h->N, B = h->B;
-  const bool big = (long long)N * B >= 148LL * 4 * kForceThreads * 2;
-  const int ipt = big ? 2 : 1;
-  const long long tiles = ((long long)N + kForceThreads * ipt - 1) / (kForceThreads * ipt) * B;
-  const long long slots = 148LL * (big ? 5 : 8);
-  double best = 1e300; int best_ns = 1, best_jlen = N;
-  for (int ns = 1; ns <= 64; ns++) {
-    int jlen = ((N + ns - 1) / ns + 7) & ~7;
-    int real_ns = (N + jlen - 1) / jlen;
-    long long ctas = tiles * real_ns;
-    long long waves = (ctas + slots - 1) / slots;
-    double cost = (double)waves * (jlen + 48 + 2 * real_ns);
-    if (cost < best * 0.999) { best = cost; best_ns = real_ns; best_jlen = jlen; }
+  double best = 1e300; int best_ns = 1, best_jlen = N, best_ipt = 1;
+  for (int ipt = 1; ipt <= 2; ipt++) {
+    const long long tiles = ((long long)N + kForceThreads * ipt - 1) / (kForceThreads * ipt) * B;
+    for (int ns = 1; ns <= 64; ns++) {
+      int jlen = ((N + ns - 1) / ns + 7) & ~7;
+      int real_ns = (N + jlen - 1) / jlen;
+      long long ctas = tiles * real_ns;
+      double per_sm = (double)ctas / 148.0;
+      // +1: expected load imbalance of one CTA per SM; below ~3.5 CTAs (14 warps) per SM the issue slots starve
+      double sat = per_sm >= 3.5 ? 1.0 : per_sm / 3.5;
+      double cost = (per_sm + 1.0) * (jlen + 60 + 2 * real_ns) * ipt * (ipt == 2 ? 0.97 : 1.0) / sat;
+      if (cost < best * 0.999) { best = cost; best_ns = real_ns; best_jlen = jlen; best_ipt = ipt; }
+    }
   }
+  const int ipt = best_ipt;
   h->nsplit = best_ns; h->jlen = best_jlen; h->ipt = ipt;
   // developer tuning knobs (kernel A/B runs): override the plan
   if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = atoi(e) == 2 ? 2 : 1;
@@ -293,6 +298,7 @@ static ForceArgs force_args(mdqt_handle* h) {
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.wrapped = h->wrapped;
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
+  a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   return a;
 }
 

@@ -6,17 +6,22 @@
 // N(N-1)/2 unordered pairs with a racy OpenMP scatter; here every ion row i gathers over ALL j (N^2 ordered
 // pair-interactions per call), which needs no scatter and sums in a fixed order.
 //
-// Bound: the FP64 pipe (64 DFMA/clk/SM). Memory traffic is negligible (24 B per j per CTA, staged in shared memory
-// and broadcast). Per ordered pair the FP64 pipe executes ~35 instructions:
-//   3 (delta) + 6 (minimum image: compare + shift) + 3 (r^2) + 5 (rsqrt: MUFU seed + one 3rd-order Newton step)
-//   + 1 (r) + 10 (exp(-kappa r): magic-number range reduction to |rr|<=ln2/256, 128-entry 2^(j/128) table in shared
-//   memory, degree-5 polynomial, exponent patched with integer adds) + 4 (prefactor) + 3 (accumulate).
-// The cut-off / self-pair mask is done with integer compares on the bit pattern of r^2 so that it costs no FP64 issue.
+// Bound: the FP64 pipe (64 lanes/clk/SM). Memory traffic is negligible (24 B per j per CTA, staged in shared memory
+// and broadcast). Two formulations of the pair geometry are compiled (MDQT_PAIR_VARIANT):
+//   3 (default) PERIODIC FIXED POINT: coordinates are converted once per CTA pass to 64-bit integers in units of
+//     L/2^64, so that the two's-complement difference x_i - x_j IS the minimum image (the reference's
+//     d -= L*round(d/L), SU:218-220) -- for free, for any (wrapped or unwrapped) input, and exactly: differences are
+//     formed without rounding and converted to double with 53-bit relative precision. Delta + minimum image cost
+//     2 integer adds + 1 int->fp64 conversion per component and NO FP64-pipe instruction.
+//   2 fp64 magic-number rint: t = fma(d,1/L,1.5*2^52); n = t-1.5*2^52; d = fma(-L,n,d): 3+9 FP64 instructions.
+// The rest is common: r^2 (3), 1/r = MUFU.RSQ64H seed + one 3rd-order Newton step (5), r (1), cut-off DSETP (1),
+// exp(-kappa r) by magic-number reduction to |rr| <= ln2/256 + a 128-entry 2^(j/128) table in shared memory + a
+// degree-5 polynomial with the exponent patched by integer adds (10), prefactor (4), accumulate (3).
 #include "mdqt_internal.h"
 #include <math.h>
 
 #ifndef MDQT_PAIR_VARIANT
-#define MDQT_PAIR_VARIANT 2
+#define MDQT_PAIR_VARIANT 3
 #endif
 
 namespace mdqt {
@@ -29,56 +34,70 @@ void upload_exp_table() {
   cudaMemcpyToSymbol(c_exp2tab, tab, sizeof(tab));
 }
 
+#define MDQT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: adding it rounds to nearest integer */
+#define MDQT_2P62 4611686018427387904.0
+#define MDQT_2P64 18446744073709551616.0
+
+// Everything the pair loop needs, in the length unit `u` of the chosen formulation (u = 1 for variant 2,
+// u = L/2^64 for the fixed-point variant): kappa*u, (rcut/u)^2, and the exp reduction constants.
 struct PairConsts {
-  double L, halfL, invL, kappa, negkappa, nk_scale, negc, rc2;
-  long long rc2bits_m1;
+  double L, invL, invL_lo;
+  double kappa_u, negkappa_u, nk_scale, negc, rc2_u;
+  double out_scale;  // 1/u^2 for forces, 1/u for the potential energy
 };
 
-__device__ __forceinline__ PairConsts make_consts(const ForceArgs& a) {
+__device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot) {
   PairConsts c;
-  c.L = a.L; c.halfL = a.halfL; c.invL = a.invL; c.kappa = a.kappa; c.negkappa = -a.kappa;
-  c.nk_scale = -a.kappa * 184.66496523378731614207035916824219;  // 128 * log2(e)
-  c.negc = -0.0054152123481245727298221259488920044;     // -ln2 / 128
-  c.rc2bits_m1 = __double_as_longlong(a.rc2) - 1; c.rc2 = a.rc2;
+  c.L = a.L; c.invL = a.invL; c.invL_lo = a.invL_lo;
+#if MDQT_PAIR_VARIANT == 3
+  const double u = a.L / MDQT_2P64;
+#else
+  const double u = 1.0;
+#endif
+  c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
+  c.nk_scale = -c.kappa_u * 184.66496523378731614207035916824219;  // 128 * log2(e)
+  c.negc = -0.0054152123481245727298221259488920044;               // -ln2 / 128
+  const double rc_u = sqrt(a.rc2) / u;
+  c.rc2_u = rc_u * rc_u;
+  c.out_scale = epot ? 1.0 / u : (1.0 / u) * (1.0 / u);
   return c;
 }
 
-#define MDQT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: adding it rounds to nearest integer */
-
-template <bool WRAPPED>
-__device__ __forceinline__ double min_image(double d, const PairConsts& c) {
-  if (WRAPPED && MDQT_PAIR_VARIANT == 0) {
-    // coordinates in [0,L] => |d| <= L => round(d/L) is -1, 0 or +1 (SU:218): one conditional shift is exact
-    return (fabs(d) > c.halfL) ? d - copysign(c.L, d) : d;
-  } else {
-    double t = fma(d, c.invL, MDQT_MAGIC);
-    double n = t - MDQT_MAGIC;
-    return fma(-c.L, n, d);
-  }
+// x (any real) -> periodic fixed point: round(frac(x/L) * 2^64) mod 2^64, accurate to ~L*2^-62.
+// x/L is formed in double-double (product residual by FMA + the rounding error of 1/L), so that two nearby ions keep
+// their exact separation (the reference's x_i - x_j is exact for nearby ions by Sterbenz' lemma).
+__device__ __forceinline__ long long to_fixed(double x, const PairConsts& c) {
+  double q = x * c.invL;
+  double ql = fma(x, c.invL, -q) + x * c.invL_lo;
+  double n = (q + MDQT_MAGIC) - MDQT_MAGIC;  // rint(q), |q| < 2^51
+  double f = q - n;                          // exact, in [-1/2, 1/2]
+  long long a = __double2ll_rn(f * MDQT_2P62) + __double2ll_rn(ql * MDQT_2P62);
+  return (long long)((unsigned long long)a << 2);
 }
 
-// Returns through (rinv, ef, valid): 1/r, exp(-kappa r), and whether 0 < r^2 < rcut^2.
-__device__ __forceinline__ void pair_core(double dx, double dy, double dz, const PairConsts& c, const double* tab,
-                                          double& rinv, double& ef, bool& valid) {
-  double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
-#if MDQT_PAIR_VARIANT >= 2
-  valid = (r2 < c.rc2) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0)
-#else
-  valid = (unsigned long long)(__double_as_longlong(r2) - 1) < (unsigned long long)c.rc2bits_m1;
-#endif
+__device__ __forceinline__ double min_image_fp(double d, const PairConsts& c) {
+  double t = fma(d, c.invL, MDQT_MAGIC);
+  double n = t - MDQT_MAGIC;
+  return fma(-c.L, n, d);
+}
+
+// From r2 (in units u^2): rinv = 1/r, ef = exp(-kappa r), valid = 0 < r2 < rcut^2.
+__device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const double* tab, double& rinv, double& ef,
+                                          bool& valid) {
+  valid = (r2 < c.rc2_u) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0; SU:222)
   double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));  // MUFU.RSQ64H: ~2^-20 relative
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));  // MUFU.RSQ64H seed
   double t = r2 * y;
   double e = fma(-t, y, 1.0);                 // 1 - r2 y^2
   double p = fma(0.375, e, 0.5);
   double ye = y * e;
-  y = fma(ye, p, y);                          // y (1 + e/2 + 3 e^2/8): error O(e^3) ~ 2^-60
+  y = fma(ye, p, y);                          // y (1 + e/2 + 3 e^2/8): the scheme of CUDA's own rsqrt(double)
   double r = r2 * y;
   // exp(x), x = -kappa r <= 0:  x = (128 q + idx) ln2/128 + rr
   double tt = fma(r, c.nk_scale, MDQT_MAGIC);
   int n = __double2loint(tt);
   double nd = tt - MDQT_MAGIC;
-  double x = c.negkappa * r;
+  double x = c.negkappa_u * r;
   double rr = fma(nd, c.negc, x);
   double q = fma(rr, 8.3333333333333332e-03, 4.1666666666666664e-02);
   q = fma(q, rr, 1.6666666666666666e-01);
@@ -93,63 +112,84 @@ __device__ __forceinline__ void pair_core(double dx, double dy, double dz, const
 
 constexpr int kTJ = 512;  // j positions staged per pass
 
-template <int IPT, bool WRAPPED, bool EPOT>
+template <int IPT, bool EPOT>
 __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
+#if MDQT_PAIR_VARIANT == 3
+  typedef long long coord_t;
+  __shared__ longlong2 sxy[kTJ];
+  __shared__ long long sz[kTJ];
+#else
+  typedef double coord_t;
   __shared__ double2 sxy[kTJ];
   __shared__ double sz[kTJ];
+#endif
   __shared__ double stab[kExpTable];
   __shared__ double sred[kForceThreads / 32];
   __shared__ int s_last;
 
   const int tid = threadIdx.x;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
-  const PairConsts c = make_consts(a);
+  const PairConsts c = make_consts(a, EPOT);
   const double* __restrict__ X = a.R + (size_t)b * 3 * a.ld;
   const double* __restrict__ Y = X + a.ld;
   const double* __restrict__ Z = Y + a.ld;
   for (int k = tid; k < kExpTable; k += kForceThreads) stab[k] = c_exp2tab[k];
 
   int irow[IPT];
-  double xi[IPT], yi[IPT], zi[IPT], ax[IPT], ay[IPT], az[IPT];
+  coord_t xi[IPT], yi[IPT], zi[IPT];
+  double ax[IPT], ay[IPT], az[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     irow[k] = a.row0 + tile * (kForceThreads * IPT) + k * kForceThreads + tid;
-    bool ok = irow[k] < a.row0 + a.nrows;
-    xi[k] = ok ? X[irow[k]] : 3e300;
-    yi[k] = ok ? Y[irow[k]] : 3e300;
-    zi[k] = ok ? Z[irow[k]] : 3e300;
+    const int ir = min(irow[k], a.row0 + a.nrows - 1);  // idle threads shadow the last row (never stored)
+#if MDQT_PAIR_VARIANT == 3
+    xi[k] = to_fixed(X[ir], c); yi[k] = to_fixed(Y[ir], c); zi[k] = to_fixed(Z[ir], c);
+#else
+    xi[k] = X[ir]; yi[k] = Y[ir]; zi[k] = Z[ir];
+#endif
     ax[k] = ay[k] = az[k] = 0.0;
   }
   const int jbeg = js * a.jlen;
   const int jend = min(a.N, jbeg + a.jlen);
   for (int jc = jbeg; jc < jend; jc += kTJ) {
+    const int cnt = min(kTJ, jend - jc);
     __syncthreads();
-    for (int k = tid; k < kTJ; k += kForceThreads) {
-      int j = jc + k;
-      bool ok = j < jend;
-      sxy[k] = make_double2(ok ? X[j] : 1e300, ok ? Y[j] : 1e300);
-      sz[k] = ok ? Z[j] : 1e300;
+    for (int k = tid; k < cnt; k += kForceThreads) {
+      const int j = jc + k;
+#if MDQT_PAIR_VARIANT == 3
+      sxy[k] = make_longlong2(to_fixed(X[j], c), to_fixed(Y[j], c));
+      sz[k] = to_fixed(Z[j], c);
+#else
+      sxy[k] = make_double2(X[j], Y[j]);
+      sz[k] = Z[j];
+#endif
     }
     __syncthreads();
-    const int cnt = min(kTJ, jend - jc);
-    const int nloop = (cnt + 3) & ~3;  // padded entries are sentinels (masked by the cut-off)
 #pragma unroll 4
-    for (int jj = 0; jj < nloop; jj++) {
-      const double2 pxy = sxy[jj];
-      const double pz = sz[jj];
+    for (int jj = 0; jj < cnt; jj++) {
+      const auto pxy = sxy[jj];
+      const coord_t pz = sz[jj];
 #pragma unroll
       for (int k = 0; k < IPT; k++) {
-        double dx = min_image<WRAPPED>(xi[k] - pxy.x, c);
-        double dy = min_image<WRAPPED>(yi[k] - pxy.y, c);
-        double dz = min_image<WRAPPED>(zi[k] - pz, c);
+#if MDQT_PAIR_VARIANT == 3
+        // two's-complement wrap-around == minimum image; exact difference, one rounding in the conversion
+        const double dx = __ll2double_rn((long long)((unsigned long long)xi[k] - (unsigned long long)pxy.x));
+        const double dy = __ll2double_rn((long long)((unsigned long long)yi[k] - (unsigned long long)pxy.y));
+        const double dz = __ll2double_rn((long long)((unsigned long long)zi[k] - (unsigned long long)pz));
+#else
+        const double dx = min_image_fp(xi[k] - pxy.x, c);
+        const double dy = min_image_fp(yi[k] - pxy.y, c);
+        const double dz = min_image_fp(zi[k] - pz, c);
+#endif
+        const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
         double rinv, ef;
         bool valid;
-        pair_core(dx, dy, dz, c, stab, rinv, ef, valid);
+        pair_core(r2, c, stab, rinv, ef, valid);
         if (EPOT) {
           double u = ef * rinv;                       // exp(-r/lDeb)/r (SU:268)
           ax[k] += valid ? u : 0.0;
         } else {
-          double f = (ef * (rinv * rinv)) * (rinv + c.kappa);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
+          double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
           f = valid ? f : 0.0;
           ax[k] = fma(f, dx, ax[k]);
           ay[k] = fma(f, dy, ay[k]);
@@ -158,6 +198,8 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
       }
     }
   }
+#pragma unroll
+  for (int k = 0; k < IPT; k++) { ax[k] *= c.out_scale; ay[k] *= c.out_scale; az[k] *= c.out_scale; }
 
   if (EPOT) {
     // fixed-order block reduction -> one partial per CTA
@@ -208,6 +250,7 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   for (int k = 0; k < IPT; k++)
     if (irow[k] < a.row0 + a.nrows) {
       double sx = 0.0, sy = 0.0, szz = 0.0;
+#pragma unroll 4
       for (int s = 0; s < a.nsplit; s++) {
         const double* Fp = a.Fpart + ((size_t)s * a.B + b) * 3 * a.ld;
         sx += __ldcg(&Fp[irow[k]]); sy += __ldcg(&Fp[a.ld + irow[k]]); szz += __ldcg(&Fp[2 * a.ld + irow[k]]);
@@ -217,21 +260,12 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
     }
 }
 
-// two rows per thread once there are enough rows to fill the machine (halves shared-memory traffic per pair);
-// decided by the planner from (N, B) only
-static int pick_ipt(const ForceArgs& a) { return a.ipt == 2 ? 2 : 1; }
-
 template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
-  int ipt = pick_ipt(a);
+  const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread: decided by the planner from (N, B) only
   dim3 grid((a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt), a.nsplit, a.B);
-  if (ipt == 2) {
-    if (a.wrapped) k_pairs<2, true, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
-    else k_pairs<2, false, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
-  } else {
-    if (a.wrapped) k_pairs<1, true, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
-    else k_pairs<1, false, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
-  }
+  if (ipt == 2) k_pairs<2, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
+  else k_pairs<1, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
 }
 
 void launch_forces(const ForceArgs& a, cudaStream_t s) { launch_pairs<false>(a, nullptr, s); }
@@ -257,15 +291,16 @@ __global__ void k_epot_final(const double* __restrict__ partials, int per_traj, 
 
 void launch_epot(const ForceArgs& a, double* partials, double* result, cudaStream_t s) {
   launch_pairs<true>(a, partials, s);
-  int ipt = pick_ipt(a);
+  const int ipt = a.ipt == 2 ? 2 : 1;
   int tiles = (a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt);
   // ordered pairs counted twice -> 1/2; per particle -> 1/N (SU:272)
   k_epot_final<<<a.B, 256, 0, s>>>(partials, tiles * a.nsplit, 0.5 / (double)a.N, result);
 }
 
-// ---- FP64 peak probe: 8 independent DFMA chains per thread ----
+// ---- FP64 peak probe: 8 independent DFMA chains per thread, all-register operands ----
 __global__ void __launch_bounds__(256) k_dfma_chain(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
   for (int i = 0; i < iters; i++) {
     x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
     x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
@@ -280,7 +315,7 @@ double run_fp64_peak(cudaStream_t s) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   double best = 0.0;
-  for (int rep = 0; rep < 5; rep++) {
+  for (int rep = 0; rep < 6; rep++) {
     cudaEventRecord(e0, s);
     k_dfma_chain<<<blocks, threads, 0, s>>>(d, iters, 0.999999, 1e-9);
     cudaEventRecord(e1, s);

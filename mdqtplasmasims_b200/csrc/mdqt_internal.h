@@ -19,7 +19,7 @@ struct ForceArgs {
   int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
   int ipt;           // ion rows per thread (1 or 2)
   int wrapped;       // 1: all coordinates known to lie in [0,L] (single-shift minimum image is exact)
-  double L, halfL, invL, kappa, rc2;
+  double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
 };
 
 struct QTArgs {

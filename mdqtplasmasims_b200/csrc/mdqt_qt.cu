@@ -113,12 +113,47 @@ __device__ __forceinline__ void apply_M(const LaneH& H, const cplx* w, cplx* m) 
   }
 }
 
+// 1/sqrt(x) for x in (0, 1]: MUFU.RSQ64H seed + one 3rd-order Newton step (the scheme of CUDA's rsqrt(double),
+// without its special-case branches: x = 1 - dp is always a normal number close to 1)
+__device__ __forceinline__ double rsqrt_near1(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-(x * y), y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// sin and cos of an arbitrary-magnitude phase (|phi| < 2^50): two-term FMA Cody-Waite reduction by pi/2 and the
+// fdlibm minimax kernels on [-pi/4, pi/4]; branch-free (~25 FP64 instructions, < 1 ulp for |phi| < 1e9).
+__device__ __forceinline__ void sincos_fast(double phi, double& sn, double& cs) {
+  const double t = fma(phi, 0.63661977236758134308, 6755399441055744.0);  // phi * 2/pi, round to nearest
+  const int q = __double2loint(t);
+  const double n = t - 6755399441055744.0;
+  double r = fma(n, -1.5707963267948966192, phi);
+  r = fma(n, -6.1232339957367658860e-17, r);
+  const double z = r * r;
+  double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double s0 = fma(r * z, ps, r);
+  double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const double a = (q & 1) ? c0 : s0, b = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -a : a;
+  cs = ((q + 1) & 2) ? -b : b;
+}
+
 template <int NL>
-__device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g, unsigned pairmask) {
+__device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g) {
   cplx m[NL];
   double own = fma(H.G1, cnorm(w[1]), H.G2 * cnorm(w[2]));
-  double dp = own + __shfl_xor_sync(pairmask, own, 1);
-  double pref = rsqrt(1.0 - dp);
+  double dp = own + __shfl_xor_sync(0xffffffffu, own, 1);
+  double pref = rsqrt_near1(1.0 - dp);
   apply_M<NL>(H, w, m);
 #pragma unroll
   for (int k = 0; k < NL; k++) {
@@ -134,14 +169,11 @@ template <int NL, bool FORCED>
 __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = gid & 1;
-  // shuffles are between the two lanes of an ion only: ions of one warp may sit in different branches
-  const unsigned pairmask = 3u << (threadIdx.x & 30);
   const long long slot = gid >> 1;
   const bool active = slot < (long long)a.nrows * a.B;
-  // inactive lanes still run (shuffles are warp-wide) on a harmless dummy ion
+  // inactive lanes still run (the shuffles are warp-wide) on a harmless shadow of the first ion; they never store
   const int b = active ? (int)(slot / a.nrows) : 0;
   const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
-  const QTLane& Lc = C.lane[lane];
   constexpr int S = (NL == 6) ? 12 : 7;
 
   double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
@@ -149,11 +181,29 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const double* __restrict__ Fb = a.F + (size_t)b * 3 * a.ld;
   double* __restrict__ Pb = a.psi + (size_t)b * 2 * S * a.ld;
 
+  // per-lane constants into registers once (block A for even lanes, block B for odd lanes)
+  const QTLane& LA = C.lane[0];
+  const QTLane& LB = C.lane[1];
+  int map[NL];
+#pragma unroll
+  for (int k = 0; k < NL; k++) map[k] = lane ? LB.map[k] : LA.map[k];
+  const double h = C.h;
+  LaneH H;
+  H.hc10 = h * (lane ? LB.c10 : LA.c10); H.hc20 = h * (lane ? LB.c20 : LA.c20);
+  H.hc13 = h * (lane ? LB.c13 : LA.c13); H.hc14 = h * (lane ? LB.c14 : LA.c14); H.hc25 = h * (lane ? LB.c25 : LA.c25);
+  const double gam1 = lane ? LB.gam1 : LA.gam1, gam2 = lane ? LB.gam2 : LA.gam2;
+  H.hg1 = 0.5 * h * gam1; H.hg2 = 0.5 * h * gam2; H.G1 = h * gam1; H.G2 = h * gam2;
+  H.hE3 = H.hE4 = H.hE5 = 0.0; H.hrr = H.hri = 0.0;
+  const double hrot = h * (lane ? LB.rot : LA.rot);
+  const double ksA = C.kick_sp * (lane ? LB.gA : LA.gA), ksB = C.kick_sp * (lane ? LB.gB : LA.gB);
+  const double kd0 = C.kick_dp * (lane ? LB.gD[0] : LA.gD[0]), kd1 = C.kick_dp * (lane ? LB.gD[1] : LA.gD[1]);
+  const double kd2 = C.kick_dp * (lane ? LB.gD[2] : LA.gD[2]), kd3 = C.kick_dp * (lane ? LB.gD[3] : LA.gD[3]);
+  const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
+
   cplx y[NL];
 #pragma unroll
   for (int k = 0; k < NL; k++) {
-    int gidx = Lc.map[k];
-    if (gidx >= 0) { y[k].re = Pb[(size_t)(2 * gidx) * a.ld + i]; y[k].im = Pb[(size_t)(2 * gidx + 1) * a.ld + i]; }
+    if (map[k] >= 0) { y[k].re = Pb[(size_t)(2 * map[k]) * a.ld + i]; y[k].im = Pb[(size_t)(2 * map[k] + 1) * a.ld + i]; }
     else { y[k].re = 0.0; y[k].im = 0.0; }
   }
   // lane A carries (x, y), lane B carries (x, z); x is advanced redundantly (bitwise identically) by both
@@ -165,13 +215,13 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
     tp = a.tPart[(size_t)b * a.ld + i];
   }
-  const double h = C.h;
   double t = a.t0;
+  const double DT = 0.5 * a.dtq;
+  const double dEDP = -a.detuning + a.detuningDP;
 
   for (int s = 0; s < a.nsub; s++) {
     // ---------------- step(): R += V dt/2 ; V += F dt ; R += V dt/2, single wrap into [0,L] (SU:356-430) ------
     if (a.do_step) {
-      const double DT = 0.5 * a.dtq;
       const bool started = t > 0;
 #pragma unroll
       for (int half = 0; half < 2; half++) {
@@ -200,17 +250,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     const double vq = vx * a.pv2qv;
     if (a.do_step) tp = __dadd_rn(tp, a.dtq);
 
-    // P populations of both blocks, in the reference's state order 2,3,4,5 -> identical jump decision in both lanes
-    const double nown1 = cnorm(y[1]), nown2 = cnorm(y[2]);
-    const double noth1 = __shfl_xor_sync(pairmask, nown1, 1), noth2 = __shfl_xor_sync(pairmask, nown2, 1);
-    double n2, n3, n4, n5;
-    if (NL == 6) {  // 12-level: idx2 = B.P1, idx3 = A.P1, idx4 = B.P2, idx5 = A.P2
-      n2 = lane ? nown1 : noth1; n3 = lane ? noth1 : nown1; n4 = lane ? nown2 : noth2; n5 = lane ? noth2 : nown2;
-    } else {        // 7-level:  idx2 = A.P1, idx3 = B.P1, idx4 = A.P2, idx5 = B.P2
-      n2 = lane ? noth1 : nown1; n3 = lane ? nown1 : noth1; n4 = lane ? noth2 : nown2; n5 = lane ? nown2 : noth2;
-    }
-    const double dp0 = h * C.gam[0] * n2 + h * C.gam[1] * n3 + h * C.gam[2] * n4 + h * C.gam[3] * n5;
-
+    // the uniforms of this (ion, substep): both lanes of an ion draw the same numbers
     double u0, u1;
     const uint64_t sidx = a.substep0 + (uint64_t)s;
     if (FORCED) {
@@ -221,62 +261,68 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       u0 = u52(o.x, o.y); u1 = u52(o.z, o.w);
     }
 
-    double kick = 0.0;
-    if (u0 > dp0) {
-      // ---- no jump: optical force from the pre-step coherences (SU:490-503), then the 4-stage propagator ----
-      if (a.do_step) {
-        double ksp = Lc.gA * im_acb(y[0], y[1]) - Lc.gB * im_acb(y[0], y[2]);
-        double own = C.kick_sp * ksp;
-        if (NL == 6) {
-          double kdp = Lc.gD[0] * im_acb(y[4], y[2]) + Lc.gD[1] * im_acb(y[3], y[1]) - Lc.gD[2] * im_acb(y[5], y[2]) -
-                       Lc.gD[3] * im_acb(y[4], y[1]);
-          own = fma(C.kick_dp, kdp, own);
-        }
-        kick = own;  // cross-lane sum below (outside the divergent region)
-      }
-      LaneH H;
-      const double uu = vq + expDet;
-      H.hc10 = h * Lc.c10; H.hc20 = h * Lc.c20; H.hc13 = h * Lc.c13; H.hc14 = h * Lc.c14; H.hc25 = h * Lc.c25;
-      H.hE1 = h * (-a.detuning - vq - expDet);                        // totalDetRightSP (SU:506)
-      H.hE2 = h * (-a.detuning + vq + expDet);                        // totalDetLeftSP  (SU:507)
-      if (NL == 6) {
-        H.hE3 = h * (-a.detuning + a.detuningDP + (a.kRat - 1) * uu); // states 11,12 (SU:510)
-        H.hE4 = h * (-a.detuning + a.detuningDP - vq - expDet - a.kRat * uu);  // states 9,10
-        H.hE5 = h * (-a.detuning + a.detuningDP + (1 - a.kRat) * uu); // states 7,8
-        double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;             // SU:508
-        double sn, cs;
-        sincos(phi, &sn, &cs);
-        H.hrr = h * (Lc.rot * cs); H.hri = h * (Lc.rot * sn);
-      } else {
-        H.hE3 = H.hE4 = H.hE5 = 0.0; H.hrr = H.hri = 0.0;
-      }
-      H.hg1 = 0.5 * h * Lc.gam1; H.hg2 = 0.5 * h * Lc.gam2;
-      H.G1 = h * Lc.gam1; H.G2 = h * Lc.gam2;
+    // P populations of both blocks in the reference's state order 2,3,4,5 -> identical jump decision in both lanes
+    const double nown1 = cnorm(y[1]), nown2 = cnorm(y[2]);
+    const double noth1 = __shfl_xor_sync(0xffffffffu, nown1, 1), noth2 = __shfl_xor_sync(0xffffffffu, nown2, 1);
+    double n2, n3, n4, n5;
+    if (NL == 6) {  // 12-level: idx2 = B.P1, idx3 = A.P1, idx4 = B.P2, idx5 = A.P2
+      n2 = lane ? nown1 : noth1; n3 = lane ? noth1 : nown1; n4 = lane ? nown2 : noth2; n5 = lane ? noth2 : nown2;
+    } else {        // 7-level:  idx2 = A.P1, idx3 = B.P1, idx4 = A.P2, idx5 = B.P2
+      n2 = lane ? noth1 : nown1; n3 = lane ? nown1 : noth1; n4 = lane ? noth2 : nown2; n5 = lane ? nown2 : noth2;
+    }
+    const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;   // SU:484-485
+    const bool jump = !(u0 > dp0);                                   // SU:487
 
+    // ---- no-jump branch, evaluated by every lane (jumps are rare, and a warp-uniform flow keeps the cross-lane
+    //      exchanges on plain full-mask shuffles); lanes that jump discard the result below ----
+    double kick = 0.0;
+    if (a.do_step) {  // optical force from the pre-step coherences (SU:490-503)
+      kick = ksA * im_acb(y[0], y[1]) - ksB * im_acb(y[0], y[2]);
+      if (NL == 6)
+        kick += kd0 * im_acb(y[4], y[2]) + kd1 * im_acb(y[3], y[1]) - kd2 * im_acb(y[5], y[2]) - kd3 * im_acb(y[4], y[1]);
+    }
+    const double uu = vq + expDet;
+    H.hE1 = h * (-a.detuning - vq - expDet);                        // totalDetRightSP (SU:506)
+    H.hE2 = h * (-a.detuning + vq + expDet);                        // totalDetLeftSP  (SU:507)
+    if (NL == 6) {
+      H.hE3 = h * (dEDP + (a.kRat - 1) * uu);                       // states 11,12 (SU:510)
+      H.hE4 = h * (dEDP - vq - expDet - a.kRat * uu);               // states 9,10
+      H.hE5 = h * (dEDP + (1 - a.kRat) * uu);                       // states 7,8
+      const double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;       // SU:508
+      double sn, cs;
+      sincos_fast(phi, sn, cs);
+      H.hrr = hrot * cs; H.hri = hrot * sn;
+    }
+    cplx yn[NL];
+    {
       cplx w[NL], g[NL], acc[NL];
-      stage<NL>(H, y, g, pairmask);
+      stage<NL>(H, y, g);
 #pragma unroll
       for (int k = 0; k < NL; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
-      stage<NL>(H, w, g, pairmask);
+      stage<NL>(H, w, g);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
         acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
         w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im);
       }
-      stage<NL>(H, w, g, pairmask);
+      stage<NL>(H, w, g);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
         acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
         w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
       }
-      stage<NL>(H, w, g, pairmask);
+      stage<NL>(H, w, g);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
-        y[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
-        y[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
+        yn[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
+        yn[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
       }
+    }
+    if (!jump) {
+#pragma unroll
+      for (int k = 0; k < NL; k++) y[k] = yn[k];
     } else {
-      // ---- quantum jump (SU:573-703 / MC408L:674-752): both lanes take identical decisions ----
+      // ---- quantum jump (SU:573-703 / MC408L:674-752): both lanes take identical decisions, no cross-lane traffic ----
       double u2, u3, u4;
       if (FORCED) {
         const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
@@ -291,10 +337,10 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       const double tot = n2 + n3 + n4 + n5;
       const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
       const bool sDecay = !(u2 < C.dfrac);
-      if (a.do_step) {
+      kick = 0.0;
+      if (a.do_step && lane == 0) {  // counted once in the cross-lane sum
         double mag = sDecay ? a.vKick : a.vKickDP;
         kick = (u3 < 0.5) ? mag : -mag;
-        if (lane) kick = 0.0;  // counted once in the cross-lane sum
       }
       int dest;
       if (NL == 6) {
@@ -311,17 +357,17 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
         else dest = sDecay ? 1 : 6;
       }
 #pragma unroll
-      for (int k = 0; k < NL; k++) { y[k].re = (Lc.map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
+      for (int k = 0; k < NL; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
     }
     if (a.do_step) {
-      kick = kick + __shfl_xor_sync(pairmask, kick, 1);
+      kick = kick + __shfl_xor_sync(0xffffffffu, kick, 1);
       vx = __dadd_rn(vx, kick);  // SU:705
     }
     if (a.renorm) {  // SU:706-712
       double own = 0.0;
 #pragma unroll
       for (int k = 0; k < NL; k++) own += cnorm(y[k]);
-      double nn = sqrt(own + __shfl_xor_sync(pairmask, own, 1));
+      double nn = sqrt(own + __shfl_xor_sync(0xffffffffu, own, 1));
 #pragma unroll
       for (int k = 0; k < NL; k++) { y[k].re /= nn; y[k].im /= nn; }
     }
@@ -330,10 +376,8 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
 
   if (!active) return;
 #pragma unroll
-  for (int k = 0; k < NL; k++) {
-    int gidx = Lc.map[k];
-    if (gidx >= 0) { Pb[(size_t)(2 * gidx) * a.ld + i] = y[k].re; Pb[(size_t)(2 * gidx + 1) * a.ld + i] = y[k].im; }
-  }
+  for (int k = 0; k < NL; k++)
+    if (map[k] >= 0) { Pb[(size_t)(2 * map[k]) * a.ld + i] = y[k].re; Pb[(size_t)(2 * map[k] + 1) * a.ld + i] = y[k].im; }
   if (a.do_step) {
     Rb[(size_t)c2 * a.ld + i] = r2;
     Vb[(size_t)c2 * a.ld + i] = v2;

@@ -1,0 +1,55 @@
+"""Host-side partitioning of the hot path across ranks (one process per GPU).
+
+Two natural shardings, no invented collectives:
+
+* ensembles -- independent trajectories (the reference's SLURM ``--array``, exampleSlurmFile.slurm:3, seeds
+  ``time+job`` SU:1219): rank r advances jobs ``ensemble_jobs(n_jobs, world, r)``; nothing is exchanged.
+* large N  -- i-row decomposition: rank r owns ions ``row_block(N, world, r)`` (their F rows, psi, V, tPart) and
+  needs everybody's positions: ONE all-gather of ``3 * N / world`` doubles per rank per MD step, written in place
+  into the ``[3][ld]`` position buffer (device memory of the engine on GPU ranks; any tensor in the gloo CPU tests).
+"""
+import numpy as np
+
+
+def row_block(n_ions, world, rank):
+    """(row0, n_rows) of rank `rank`: equal blocks; n_ions must divide evenly (all-gather of equal chunks)."""
+    if n_ions % world:
+        raise ValueError("n_ions=%d is not a multiple of world=%d (pad the system or pick another N)" % (n_ions, world))
+    rows = n_ions // world
+    return rank * rows, rows
+
+
+def padded_ions(n_ions, world):
+    """Smallest N' >= n_ions that row_block accepts."""
+    return ((n_ions + world - 1) // world) * world
+
+
+def ensemble_jobs(n_jobs, world, rank, first_job=1):
+    """Job numbers (the reference's argv[1]) advanced by `rank`: contiguous, balanced to within one."""
+    base, extra = divmod(n_jobs, world)
+    start = rank * base + min(rank, extra)
+    count = base + (1 if rank < extra else 0)
+    return list(range(first_job + start, first_job + start + count))
+
+
+def allgather_positions(R, n_ions, world, rank, dist):
+    """In-place all-gather of the row blocks of a ``[3][ld]`` position tensor (torch tensor, CPU or CUDA).
+
+    Every rank contributes ``R[c, row0:row0+rows]`` and receives all N columns of each component. One collective per
+    component (x, y, z); with NCCL the send buffer aliases its slot of the receive buffer (in-place all-gather)."""
+    row0, rows = row_block(n_ions, world, rank)
+    for c in range(3):
+        out = R[c, :n_ions]
+        if out.is_cuda:
+            dist.all_gather_into_tensor(out, R[c, row0:row0 + rows])
+        else:  # gloo: no aliasing of input and output
+            dist.all_gather_into_tensor(out, R[c, row0:row0 + rows].clone())
+    return R
+
+
+def allreduce_scalars(values, dist):
+    """Sum of per-rank partial observables (E_pot partial sums, kinetic sums, KDE bins) on output steps."""
+    import torch
+    t = torch.as_tensor(np.asarray(values, dtype=np.float64))
+    dist.all_reduce(t)
+    return t.numpy()

@@ -7,9 +7,8 @@ from mdqtplasmasims_b200 import Engine, su_params, synthetic
 def timeit(fn, eng, reps):
     fn(); eng.sync()
     t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.4:  # let the clocks ramp
-        fn()
-    eng.sync()
+    while time.perf_counter() - t0 < 0.4:  # let the clocks ramp (sync every call: launches are asynchronous)
+        fn(); eng.sync()
     t0 = time.perf_counter()
     for _ in range(reps): fn()
     eng.sync()
