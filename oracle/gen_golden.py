@@ -182,9 +182,39 @@ def gen_mc408():
     print("mc408l_nojump: %d substeps" % nsub)
 
 
+def gen_su_mainloop():
+    """The reference's whole main loop, files included: init() with srand48(777), lasers off (Om = OmDP = 0: no P
+    population, hence no jumps and no dependence on the random stream), run to tmax = 0.081 (41 MD steps, one output()
+    at c0 = 39), writeConditions. The produced files are the fixture for the mdqt_run driver (gzip'd text)."""
+    import gzip
+    import shutil
+    import tempfile
+    ref = po.RefSU(Om=0.0, OmDP=0.0)
+    d = tempfile.mkdtemp() + "/"
+    ref.set_savedir(d)
+    n = ref.init(777)
+    nsub = ref.run_until(0.081, do_output=1)
+    c0, counter = ref.counters()
+    out = os.path.join(OUT, "su_mainloop")
+    os.makedirs(out, exist_ok=True)
+    keep = ["energies.dat", "ions_timestep%06d.dat" % c0, "conditions_timestep%06d.dat" % c0, "wvFns_timestep%06d.dat" % c0,
+            "vel_distX_time000000.dat", "vel_distY_time000000.dat", "vel_distZ_time000000.dat", "statePopulationsVsVTime000000.dat",
+            "VZERO_timestep%06d_interval0.dat" % c0]
+    for f in keep:
+        with open(os.path.join(d, f), "rb") as src, gzip.GzipFile(os.path.join(out, f + ".gz"), "wb", mtime=0) as dst:
+            shutil.copyfileobj(src, dst)
+    with open(os.path.join(out, "README"), "w") as f:
+        f.write("reference main loop (SU:1139-1383), seed 777, Om=OmDP=0, tmax=0.081: N=%d, %d substeps, c0=%d, counter=%d\n"
+                "files written by the unmodified reference (oracle/gen_golden.py: gen_su_mainloop)\n" % (n, nsub, c0, counter))
+    print("su_mainloop: N=%d substeps=%d c0=%d counter=%d files=%s" % (n, nsub, c0, counter, sorted(os.listdir(d))[:4]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     po.build()
+    if "--mainloop" in sys.argv:
+        gen_su_mainloop()
+        sys.exit(0)
     gen_su_forces()
     gen_su_nojump()
     gen_su_jumps()

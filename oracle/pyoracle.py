@@ -245,6 +245,35 @@ class RefSU:
     def epot(self):
         return self.lib.ref_su_epot()
 
+    # ---- driver-level functions of the reference (directory naming, restart and output files, main loop) ----
+    def savedir(self):
+        self.lib.ref_su_get_savedir.restype = ctypes.c_char_p
+        return self.lib.ref_su_get_savedir().decode()
+
+    def set_savedir(self, d):
+        self.lib.ref_su_set_savedir(d.encode())
+
+    def set_counters(self, c0, counter):
+        self.lib.ref_su_set_counters(c0, counter)
+
+    def counters(self):
+        return self.lib.ref_su_get_c0(), self.lib.ref_su_get_counter()
+
+    def write_conditions(self, c0):
+        self.lib.ref_su_write_conditions(c0)
+
+    def read_conditions(self, c0):
+        self.lib.ref_su_read_conditions(c0)
+
+    def output(self):
+        self.lib.ref_su_output()
+
+    def run_until(self, tmax, do_output=1):
+        """The reference main loop (SU:1248-1381) from the current state; returns the number of substeps."""
+        self.lib.ref_su_run_until.restype = ctypes.c_long
+        self.lib.ref_su_run_until.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_int]
+        return self.lib.ref_su_run_until(tmax, int(self.consts["ratio"]), do_output)
+
     def tables(self):
         c, d, hd = np.empty((12, 12, 2)), np.empty((12, 12, 2)), np.empty((12, 12, 2))
         gs = np.empty(18)

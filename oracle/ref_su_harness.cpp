@@ -205,4 +205,18 @@ int ref_su_run_loop(int nsub, int timeStepCounter, int do_output) {
   return timeStepCounter;
 }
 
+const char* ref_su_get_savedir() { return saveDirectory; }
+
+// The whole main loop `while (t <= tmax + 0.0009) {...}  writeConditions(c0);` (SU:1248-1381) with a run-time tmax
+// (the reference's is a #define). State must have been prepared by init()/readConditions(). Returns substeps done.
+long ref_su_run_until(double tmax_, int timeStepCounter, int do_output) {
+  long n = 0;
+  while (t <= tmax_ + 0.0009) {
+    timeStepCounter = ref_su_run_loop(1, timeStepCounter, do_output);
+    n++;
+  }
+  writeConditions(c0);
+  return n;
+}
+
 }  // extern "C"
