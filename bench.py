@@ -260,6 +260,7 @@ def run_ours(args):
             if world > 1:
                 with torch.cuda.stream(ls):  # the collective is ordered after the substep kernel on the engine's stream
                     sharding.allgather_positions(Rdev, NL, world, rank, dist)
+                el.mark_wrapped(True)  # R was written from outside: the fixed-point copy is refreshed before the next force call
 
         md_step_large(); el.sync(); torch.cuda.synchronize(); barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -276,6 +277,50 @@ def run_ours(args):
                              "fp64_frac": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (fp64_peak * world),
                              "collective": "ncclAllGather of 3 x N/G fp64 per rank per MD step" if world > 1 else "none (1 GPU)"}
         el.close()
+
+    # ---- extra: the MD-family shapes (BASELINE configs[0] and [2]): MDStep at N=4096 and the 7-level pump stage -------------
+    if args.md_family and rank == 0:
+        from mdqtplasmasims_b200 import SCHEME_NONE, SCHEME_SR7, md_params, synthetic
+
+        def timed(fn, eng_, stream_, reps):
+            fn(); eng_.sync()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream_)
+            for _ in range(reps):
+                fn()
+            b_.record(stream_)
+            eng_.sync(); torch.cuda.synchronize()
+            return a.elapsed_time(b_) / reps
+
+        nm = 4096
+        pm = md_params(scheme=SCHEME_NONE, n_ions=nm, kappa=0.5, density=0.4, device=local)
+        em = Engine(pm)
+        em.upload(R=synthetic.random_positions(nm, pm.L, seed=3), V=synthetic.maxwellian(nm, np.sqrt(1 / 3.), seed=3))
+        em.forces()
+        sm = torch.cuda.ExternalStream(em.lib.mdqt_stream(em.h), device=torch.device("cuda", local))
+        for _ in range(200):
+            em.MDStep(dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.))
+        ms = timed(lambda: em.MDStep(dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.)), em, sm, 400)
+        extras["md_only_N4096"] = {"workload": "MDStep(): velocity Verlet + Andersen collisions, kappa=0.5 (MD:66-88, 504-511)",
+                                   "ms_per_md_step": ms, "pair_interactions_per_s": float(nm) * nm / (ms * 1e-3)}
+        em.close()
+        p7 = md_params(scheme=SCHEME_SR7, n_ions=nm, kappa=0.5, density=2.0, device=local)
+        e7 = Engine(p7)
+        e7.upload(R=synthetic.random_positions(nm, p7.L, seed=4), V=synthetic.maxwellian(nm, np.sqrt(1 / 3.), seed=4),
+                  psi=synthetic.random_s_state(nm, 7, seed=4))
+        e7.forces()
+        s7 = torch.cuda.ExternalStream(e7.lib.mdqt_stream(e7.h), device=torch.device("cuda", local))
+
+        def pump_step():
+            e7.qstep7(p7.substeps_per_md)  # for l < plasmaToQuantumTimestepRatio: qstep()  (MC408L:1228-1230)
+            e7.MDStep(dt=0.005)            # MDStep(k)                                     (MC408L:1231)
+
+        for _ in range(50):
+            pump_step()
+        ms = timed(pump_step, e7, s7, 100)
+        extras["qt_tagging_408_N4096"] = {"workload": "pump stage: 62 x 7-level qstep() + MDStep() per MD step (MC408L:1227-1232)",
+                                          "ms_per_md_step": ms, "ion_steps_per_s": float(nm) * p7.substeps_per_md / (ms * 1e-3)}
+        e7.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -420,6 +465,7 @@ def main():
     ap.add_argument("--traj-per-gpu", type=int, default=1)
     ap.add_argument("--ensemble", type=int, default=64, help="extra pass: trajectories batched per GPU (0/1 = skip)")
     ap.add_argument("--large-n", type=int, default=200000, help="extra pass: row-decomposed large-N MD step (0 = skip)")
+    ap.add_argument("--no-md-family", dest="md_family", action="store_false", help="skip the MD-only / 7-level pump extras")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -31,11 +31,13 @@ struct mdqt_handle {
   cudaStream_t stream;
   double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops;
   unsigned* counters;
+  long long* Rfix;  // periodic fixed-point copy of R (what the pair kernels read)
+  int rfix_dirty;   // R was written by an upload / externally: refresh Rfix before the next pair kernel
   double* forced_u; int forced_nsub, forced_cursor;
   double *forced_cu, *forced_cn;
   QTConsts qc;
   double t; uint64_t substep, vv_step;
-  int wrapped, nsplit, jlen, itiles, ipt;
+  int nsplit, jlen, itiles, ipt;
   bool timing;
   std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
   size_t ev_used;
@@ -155,7 +157,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->p = *p;
   h->N = p->n_ions; h->B = p->n_traj; h->S = p->scheme; h->row0 = row0; h->nrows = nrows;
   h->ld = (p->n_ions + 31) & ~31;
-  h->t = 0.0; h->substep = 0; h->vv_step = 0; h->wrapped = 0;
+  h->t = 0.0; h->substep = 0; h->vv_step = 0; h->Rfix = nullptr; h->rfix_dirty = 1;
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
   h->timing = false; h->ev_used = 0; h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
   plan_force(h);
@@ -177,6 +179,10 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   alloc(&h->pvel, (size_t)h->B * 3 * kVelBins);
   alloc(&h->pops, (size_t)h->B * h->N * 3);
   if (e == cudaSuccess) {
+    e = cudaMalloc((void**)&h->Rfix, sizeof(long long) * std::max<size_t>(ne, 1));
+    if (e == cudaSuccess) e = cudaMemset(h->Rfix, 0, sizeof(long long) * std::max<size_t>(ne, 1));
+  }
+  if (e == cudaSuccess) {
     e = cudaMalloc((void**)&h->counters, sizeof(unsigned) * (size_t)h->B * h->itiles);
     if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(unsigned) * (size_t)h->B * h->itiles);
   }
@@ -197,6 +203,7 @@ int mdqt_destroy(mdqt_handle* h) {
                     h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn};
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->counters) cudaFree(h->counters);
+  if (h->Rfix) cudaFree(h->Rfix);
   for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -223,13 +230,7 @@ int mdqt_upload_state(mdqt_handle* h, const double* R, const double* V, const do
   if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
   CU(cudaSetDevice(h->p.device));
   if (R) {
-    // coordinates inside [0,L] allow the exact single-shift minimum image; anything else takes the general path
-    int wrapped = 1;
-    for (int r = 0; r < h->B * 3 && wrapped; r++) {
-      const double* row = R + (size_t)r * ld;
-      for (int i = 0; i < h->N; i++) if (!(row[i] >= 0.0 && row[i] <= h->p.L)) { wrapped = 0; break; }
-    }
-    h->wrapped = wrapped;
+    h->rfix_dirty = 1;
     CU(copy_state(h, h->R, R, nullptr, ld));
   }
   if (V) CU(copy_state(h, h->V, V, nullptr, ld));
@@ -296,16 +297,25 @@ static ForceArgs force_args(mdqt_handle* h) {
   ForceArgs a;
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
-  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.wrapped = h->wrapped;
+  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.Rfix = h->Rfix;
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   return a;
+}
+
+// the pair kernels read the fixed-point copy of R: refresh it if R was written from outside the engine's kernels
+static void refresh_fixed(mdqt_handle* h) {
+  if (!h->rfix_dirty) return;
+  const double invL = 1.0 / h->p.L;
+  launch_to_fixed(h->R, h->Rfix, state_elems(h), invL, fma(-invL, h->p.L, 1.0) * invL, h->stream);
+  h->rfix_dirty = 0;
 }
 
 static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step) {
   QTArgs a;
   const mdqt_params& p = h->p;
   a.R = h->R; a.V = h->V; a.F = h->F; a.psi = h->psi; a.tPart = h->tPart;
+  a.Rfix = h->Rfix; a.invL = 1.0 / p.L; a.invL_lo = fma(-a.invL, p.L, 1.0) * a.invL;
   a.forced_u = h->forced_u ? h->forced_u + (size_t)h->forced_cursor * h->N * 5 : nullptr;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = p.traj0;
   a.nsub = nsub; a.do_step = do_step; a.renorm = p.renormalize; a.quad = p.quad;
@@ -340,6 +350,7 @@ static int enqueue_substeps(mdqt_handle* h, int nsub, int do_step) {
 int mdqt_forces(mdqt_handle* h) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   CU(cudaSetDevice(h->p.device));
+  refresh_fixed(h);
   launch_forces(force_args(h), h->stream);
   CU(cudaGetLastError());
   return MDQT_OK;
@@ -376,6 +387,7 @@ int mdqt_md_steps(mdqt_handle* h, int nsteps) {
   CU(cudaSetDevice(h->p.device));
   if (h->timing) h->ev_used = 0;
   for (int k = 0; k < nsteps; k++) {
+    refresh_fixed(h);
     if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
     launch_forces(force_args(h), h->stream);
     if (h->timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
@@ -409,6 +421,7 @@ int mdqt_md_steps_host(mdqt_handle* h, int nsteps, double* R, double* V, double*
 int mdqt_epot(mdqt_handle* h, double* epot) {
   if (!h || !epot) return fail(MDQT_EINVAL, "null argument");
   CU(cudaSetDevice(h->p.device));
+  refresh_fixed(h);
   launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);
   CU(cudaMemcpyAsync(epot, h->scalars + (size_t)h->B * 8, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -419,6 +432,7 @@ int mdqt_epot(mdqt_handle* h, double* epot) {
 int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
   if (!h || !out) return fail(MDQT_EINVAL, "null argument");
   CU(cudaSetDevice(h->p.device));
+  refresh_fixed(h);
   launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
   launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);
   std::vector<double> s((size_t)h->B * 16);
@@ -464,6 +478,8 @@ int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = h->p.traj0;
   a.L = h->p.L; a.dt = dt; a.collisionFreq = collisionFreq; a.sigma_v = sigma_v; a.laser_coeff = laser_coeff; a.laser = laser;
   a.step = h->vv_step; a.seed = h->p.seed; a.forced_u = h->forced_cu; a.forced_n = h->forced_cn;
+  a.Rfix = h->Rfix; a.invL = 1.0 / h->p.L; a.invL_lo = fma(-a.invL, h->p.L, 1.0) * a.invL;
+  refresh_fixed(h);
   launch_vv_positions(a, h->stream);    // stepPositions (MD:507)
   launch_forces(force_args(h), h->stream);  // calculateAccelerations (MD:508)
   a.A = h->F;
@@ -538,7 +554,8 @@ void* mdqt_stream(mdqt_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int mdqt_mark_wrapped(mdqt_handle* h, int wrapped) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
-  h->wrapped = wrapped ? 1 : 0;
+  (void)wrapped;       // the fixed-point pair kernel handles any coordinates; what matters is that R changed
+  h->rfix_dirty = 1;
   return MDQT_OK;
 }
 

@@ -18,7 +18,10 @@
 // exp(-kappa r) by magic-number reduction to |rr| <= ln2/256 + a 128-entry 2^(j/128) table in shared memory + a
 // degree-5 polynomial with the exponent patched by integer adds (10), prefactor (4), accumulate (3).
 #include "mdqt_internal.h"
+#include "mdqt_fixed.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #ifndef MDQT_PAIR_VARIANT
 #define MDQT_PAIR_VARIANT 3
@@ -28,15 +31,24 @@ namespace mdqt {
 
 __constant__ double c_exp2tab[kExpTable];
 
-void upload_exp_table() {
-  double tab[kExpTable];
-  for (int j = 0; j < kExpTable; j++) tab[j] = (double)exp2l((long double)j / (long double)kExpTable);
-  cudaMemcpyToSymbol(c_exp2tab, tab, sizeof(tab));
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER on B200 at N=3500 (114 vs 74 us per MD step)
+  return on;
 }
 
-#define MDQT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: adding it rounds to nearest integer */
-#define MDQT_2P62 4611686018427387904.0
-#define MDQT_2P64 18446744073709551616.0
+void upload_exp_table() {
+  double tab[kExpTable];
+  // entry j holds the bit pattern of 2^(j/128) with (j << 13) pre-subtracted from its high word, so that the kernel
+  // patches the exponent with a single add of (n << 13), n = 128 q + j  (high word += q << 20)
+  for (int j = 0; j < kExpTable; j++) {
+    tab[j] = (double)exp2l((long double)j / (long double)kExpTable);
+    unsigned long long bits;
+    memcpy(&bits, &tab[j], 8);
+    bits -= (unsigned long long)((unsigned)j << 13) << 32;
+    memcpy(&tab[j], &bits, 8);
+  }
+  cudaMemcpyToSymbol(c_exp2tab, tab, sizeof(tab));
+}
 
 // Everything the pair loop needs, in the length unit `u` of the chosen formulation (u = 1 for variant 2,
 // u = L/2^64 for the fixed-point variant): kappa*u, (rcut/u)^2, and the exp reduction constants.
@@ -61,18 +73,6 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
   c.rc2_u = rc_u * rc_u;
   c.out_scale = epot ? 1.0 / u : (1.0 / u) * (1.0 / u);
   return c;
-}
-
-// x (any real) -> periodic fixed point: round(frac(x/L) * 2^64) mod 2^64, accurate to ~L*2^-62.
-// x/L is formed in double-double (product residual by FMA + the rounding error of 1/L), so that two nearby ions keep
-// their exact separation (the reference's x_i - x_j is exact for nearby ions by Sterbenz' lemma).
-__device__ __forceinline__ long long to_fixed(double x, const PairConsts& c) {
-  double q = x * c.invL;
-  double ql = fma(x, c.invL, -q) + x * c.invL_lo;
-  double n = (q + MDQT_MAGIC) - MDQT_MAGIC;  // rint(q), |q| < 2^51
-  double f = q - n;                          // exact, in [-1/2, 1/2]
-  long long a = __double2ll_rn(f * MDQT_2P62) + __double2ll_rn(ql * MDQT_2P62);
-  return (long long)((unsigned long long)a << 2);
 }
 
 __device__ __forceinline__ double min_image_fp(double d, const PairConsts& c) {
@@ -105,14 +105,14 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
   q = fma(q, rr, 1.0);
   q = fma(q, rr, 1.0);
   double T = tab[n & (kExpTable - 1)];
-  int hi = __double2hiint(T) + ((n & ~(kExpTable - 1)) << 13);  // += floor(n/128) << 20
+  int hi = __double2hiint(T) + (n << 13);  // table high words carry -(idx << 13): net += floor(n/128) << 20
   ef = __hiloint2double(hi, __double2loint(T)) * q;
   rinv = y;
 }
 
 constexpr int kTJ = 512;  // j positions staged per pass
 
-template <int IPT, bool EPOT>
+template <int IPT, bool EPOT, int UNR>
 __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
 #if MDQT_PAIR_VARIANT == 3
   typedef long long coord_t;
@@ -130,10 +130,18 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   const int tid = threadIdx.x;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
   const PairConsts c = make_consts(a, EPOT);
+#if MDQT_PAIR_VARIANT == 3
+  const long long* __restrict__ X = a.Rfix + (size_t)b * 3 * a.ld;
+  const long long* __restrict__ Y = X + a.ld;
+  const long long* __restrict__ Z = Y + a.ld;
+#else
   const double* __restrict__ X = a.R + (size_t)b * 3 * a.ld;
   const double* __restrict__ Y = X + a.ld;
   const double* __restrict__ Z = Y + a.ld;
+#endif
+  pdl_launch_dependents();
   for (int k = tid; k < kExpTable; k += kForceThreads) stab[k] = c_exp2tab[k];
+  pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
 
   int irow[IPT];
   coord_t xi[IPT], yi[IPT], zi[IPT];
@@ -142,11 +150,7 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   for (int k = 0; k < IPT; k++) {
     irow[k] = a.row0 + tile * (kForceThreads * IPT) + k * kForceThreads + tid;
     const int ir = min(irow[k], a.row0 + a.nrows - 1);  // idle threads shadow the last row (never stored)
-#if MDQT_PAIR_VARIANT == 3
-    xi[k] = to_fixed(X[ir], c); yi[k] = to_fixed(Y[ir], c); zi[k] = to_fixed(Z[ir], c);
-#else
     xi[k] = X[ir]; yi[k] = Y[ir]; zi[k] = Z[ir];
-#endif
     ax[k] = ay[k] = az[k] = 0.0;
   }
   const int jbeg = js * a.jlen;
@@ -157,15 +161,14 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
     for (int k = tid; k < cnt; k += kForceThreads) {
       const int j = jc + k;
 #if MDQT_PAIR_VARIANT == 3
-      sxy[k] = make_longlong2(to_fixed(X[j], c), to_fixed(Y[j], c));
-      sz[k] = to_fixed(Z[j], c);
+      sxy[k] = make_longlong2(X[j], Y[j]);
 #else
       sxy[k] = make_double2(X[j], Y[j]);
-      sz[k] = Z[j];
 #endif
+      sz[k] = Z[j];
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll UNR
     for (int jj = 0; jj < cnt; jj++) {
       const auto pxy = sxy[jj];
       const coord_t pz = sz[jj];
@@ -190,7 +193,9 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
           ax[k] += valid ? u : 0.0;
         } else {
           double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
-          f = valid ? f : 0.0;
+          // 0 < r2 < rc2 as ONE predicate (DSETP, then ISETP chained with .and) and one select
+          asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %2;\n\tsetp.ne.and.s32 q, %3, 0, p;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+              : "+d"(f) : "d"(r2), "d"(c.rc2_u), "r"(__double2hiint(r2)));
           ax[k] = fma(f, dx, ax[k]);
           ay[k] = fma(f, dy, ay[k]);
           az[k] = fma(f, dz, az[k]);
@@ -264,11 +269,24 @@ template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
   const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread: decided by the planner from (N, B) only
   dim3 grid((a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt), a.nsplit, a.B);
-  if (ipt == 2) k_pairs<2, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
-  else k_pairs<1, EPOT><<<grid, kForceThreads, 0, s>>>(a, partials);
+  // few resident warps (small N): unroll the j loop further so that one warp carries more independent pairs
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  const bool deep = ipt == 1 && ctas < 148LL * 7 && getenv("MDQT_NO_DEEP_UNROLL") == nullptr;
+  const bool pdl = !EPOT && pdl_enabled();
+  if (ipt == 2) launch_kernel(k_pairs<2, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  else if (deep) launch_kernel(k_pairs<1, EPOT, 8>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  else launch_kernel(k_pairs<1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
 }
 
 void launch_forces(const ForceArgs& a, cudaStream_t s) { launch_pairs<false>(a, nullptr, s); }
+
+__global__ void k_to_fixed(const double* __restrict__ R, long long* __restrict__ Rfix, size_t n, double invL, double invL_lo) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) Rfix[k] = to_fixed(R[k], invL, invL_lo);
+}
+void launch_to_fixed(const double* R, long long* Rfix, size_t n, double invL, double invL_lo, cudaStream_t s) {
+  k_to_fixed<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, Rfix, n, invL, invL_lo);
+}
 
 int epot_partials_needed(const ForceArgs& a) {
   int tiles = (a.nrows + kForceThreads - 1) / kForceThreads;  // upper bound (IPT = 1)

@@ -11,6 +11,7 @@ constexpr int kVelBins = 2001;       // KDE bins of output() (SU:120-123)
 
 struct ForceArgs {
   const double* R;   // [B][3][ld] all positions
+  const long long* Rfix;  // [B][3][ld] the same positions in periodic fixed point (mdqt_fixed.cuh)
   double* F;         // [B][3][ld] result
   double* Fpart;     // [nsplit][B][3][ld] partial sums when nsplit > 1
   unsigned* counters;// [B][itiles] arrival counters (self-resetting)
@@ -18,12 +19,13 @@ struct ForceArgs {
   int row0, nrows;   // rows owned by this handle
   int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
   int ipt;           // ion rows per thread (1 or 2)
-  int wrapped;       // 1: all coordinates known to lie in [0,L] (single-shift minimum image is exact)
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
 };
 
 struct QTArgs {
   double* R; double* V; const double* F;  // [B][3][ld]
+  long long* Rfix;                        // [B][3][ld] fixed-point copy of R, refreshed on exit
+  double invL, invL_lo;
   double* psi;                            // [B][2*S][ld] component-major: (2*k+{0,1})*ld + i
   double* tPart;                          // [B][ld]
   const double* forced_u;                 // [nsub][N][5] or null
@@ -39,6 +41,7 @@ struct QTArgs {
 
 struct VVArgs {
   double* R; double* V; const double* A; const double* oldA;  // [B][3][ld]
+  long long* Rfix; double invL, invL_lo;
   int N, ld, B, row0, nrows, traj0;
   double L, dt, collisionFreq, sigma_v, laser_coeff;
   int laser;
@@ -47,7 +50,26 @@ struct VVArgs {
   const double* forced_n;   // [N][3] velocities assigned on collision or null
 };
 
+// Programmatic dependent launch (sm_90+): the hot kernels of an MD step call griddepcontrol.launch_dependents at
+// their start and griddepcontrol.wait before touching data of their predecessor, so the next kernel's launch latency
+// and prologue overlap the current kernel's tail. `pdl` = launch with the programmatic-serialization attribute.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 void launch_forces(const ForceArgs& a, cudaStream_t s);
+// Rfix[k] = to_fixed(R[k]) for all B*3*ld entries (after an upload or an external write into R)
+void launch_to_fixed(const double* R, long long* Rfix, size_t n, double invL, double invL_lo, cudaStream_t s);
 void launch_epot(const ForceArgs& a, double* block_partials, double* result, cudaStream_t s);  // result[B]
 int epot_partials_needed(const ForceArgs& a);
 struct QTConsts;

@@ -19,6 +19,7 @@
 // (seed; substep, ion, trajectory) -- no state, no ordering dependence (the reference's shared drand48 races).
 #include "mdqt_internal.h"
 #include "mdqt_qtconsts.h"
+#include "mdqt_fixed.cuh"
 #include <math.h>
 
 namespace mdqt {
@@ -167,6 +168,7 @@ __device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g) {
 // ------------------------------------------------------------------------------------------------------------
 template <int NL, bool FORCED>
 __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
+  pdl_launch_dependents();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = gid & 1;
   const long long slot = gid >> 1;
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const double kd2 = C.kick_dp * (lane ? LB.gD[2] : LA.gD[2]), kd3 = C.kick_dp * (lane ? LB.gD[3] : LA.gD[3]);
   const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
 
+  pdl_wait();  // forces / state come from the previous kernels in the stream
   cplx y[NL];
 #pragma unroll
   for (int k = 0; k < NL; k++) {
@@ -379,9 +382,14 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   for (int k = 0; k < NL; k++)
     if (map[k] >= 0) { Pb[(size_t)(2 * map[k]) * a.ld + i] = y[k].re; Pb[(size_t)(2 * map[k] + 1) * a.ld + i] = y[k].im; }
   if (a.do_step) {
+    long long* __restrict__ Xf = a.Rfix + (size_t)b * 3 * a.ld;
     Rb[(size_t)c2 * a.ld + i] = r2;
+    Xf[(size_t)c2 * a.ld + i] = to_fixed(r2, a.invL, a.invL_lo);
     Vb[(size_t)c2 * a.ld + i] = v2;
-    if (lane == 0) { Rb[i] = rx; Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp; }
+    if (lane == 0) {
+      Rb[i] = rx; Xf[i] = to_fixed(rx, a.invL, a.invL_lo);
+      Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp;
+    }
   }
 }
 
@@ -391,8 +399,8 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   int grid = (int)((threads + block - 1) / block);
   bool forced = a.forced_u != nullptr;
   if (scheme == 12) {
-    if (forced) k_substeps<6, true><<<grid, block, 0, s>>>(a, C);
-    else k_substeps<6, false><<<grid, block, 0, s>>>(a, C);
+    if (forced) launch_kernel(k_substeps<6, true>, dim3(grid), dim3(block), s, false, a, C);
+    else launch_kernel(k_substeps<6, false>, dim3(grid), dim3(block), s, pdl_enabled(), a, C);
   } else {
     if (forced) k_substeps<4, true><<<grid, block, 0, s>>>(a, C);
     else k_substeps<4, false><<<grid, block, 0, s>>>(a, C);
@@ -414,6 +422,7 @@ __global__ void k_vv_positions(VVArgs a) {
   if (r < 0) r = __dadd_rn(r, a.L);
   if (r > a.L) r = __dadd_rn(r, -a.L);
   a.R[idx] = r;
+  a.Rfix[idx] = to_fixed(r, a.invL, a.invL_lo);
 }
 
 __global__ void k_vv_velocities(VVArgs a) {

@@ -209,11 +209,46 @@ def gen_su_mainloop():
     print("su_mainloop: N=%d substeps=%d c0=%d counter=%d files=%s" % (n, nsub, c0, counter, sorted(os.listdir(d))[:4]))
 
 
+def gen_su_ensemble_stats():
+    """Ensemble statistics of the reference's own stochastic evolution (its own drand48 stream, srand48(2468)): 2048
+    ions, no plasma forces, 1500 qstep() sweeps from random S states and a thermal v_x spread. Every 100 substeps:
+    mean S/P/D populations, mean and variance of v_x. The GPU engine (Philox streams) must agree statistically."""
+    ref = po.RefSU()
+    rng = np.random.default_rng(31)
+    n, nsub, every = 2048, 1500, 100
+    psi = np.zeros((n, 12, 2))
+    r1, r2 = rng.uniform(size=n), rng.uniform(size=n)
+    psi[:, 0, 0] = np.sqrt(r1); psi[:, 1, 0] = np.sqrt(1 - r1) * np.sqrt(r2); psi[:, 1, 1] = np.sqrt(1 - r1) * np.sqrt(1 - r2)
+    V = np.zeros((3, n)); V[0] = rng.normal(size=n) * 0.05
+    ref.set_state(R=np.zeros((3, n)), V=V, psi=psi, tPart=np.zeros(n), t=1.0)
+    seed_stream(ref, 2468)
+    rows = []
+    for s in range(1, nsub + 1):
+        ref.qstep()
+        if s % every == 0:
+            st = ref.get_state()
+            p = (st["psi"] ** 2).sum(axis=2)
+            rows.append([s, p[:, :2].sum(axis=1).mean(), p[:, 2:6].sum(axis=1).mean(), p[:, 6:].sum(axis=1).mean(),
+                         st["V"][0].mean(), st["V"][0].var(), p[:, 2:6].sum(axis=1).std(), (st["tPart"] < 50 * ref.consts["dtq"]).mean()])
+    np.savez(os.path.join(OUT, "su_ensemble_stats.npz"), psi=psi, Vx=V[0], rows=np.array(rows), n=n, nsub=nsub, every=every)
+    print("su_ensemble_stats: final popS,P,D = %s" % rows[-1][1:4])
+
+
+def seed_stream(ref, seed):
+    """srand48(seed) inside the harness process (the reference's drand48 stream is then its own, un-injected)."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    libc.srand48(ctypes.c_long(seed))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     po.build()
     if "--mainloop" in sys.argv:
         gen_su_mainloop()
+        sys.exit(0)
+    if "--ensemble" in sys.argv:
+        gen_su_ensemble_stats()
         sys.exit(0)
     gen_su_forces()
     gen_su_nojump()

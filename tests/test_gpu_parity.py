@@ -421,3 +421,37 @@ def test_error_paths():
     e7 = Engine(md_params(scheme=SCHEME_SR7, n_ions=32, density=2.0))
     with pytest.raises(MDQTError):
         e7.md_steps(1)
+
+
+def test_ensemble_statistics_match_reference_stream(golden_dir):
+    """Statistical parity of the stochastic evolution (jumps included): 2048 ions advanced 1500 substeps by the engine
+    with its Philox streams vs the reference advanced with its own drand48 stream (tests/golden/su_ensemble_stats.npz).
+    Two independent ensembles: z-tests on the S/P/D populations and on <v_x>, an F-like ratio test on var(v_x)."""
+    g = np.load(os.path.join(golden_dir, "su_ensemble_stats.npz"))
+    n, nsub, every = int(g["n"]), int(g["nsub"]), int(g["every"])
+    p = su_params(n_ions=n, seed=97531)
+    V = np.zeros((3, n)); V[0] = g["Vx"]
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=g["psi"], tPart=np.zeros(n), t=1.0, substep=0)
+    eng.upload_forces(np.zeros((3, n)))
+    rows = []
+    for s in range(every, nsub + 1, every):
+        eng.step_qstep(every)
+        pops = eng.populations()
+        vx = eng.download(("V",))["V"][0]
+        rows.append([s, pops[:, 0].mean(), pops[:, 1].mean(), pops[:, 2].mean(), vx.mean(), vx.var(), pops[:, 1].std()])
+    rows = np.array(rows)
+    ref = g["rows"]
+    assert np.array_equal(rows[:, 0], ref[:, 0])
+    # populations: per-ion std <= 0.5 -> standard error of the difference of two ensemble means <= 0.5*sqrt(2/n)
+    se = 0.5 * np.sqrt(2.0 / n)
+    for col, name in ((1, "popS"), (2, "popP"), (3, "popD")):
+        z = np.abs(rows[:, col] - ref[:, col]) / se
+        assert z.max() < 4.5, (name, z.max(), rows[:, col], ref[:, col])
+    # the P population settles near 0.17 in both; the D manifold fills up through jumps (and is repumped by the 1033 nm laser)
+    assert abs(rows[-1, 2] - ref[-1, 2]) < 0.02 and 0.05 < rows[-1, 3] < 0.2 and rows[-1, 3] > rows[0, 3]
+    # velocities: same kicks statistics -> same drift of the mean and same cooling of the variance
+    se_v = np.sqrt(ref[:, 5] * 2.0 / n)
+    assert (np.abs(rows[:, 4] - ref[:, 4]) / se_v).max() < 4.5
+    assert np.abs(rows[:, 5] / ref[:, 5] - 1).max() < 0.02
+    assert rows[-1, 5] < rows[0, 5]  # laser cooling: var(v_x) decreases (red detuning)
