@@ -37,7 +37,7 @@ struct mdqt_handle {
   double *forced_cu, *forced_cn;
   QTConsts qc;
   double t; uint64_t substep, vv_step;
-  int nsplit, jlen, itiles, ipt;
+  int nsplit, jlen, itiles, ipt, jsub;
   bool timing;
   std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
   size_t ev_used;
@@ -124,6 +124,12 @@ static void plan_force(mdqt_handle* h) {
   }
   const int ipt = best_ipt;
   h->nsplit = best_ns; h->jlen = best_jlen; h->ipt = ipt;
+  // few CTAs per SM (small N): split every j tile over two 128-thread groups inside the CTA -> twice the resident warps
+  {
+    const long long tiles1 = ((long long)N + kForceThreads - 1) / kForceThreads * B;
+    h->jsub = (ipt == 1 && tiles1 * h->nsplit < 148LL * 7) ? 2 : 1;
+  }
+  if (const char* e = getenv("MDQT_FORCE_JSUB")) h->jsub = (atoi(e) == 2 && h->ipt == 1) ? 2 : 1;
   // developer tuning knobs (kernel A/B runs): override the plan
   if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("MDQT_FORCE_NSPLIT")) {
@@ -297,7 +303,7 @@ static ForceArgs force_args(mdqt_handle* h) {
   ForceArgs a;
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
-  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.Rfix = h->Rfix;
+  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.Rfix = h->Rfix;
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   return a;

@@ -7,8 +7,8 @@
 // pair-interactions per call), which needs no scatter and sums in a fixed order.
 //
 // Bound: the FP64 pipe (64 lanes/clk/SM). Memory traffic is negligible (24 B per j per CTA, staged in shared memory
-// and broadcast). Two formulations of the pair geometry are compiled (MDQT_PAIR_VARIANT):
-//   3 (default) PERIODIC FIXED POINT: coordinates are converted once per CTA pass to 64-bit integers in units of
+// and broadcast). Pair geometry:
+//   PERIODIC FIXED POINT: coordinates are kept as 64-bit integers in units of
 //     L/2^64, so that the two's-complement difference x_i - x_j IS the minimum image (the reference's
 //     d -= L*round(d/L), SU:218-220) -- for free, for any (wrapped or unwrapped) input, and exactly: differences are
 //     formed without rounding and converted to double with 53-bit relative precision. Delta + minimum image cost
@@ -22,10 +22,6 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
-
-#ifndef MDQT_PAIR_VARIANT
-#define MDQT_PAIR_VARIANT 3
-#endif
 
 namespace mdqt {
 
@@ -61,11 +57,7 @@ struct PairConsts {
 __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot) {
   PairConsts c;
   c.L = a.L; c.invL = a.invL; c.invL_lo = a.invL_lo;
-#if MDQT_PAIR_VARIANT == 3
   const double u = a.L / MDQT_2P64;
-#else
-  const double u = 1.0;
-#endif
   c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
   c.nk_scale = -c.kappa_u * 184.66496523378731614207035916824219;  // 128 * log2(e)
   c.negc = -0.0054152123481245727298221259488920044;               // -ln2 / 128
@@ -73,12 +65,6 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
   c.rc2_u = rc_u * rc_u;
   c.out_scale = epot ? 1.0 / u : (1.0 / u) * (1.0 / u);
   return c;
-}
-
-__device__ __forceinline__ double min_image_fp(double d, const PairConsts& c) {
-  double t = fma(d, c.invL, MDQT_MAGIC);
-  double n = t - MDQT_MAGIC;
-  return fma(-c.L, n, d);
 }
 
 // From r2 (in units u^2): rinv = 1/r, ef = exp(-kappa r), valid = 0 < r2 < rcut^2.
@@ -112,43 +98,36 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
 
 constexpr int kTJ = 512;  // j positions staged per pass
 
-template <int IPT, bool EPOT, int UNR>
-__global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
-#if MDQT_PAIR_VARIANT == 3
-  typedef long long coord_t;
+// IPT rows per thread; JS = intra-CTA split of every staged j tile over JS groups of 128 threads (more resident warps
+// at small N without more partial sums: the groups' sums are combined through shared memory in ascending group order);
+// UNR = unroll of the j loop.
+template <int IPT, int JS, bool EPOT, int UNR>
+__global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
   __shared__ longlong2 sxy[kTJ];
   __shared__ long long sz[kTJ];
-#else
-  typedef double coord_t;
-  __shared__ double2 sxy[kTJ];
-  __shared__ double sz[kTJ];
-#endif
   __shared__ double stab[kExpTable];
-  __shared__ double sred[kForceThreads / 32];
+  __shared__ double sred[kForceThreads * JS / 32];
+  __shared__ double sjs[(JS > 1 ? JS - 1 : 1) * IPT * 3 * kForceThreads];
   __shared__ int s_last;
+  constexpr int NT = kForceThreads * JS;
 
   const int tid = threadIdx.x;
+  const int ti = tid % kForceThreads, jh = tid / kForceThreads;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
   const PairConsts c = make_consts(a, EPOT);
-#if MDQT_PAIR_VARIANT == 3
   const long long* __restrict__ X = a.Rfix + (size_t)b * 3 * a.ld;
   const long long* __restrict__ Y = X + a.ld;
   const long long* __restrict__ Z = Y + a.ld;
-#else
-  const double* __restrict__ X = a.R + (size_t)b * 3 * a.ld;
-  const double* __restrict__ Y = X + a.ld;
-  const double* __restrict__ Z = Y + a.ld;
-#endif
   pdl_launch_dependents();
-  for (int k = tid; k < kExpTable; k += kForceThreads) stab[k] = c_exp2tab[k];
+  for (int k = tid; k < kExpTable; k += NT) stab[k] = c_exp2tab[k];
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
 
   int irow[IPT];
-  coord_t xi[IPT], yi[IPT], zi[IPT];
+  long long xi[IPT], yi[IPT], zi[IPT];
   double ax[IPT], ay[IPT], az[IPT];
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
-    irow[k] = a.row0 + tile * (kForceThreads * IPT) + k * kForceThreads + tid;
+    irow[k] = a.row0 + tile * (kForceThreads * IPT) + k * kForceThreads + ti;
     const int ir = min(irow[k], a.row0 + a.nrows - 1);  // idle threads shadow the last row (never stored)
     xi[k] = X[ir]; yi[k] = Y[ir]; zi[k] = Z[ir];
     ax[k] = ay[k] = az[k] = 0.0;
@@ -158,32 +137,23 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   for (int jc = jbeg; jc < jend; jc += kTJ) {
     const int cnt = min(kTJ, jend - jc);
     __syncthreads();
-    for (int k = tid; k < cnt; k += kForceThreads) {
+    for (int k = tid; k < cnt; k += NT) {
       const int j = jc + k;
-#if MDQT_PAIR_VARIANT == 3
       sxy[k] = make_longlong2(X[j], Y[j]);
-#else
-      sxy[k] = make_double2(X[j], Y[j]);
-#endif
       sz[k] = Z[j];
     }
     __syncthreads();
+    const int lo = (cnt * jh) / JS, hi = (cnt * (jh + 1)) / JS;
 #pragma unroll UNR
-    for (int jj = 0; jj < cnt; jj++) {
-      const auto pxy = sxy[jj];
-      const coord_t pz = sz[jj];
+    for (int jj = lo; jj < hi; jj++) {
+      const longlong2 pxy = sxy[jj];
+      const long long pz = sz[jj];
 #pragma unroll
       for (int k = 0; k < IPT; k++) {
-#if MDQT_PAIR_VARIANT == 3
         // two's-complement wrap-around == minimum image; exact difference, one rounding in the conversion
         const double dx = __ll2double_rn((long long)((unsigned long long)xi[k] - (unsigned long long)pxy.x));
         const double dy = __ll2double_rn((long long)((unsigned long long)yi[k] - (unsigned long long)pxy.y));
         const double dz = __ll2double_rn((long long)((unsigned long long)zi[k] - (unsigned long long)pz));
-#else
-        const double dx = min_image_fp(xi[k] - pxy.x, c);
-        const double dy = min_image_fp(yi[k] - pxy.y, c);
-        const double dz = min_image_fp(zi[k] - pz, c);
-#endif
         const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
         double rinv, ef;
         bool valid;
@@ -203,6 +173,26 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
       }
     }
   }
+  if (JS > 1) {  // combine the thread groups: group 0 adds the others' sums in ascending group order
+    if (jh > 0) {
+#pragma unroll
+      for (int k = 0; k < IPT; k++) {
+        double* o = sjs + (((jh - 1) * IPT + k) * 3) * kForceThreads + ti;
+        o[0] = ax[k]; o[kForceThreads] = ay[k]; o[2 * kForceThreads] = az[k];
+      }
+    }
+    __syncthreads();
+    if (jh == 0) {
+#pragma unroll
+      for (int g = 1; g < JS; g++)
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+          const double* o = sjs + (((g - 1) * IPT + k) * 3) * kForceThreads + ti;
+          ax[k] += o[0]; ay[k] += o[kForceThreads]; az[k] += o[2 * kForceThreads];
+        }
+    }
+  }
+  const bool owner = jh == 0;  // only group 0 holds complete sums
 #pragma unroll
   for (int k = 0; k < IPT; k++) { ax[k] *= c.out_scale; ay[k] *= c.out_scale; az[k] *= c.out_scale; }
 
@@ -210,14 +200,14 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
     // fixed-order block reduction -> one partial per CTA
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < IPT; k++) s += (irow[k] < a.row0 + a.nrows) ? ax[k] : 0.0;
+    for (int k = 0; k < IPT; k++) s += (owner && irow[k] < a.row0 + a.nrows) ? ax[k] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     if ((tid & 31) == 0) sred[tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
       double tot = 0.0;
-      for (int w = 0; w < kForceThreads / 32; w++) tot += sred[w];
+      for (int w = 0; w < kForceThreads / 32; w++) tot += sred[w];  // the warps of group 0
       block_partials[((size_t)b * gridDim.y + js) * gridDim.x + tile] = tot;
     }
     return;
@@ -226,7 +216,7 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   if (a.nsplit == 1) {
 #pragma unroll
     for (int k = 0; k < IPT; k++)
-      if (irow[k] < a.row0 + a.nrows) {
+      if (owner && irow[k] < a.row0 + a.nrows) {
         double* Fb = a.F + (size_t)b * 3 * a.ld;
         Fb[irow[k]] = ax[k]; Fb[a.ld + irow[k]] = ay[k]; Fb[2 * a.ld + irow[k]] = az[k];
       }
@@ -236,7 +226,7 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   // order -> deterministic, independent of arrival order and of how many ranks share the rows.
 #pragma unroll
   for (int k = 0; k < IPT; k++)
-    if (irow[k] < a.row0 + a.nrows) {
+    if (owner && irow[k] < a.row0 + a.nrows) {
       double* Fp = a.Fpart + ((size_t)js * a.B + b) * 3 * a.ld;
       __stcg(&Fp[irow[k]], ax[k]); __stcg(&Fp[a.ld + irow[k]], ay[k]); __stcg(&Fp[2 * a.ld + irow[k]], az[k]);
     }
@@ -251,31 +241,29 @@ __global__ void __launch_bounds__(kForceThreads) k_pairs(ForceArgs a, double* __
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-#pragma unroll
-  for (int k = 0; k < IPT; k++)
-    if (irow[k] < a.row0 + a.nrows) {
-      double sx = 0.0, sy = 0.0, szz = 0.0;
+  // the last CTA: all NT threads share the final reduction (thread -> (row slot, component) round robin)
+  for (int w = tid; w < kForceThreads * IPT * 3; w += NT) {
+    const int comp = w / (kForceThreads * IPT), slot = w % (kForceThreads * IPT);
+    const int row = a.row0 + tile * (kForceThreads * IPT) + slot;
+    if (row < a.row0 + a.nrows) {
+      double sum = 0.0;
 #pragma unroll 4
-      for (int s = 0; s < a.nsplit; s++) {
-        const double* Fp = a.Fpart + ((size_t)s * a.B + b) * 3 * a.ld;
-        sx += __ldcg(&Fp[irow[k]]); sy += __ldcg(&Fp[a.ld + irow[k]]); szz += __ldcg(&Fp[2 * a.ld + irow[k]]);
-      }
-      double* Fb = a.F + (size_t)b * 3 * a.ld;
-      Fb[irow[k]] = sx; Fb[a.ld + irow[k]] = sy; Fb[2 * a.ld + irow[k]] = szz;
+      for (int s = 0; s < a.nsplit; s++) sum += __ldcg(a.Fpart + (((size_t)s * a.B + b) * 3 + comp) * a.ld + row);
+      a.F[((size_t)b * 3 + comp) * a.ld + row] = sum;
     }
+  }
 }
 
 template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
-  const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread: decided by the planner from (N, B) only
+  const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread and intra-CTA split: decided by the planner from (N, B) only
+  const int jsub = a.jsub == 2 ? 2 : 1;
   dim3 grid((a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt), a.nsplit, a.B);
-  // few resident warps (small N): unroll the j loop further so that one warp carries more independent pairs
-  const long long ctas = (long long)grid.x * grid.y * grid.z;
-  const bool deep = ipt == 1 && ctas < 148LL * 7 && getenv("MDQT_NO_DEEP_UNROLL") == nullptr;
   const bool pdl = !EPOT && pdl_enabled();
-  if (ipt == 2) launch_kernel(k_pairs<2, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
-  else if (deep) launch_kernel(k_pairs<1, EPOT, 8>, grid, dim3(kForceThreads), s, pdl, a, partials);
-  else launch_kernel(k_pairs<1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
+  if (ipt == 2) launch_kernel(k_pairs<2, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  else if (jsub == 2) launch_kernel(k_pairs<1, 2, EPOT, 8>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
+  else launch_kernel(k_pairs<1, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
 }
 
 void launch_forces(const ForceArgs& a, cudaStream_t s) { launch_pairs<false>(a, nullptr, s); }

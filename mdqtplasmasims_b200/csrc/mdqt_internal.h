@@ -19,6 +19,7 @@ struct ForceArgs {
   int row0, nrows;   // rows owned by this handle
   int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
   int ipt;           // ion rows per thread (1 or 2)
+  int jsub;          // intra-CTA split of each j tile over 128-thread groups (1 or 2)
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
 };
 

@@ -31,7 +31,7 @@ for (N, ipt, ns) in cases:
     print("  N=%%d ipt=%%d plan=%%s %%.1f us %%.3e pairs/s" %% (N, ipt, eng.force_plan(), dt * 1e6, N * N / dt), flush=True)
     eng.close()
 ''' % ROOT
-cases = [(3500, 1, None), (3500, 1, 16), (3500, 1, 28), (3500, 1, 40), (4096, 1, None), (4096, 1, 37), (20000, 1, None)]
+cases = eval(os.environ.get('AB_CASES', '[(3500, 1, None)]'))
 libs = sys.argv[1:] or ["libmdqt_b200.so"]
 for lib in libs:
     env = dict(os.environ, MDQT_LIB_PATH=os.path.join(ROOT, "mdqtplasmasims_b200", lib))
