@@ -129,7 +129,10 @@ static void plan_force(mdqt_handle* h) {
     const long long tiles1 = ((long long)N + kForceThreads - 1) / kForceThreads * B;
     h->jsub = (ipt == 1 && tiles1 * h->nsplit < 148LL * 7) ? 2 : 1;
   }
-  if (const char* e = getenv("MDQT_FORCE_JSUB")) h->jsub = (atoi(e) == 2 && h->ipt == 1) ? 2 : 1;
+  if (const char* e = getenv("MDQT_FORCE_JSUB")) {
+    int js = atoi(e);
+    h->jsub = (js == 2 || (js == 4 && getenv("MDQT_FORCE_IPT") && atoi(getenv("MDQT_FORCE_IPT")) == 2)) ? js : 1;
+  }
   // developer tuning knobs (kernel A/B runs): override the plan
   if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("MDQT_FORCE_NSPLIT")) {

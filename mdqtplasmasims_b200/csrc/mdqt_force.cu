@@ -257,11 +257,13 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
 template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
   const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread and intra-CTA split: decided by the planner from (N, B) only
-  const int jsub = a.jsub == 2 ? 2 : 1;
+  const int jsub = (a.jsub == 2 || a.jsub == 4) ? a.jsub : 1;
   dim3 grid((a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt), a.nsplit, a.B);
   const bool pdl = !EPOT && pdl_enabled();
   // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
-  if (ipt == 2) launch_kernel(k_pairs<2, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  if (ipt == 2 && jsub == 4) launch_kernel(k_pairs<2, 4, EPOT, 4>, grid, dim3(kForceThreads * 4), s, pdl, a, partials);
+  else if (ipt == 2 && jsub == 2) launch_kernel(k_pairs<2, 2, EPOT, 4>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
+  else if (ipt == 2) launch_kernel(k_pairs<2, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
   else if (jsub == 2) launch_kernel(k_pairs<1, 2, EPOT, 8>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
   else launch_kernel(k_pairs<1, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
 }

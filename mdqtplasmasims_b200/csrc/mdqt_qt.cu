@@ -21,6 +21,7 @@
 #include "mdqt_qtconsts.h"
 #include "mdqt_fixed.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace mdqt {
 
@@ -393,11 +394,281 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K2, four lanes per ion (12-level scheme, small systems). With N ~ 3500 the two-lane kernel fills 220 of the chip's 592
+// warp schedulers with ONE warp each and is bound by the latency of its own instruction stream. Here every Hamiltonian
+// block is split once more -- lane (blk, 0) holds {S, P1, D3}, lane (blk, 1) holds {P2, D4, D5} -- so a warp carries
+// 8 ions and ~35 % fewer instructions per substep. Both halves run ONE uniform instruction stream with per-lane
+// coefficients (no divergence):
+//   row0 = D0 w0 + A01 w1 + a02 w2 + b00 r0      half0: S  (D0 = 0, A01 = c10, b00 = c20, r0 = P2)
+//                                                half1: P2 (D0 = E2 - i g2, A01 = conj(rot), a02 = c25, b00 = c20, r0 = S)
+//   row1 = D1 w1 + A10 w0 + a12 w2 + b11 r1      half0: P1 (D1 = E1 - i g1, A10 = c10, a12 = c13, b11 = c14, r1 = D4)
+//                                                half1: D4 (D1 = E4, A10 = rot, b11 = c14, r1 = P1)
+//   row2 = E2' w2 + a21 w1 + a20 w0              half0: D3 (a21 = c13)          half1: D5 (a20 = c25)
+// with (r0, r1) = the partner half's (w0, w1), one shuffle pair per stage. Same physics, same uniforms, same jump
+// logic as k_substeps; sums that cross lanes are formed in a different (fixed) order, so results agree to rounding.
+// ------------------------------------------------------------------------------------------------------------
+struct Lane4H {
+  double hE0, hg0, hE1, hg1, hE2;   // h * (energy, Gamma/2) of the three local rows
+  double a01r, a01i, a10r, a10i;    // h * complex couplings row0<-w1, row1<-w0
+  double a02, b00, a12, b11, a21, a20;
+  double G0, G1;                    // h * Gamma weights of |w0|^2, |w1|^2 in dp
+};
+
+__device__ __forceinline__ void stage4(const Lane4H& H, const cplx* w, cplx* g) {
+  const cplx r0 = {__shfl_xor_sync(0xffffffffu, w[0].re, 1), __shfl_xor_sync(0xffffffffu, w[0].im, 1)};
+  const cplx r1 = {__shfl_xor_sync(0xffffffffu, w[1].re, 1), __shfl_xor_sync(0xffffffffu, w[1].im, 1)};
+  double own = fma(H.G0, cnorm(w[0]), H.G1 * cnorm(w[1]));
+  own += __shfl_xor_sync(0xffffffffu, own, 1);
+  own += __shfl_xor_sync(0xffffffffu, own, 2);
+  const double pref = rsqrt_near1(1.0 - own);
+  cplx m[3];
+  {  // row0
+    double hr = fma(H.hE0, w[0].re, H.hg0 * w[0].im), hi = fma(H.hE0, w[0].im, -(H.hg0 * w[0].re));
+    hr = fma(H.a01r, w[1].re, fma(-H.a01i, w[1].im, hr)); hi = fma(H.a01r, w[1].im, fma(H.a01i, w[1].re, hi));
+    hr = fma(H.a02, w[2].re, hr); hi = fma(H.a02, w[2].im, hi);
+    hr = fma(H.b00, r0.re, hr); hi = fma(H.b00, r0.im, hi);
+    m[0].re = w[0].re + hi; m[0].im = w[0].im - hr;
+  }
+  {  // row1
+    double hr = fma(H.hE1, w[1].re, H.hg1 * w[1].im), hi = fma(H.hE1, w[1].im, -(H.hg1 * w[1].re));
+    hr = fma(H.a10r, w[0].re, fma(-H.a10i, w[0].im, hr)); hi = fma(H.a10r, w[0].im, fma(H.a10i, w[0].re, hi));
+    hr = fma(H.a12, w[2].re, hr); hi = fma(H.a12, w[2].im, hi);
+    hr = fma(H.b11, r1.re, hr); hi = fma(H.b11, r1.im, hi);
+    m[1].re = w[1].re + hi; m[1].im = w[1].im - hr;
+  }
+  {  // row2
+    double hr = fma(H.hE2, w[2].re, fma(H.a21, w[1].re, H.a20 * w[0].re));
+    double hi = fma(H.hE2, w[2].im, fma(H.a21, w[1].im, H.a20 * w[0].im));
+    m[2].re = w[2].re + hi; m[2].im = w[2].im - hr;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    g[k].re = fma(pref, m[k].re, -w[k].re);
+    g[k].im = fma(pref, m[k].im, -w[k].im);
+  }
+}
+
+template <bool FORCED>
+__global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = gid & 3, blk = q >> 1, half = q & 1;
+  const long long slot = gid >> 2;
+  const bool active = slot < (long long)a.nrows * a.B;
+  const int b = active ? (int)(slot / a.nrows) : 0;
+  const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
+
+  double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
+  double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
+  const double* __restrict__ Fb = a.F + (size_t)b * 3 * a.ld;
+  double* __restrict__ Pb = a.psi + (size_t)b * 24 * a.ld;
+
+  // local state -> reference state: half0 = {S, P1, D3}, half1 = {P2, D4, D5} of block blk (QTLane.map order S,P1,P2,D3,D4,D5)
+  const QTLane& LA = C.lane[0];
+  const QTLane& LB = C.lane[1];
+#define LSEL(f) (blk ? LB.f : LA.f)
+  int map[3];
+  map[0] = half ? LSEL(map[2]) : LSEL(map[0]);
+  map[1] = half ? LSEL(map[4]) : LSEL(map[1]);
+  map[2] = half ? LSEL(map[5]) : LSEL(map[3]);
+  const double h = C.h;
+  const double hc10 = h * LSEL(c10), hc20 = h * LSEL(c20), hc13 = h * LSEL(c13), hc14 = h * LSEL(c14), hc25 = h * LSEL(c25);
+  const double hrot = h * LSEL(rot);
+  const double gam1 = LSEL(gam1), gam2 = LSEL(gam2);
+  const double dEDP = -a.detuning + a.detuningDP;
+  Lane4H H;
+  // energies as e0 + e1 * (vq + expDetuning)  (SU:506-510), pre-multiplied by h
+  const double e0_0 = half ? -h * a.detuning : 0.0, e1_0 = half ? h : 0.0;                       // S | P2: -det + u
+  const double e0_1 = half ? h * dEDP : -h * a.detuning, e1_1 = half ? -h * (1 + a.kRat) : -h;   // P1: -det - u | D4
+  const double e0_2 = h * dEDP, e1_2 = half ? h * (1 - a.kRat) : h * (a.kRat - 1);               // D3 | D5
+  H.hg0 = half ? 0.5 * h * gam2 : 0.0; H.hg1 = half ? 0.0 : 0.5 * h * gam1;
+  H.G0 = half ? h * gam2 : 0.0; H.G1 = half ? 0.0 : h * gam1;
+  H.a02 = half ? hc25 : 0.0; H.b00 = hc20; H.a12 = half ? 0.0 : hc13; H.b11 = hc14;
+  H.a21 = half ? 0.0 : hc13; H.a20 = half ? hc25 : 0.0;
+  H.a01r = hc10; H.a01i = 0.0; H.a10r = hc10; H.a10i = 0.0;  // half1: set from the rotating phase every substep
+  // optical-force weights (SU:503), generic form k1 Im(w0 w1*) + k2 Im(w2 w1*) + k3 Im(r0 w0*) + k4 Im(w2 w0*) + k5 Im(w1 r1*)
+  const double k1 = half ? -C.kick_dp * LSEL(gD[0]) : C.kick_sp * LSEL(gA);
+  const double k2 = half ? 0.0 : C.kick_dp * LSEL(gD[1]);
+  const double k3 = half ? -C.kick_sp * LSEL(gB) : 0.0;
+  const double k4 = half ? -C.kick_dp * LSEL(gD[2]) : 0.0;
+  const double k5 = half ? -C.kick_dp * LSEL(gD[3]) : 0.0;
+#undef LSEL
+  const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
+  const int base = threadIdx.x & 28;  // first lane of this ion's quad within the warp
+
+  pdl_wait();
+  cplx y[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { y[k].re = Pb[(size_t)(2 * map[k]) * a.ld + i]; y[k].im = Pb[(size_t)(2 * map[k] + 1) * a.ld + i]; }
+  // quad lane 0 carries (x, y), lane 1 (x, z); lanes 2, 3 shadow (x, y) without storing
+  const int c2 = (q == 1) ? 2 : 1;
+  double rx = Rb[i], r2 = Rb[(size_t)c2 * a.ld + i], vx = Vb[i], v2 = Vb[(size_t)c2 * a.ld + i];
+  const double fx = Fb[i], f2 = Fb[(size_t)c2 * a.ld + i];
+  double tp = a.tPart[(size_t)b * a.ld + i];
+  double t = a.t0;
+  const double DT = 0.5 * a.dtq;
+
+  for (int s = 0; s < a.nsub; s++) {
+    {  // step() (SU:356-430)
+      const bool started = t > 0;
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {
+        if (started) {
+          rx = __dadd_rn(rx, __dmul_rn(DT, vx));
+          r2 = __dadd_rn(r2, __dmul_rn(DT, v2));
+        } else {
+          rx = __dadd_rn(rx, __dadd_rn(__dmul_rn(DT, vx), __dmul_rn(__dmul_rn(DT, DT), fx)));
+          r2 = __dadd_rn(r2, __dadd_rn(__dmul_rn(DT, v2), __dmul_rn(__dmul_rn(DT, DT), f2)));
+        }
+        if (rx < 0) rx = __dadd_rn(rx, a.L);
+        if (rx > a.L) rx = __dadd_rn(rx, -a.L);
+        if (r2 < 0) r2 = __dadd_rn(r2, a.L);
+        if (r2 > a.L) r2 = __dadd_rn(r2, -a.L);
+        if (hf == 0) {
+          vx = __dadd_rn(vx, __dmul_rn(a.dtq, fx));
+          v2 = __dadd_rn(v2, __dmul_rn(a.dtq, f2));
+        }
+      }
+    }
+    double expDet = 0.0;
+    if (a.fracOfSig != 0.0)
+      expDet = 0.0126 * a.fracOfSig * a.Te * t /
+               (sqrt(a.density) * a.sig0 * sqrt(1 + 0.00014314 * t * t * a.Te / (a.density * a.sig0 * a.sig0)));
+    const double vq = vx * a.pv2qv;
+    tp = __dadd_rn(tp, a.dtq);
+
+    double u0, u1;
+    const uint64_t sidx = a.substep0 + (uint64_t)s;
+    if (FORCED) {
+      const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
+      u0 = up[0]; u1 = up[1];
+    } else {
+      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
+      u0 = u52(o.x, o.y); u1 = u52(o.z, o.w);
+    }
+    // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
+    const double pn = half ? cnorm(y[0]) : cnorm(y[1]);
+    const double n3 = __shfl_sync(0xffffffffu, pn, base), n5 = __shfl_sync(0xffffffffu, pn, base + 1);
+    const double n2 = __shfl_sync(0xffffffffu, pn, base + 2), n4 = __shfl_sync(0xffffffffu, pn, base + 3);
+    const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;
+    const bool jump = !(u0 > dp0);
+
+    const double uu = vq + expDet;
+    H.hE0 = fma(e1_0, uu, e0_0); H.hE1 = fma(e1_1, uu, e0_1); H.hE2 = fma(e1_2, uu, e0_2);
+    {
+      const double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;  // SU:508
+      double sn, cs;
+      sincos_fast(phi, sn, cs);
+      if (half) { H.a01r = hrot * cs; H.a01i = -(hrot * sn); H.a10r = hrot * cs; H.a10i = hrot * sn; }
+    }
+    cplx yn[3];
+    double kick;
+    {
+      cplx w[3], g[3], acc[3];
+      // stage 1 also yields the partner amplitudes needed by the optical force (pre-step coherences)
+      const cplx r0 = {__shfl_xor_sync(0xffffffffu, y[0].re, 1), __shfl_xor_sync(0xffffffffu, y[0].im, 1)};
+      const cplx r1 = {__shfl_xor_sync(0xffffffffu, y[1].re, 1), __shfl_xor_sync(0xffffffffu, y[1].im, 1)};
+      kick = k1 * im_acb(y[0], y[1]) + k2 * im_acb(y[2], y[1]) + k3 * im_acb(r0, y[0]) + k4 * im_acb(y[2], y[0]) +
+             k5 * im_acb(y[1], r1);
+      stage4(H, y, g);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
+      stage4(H, w, g);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
+        w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im);
+      }
+      stage4(H, w, g);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
+        w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
+      }
+      stage4(H, w, g);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        yn[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
+        yn[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
+      }
+    }
+    if (!jump) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) y[k] = yn[k];
+    } else {  // quantum jump (SU:573-703): all four lanes decide identically
+      double u2, u3, u4;
+      if (FORCED) {
+        const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
+        u2 = up[2]; u3 = up[3]; u4 = up[4];
+      } else {
+        uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
+        u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
+        u4 = u52(o.x, o.y);
+      }
+      tp = 0.0;
+      const double tot = n2 + n3 + n4 + n5;
+      const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
+      const bool sDecay = !(u2 < C.dfrac);
+      kick = 0.0;
+      if (q == 0) {
+        double mag = sDecay ? a.vKick : a.vKickDP;
+        kick = (u3 < 0.5) ? mag : -mag;
+      }
+      int dest;
+      if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
+      else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
+      else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
+      else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
+#pragma unroll
+      for (int k = 0; k < 3; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
+    }
+    kick += __shfl_xor_sync(0xffffffffu, kick, 1);
+    kick += __shfl_xor_sync(0xffffffffu, kick, 2);
+    vx = __dadd_rn(vx, kick);  // SU:705
+    if (a.renorm) {
+      double own = cnorm(y[0]) + cnorm(y[1]) + cnorm(y[2]);
+      own += __shfl_xor_sync(0xffffffffu, own, 1);
+      own += __shfl_xor_sync(0xffffffffu, own, 2);
+      const double nn = sqrt(own);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { y[k].re /= nn; y[k].im /= nn; }
+    }
+    t = __dadd_rn(t, a.dtq);  // SU:716
+  }
+
+  if (!active) return;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { Pb[(size_t)(2 * map[k]) * a.ld + i] = y[k].re; Pb[(size_t)(2 * map[k] + 1) * a.ld + i] = y[k].im; }
+  if (q < 2) {
+    long long* __restrict__ Xf = a.Rfix + (size_t)b * 3 * a.ld;
+    Rb[(size_t)c2 * a.ld + i] = r2;
+    Xf[(size_t)c2 * a.ld + i] = to_fixed(r2, a.invL, a.invL_lo);
+    Vb[(size_t)c2 * a.ld + i] = v2;
+    if (q == 0) {
+      Rb[i] = rx; Xf[i] = to_fixed(rx, a.invL, a.invL_lo);
+      Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp;
+    }
+  }
+}
+
 void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s) {
   long long threads = 2LL * a.nrows * a.B;
   int block = threads >= 148LL * 4 * 128 ? 128 : 64;
   int grid = (int)((threads + block - 1) / block);
   bool forced = a.forced_u != nullptr;
+  // Four lanes per ion is opt-in (MDQT_QT_LANES=4): measured on B200 at N = 3500 it is SLOWER than two lanes (35.2 vs
+  // 31.2 us per 25 substeps) -- the extra shuffle round trips per Runge-Kutta stage cost more latency than the shorter
+  // instruction stream saves. Kept as the verified alternative mapping (tests/test_gpu_parity.py runs it).
+  static const int lanes_override = [] { const char* e = getenv("MDQT_QT_LANES"); return e ? atoi(e) : 0; }();
+  const bool four = scheme == 12 && a.do_step && lanes_override == 4;
+  if (four) {
+    long long th = 4LL * a.nrows * a.B;
+    int g4 = (int)((th + 31) / 32);
+    if (forced) launch_kernel(k_substeps4<true>, dim3(g4), dim3(32), s, false, a, C);
+    else launch_kernel(k_substeps4<false>, dim3(g4), dim3(32), s, pdl_enabled(), a, C);
+    return;
+  }
   if (scheme == 12) {
     if (forced) launch_kernel(k_substeps<6, true>, dim3(grid), dim3(block), s, false, a, C);
     else launch_kernel(k_substeps<6, false>, dim3(grid), dim3(block), s, pdl_enabled(), a, C);

@@ -1,0 +1,25 @@
+"""GPU suite, part 3: the opt-in kernel mappings (environment knobs read once per process) stay parity-green:
+MDQT_QT_LANES=4 (four lanes per ion in the fused substep kernel), MDQT_PDL=1 (programmatic dependent launch) and the
+force-kernel plan overrides. Each runs __graft_entry__.smoke() -- one MD step with jumps against the oracle -- plus the
+no-jump and jump-table goldens in a fresh interpreter."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("env", [{"MDQT_QT_LANES": "4"}, {"MDQT_PDL": "1"}, {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_JSUB": "4"},
+                                 {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_NSPLIT": "3"}, {"MDQT_FORCE_JSUB": "1", "MDQT_FORCE_NSPLIT": "7"}])
+def test_variant_parity(env):
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=ROOT, env=e, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "nojump_golden or jump_table or forces_golden or trajectory_golden"], cwd=ROOT, env=e, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
