@@ -455,3 +455,48 @@ def test_ensemble_statistics_match_reference_stream(golden_dir):
     assert (np.abs(rows[:, 4] - ref[:, 4]) / se_v).max() < 4.5
     assert np.abs(rows[:, 5] / ref[:, 5] - 1).max() < 0.02
     assert rows[-1, 5] < rows[0, 5]  # laser cooling: var(v_x) decreases (red detuning)
+
+
+def test_forces_large_n_properties_and_sampled_rows():
+    """BASELINE's large-N shape (N = 1e5 here; the oracle is O(N^2)): size-independent properties -- Newton's third
+    law, translation invariance under a periodic shift, permutation equivariance -- and direct parity of 48 sampled
+    rows against a float64 numpy evaluation of SU:207-233 for those rows."""
+    n = 100000
+    p = su_params(n_ions=n, N0=n)
+    R = synthetic.random_positions(n, p.L, seed=11)
+    eng = Engine(p)
+    eng.upload(R=R)
+    eng.forces()
+    F = eng.download_forces()
+    assert np.all(np.isfinite(F))
+    scale = np.abs(F).sum(axis=1)
+    assert np.abs(F.sum(axis=1)).max() <= 1e-12 * scale.max()            # sum_i F_i = 0
+    rows = np.random.default_rng(5).choice(n, 48, replace=False)
+    lDeb = 1.0 / p.kappa
+    for i in rows:
+        d = R[:, i:i + 1] - R
+        d -= p.L * np.round(d / p.L)
+        r = np.sqrt((d ** 2).sum(axis=0))
+        m = (r > 0) & (r < p.L / 2)
+        ft = np.zeros(n)
+        ft[m] = (1. / r[m] + 1. / lDeb) * np.exp(-r[m] / lDeb) / (r[m] * r[m])
+        Fi = (d * ft).sum(axis=1)
+        denom = (ft * r).sum()
+        assert np.abs(F[:, i] - Fi).max() <= 1e-12 * denom, i
+    # periodic translation: forces are unchanged
+    shift = np.array([[0.37 * p.L], [5.5], [-2.25 * p.L]])
+    eng.upload(R=np.ascontiguousarray(R + shift))
+    eng.forces()
+    F2 = eng.download_forces()
+    assert np.abs(F2 - F).max() <= 1e-11 * np.abs(F).max()
+    # permutation equivariance
+    perm = np.random.default_rng(6).permutation(n)
+    eng.upload(R=np.ascontiguousarray(R[:, perm]))
+    eng.forces()
+    F3 = eng.download_forces()
+    assert np.abs(F3 - F[:, perm]).max() <= 1e-11 * np.abs(F).max()
+    # potential energy: sampled-row estimate is not possible, but E_pot must be translation invariant too
+    e1 = eng.Epotential()
+    eng.upload(R=R)
+    e0 = eng.Epotential()
+    assert abs(e1 - e0) <= 1e-12 * abs(e0)
