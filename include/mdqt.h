@@ -20,7 +20,7 @@
  * device every compute entry point fails with MDQT_ENODEVICE.
  *
  * Host array layouts are the reference's: R, V, F = double [3][ld] (component-major, ld >= n_ions);
- * psi = double [n_ions][S][2] (re, im) with S = scheme (12 or 7); tPart = double [n_ions].
+ * psi = double [n_ions][S][2] (re, im) with S = scheme (12, 7, 5 or 3); tPart = double [n_ions].
  * With n_traj > 1 (an ensemble shard batched in one handle) every array gains a leading [n_traj] dimension.
  * A handle is bound to one GPU; calls on one handle are stream-ordered and must not be made concurrently.
  */
@@ -41,6 +41,8 @@ extern "C" {
 #define MDQT_SCHEME_NONE 0 /* MD only: no wavefunctions (MD family) */
 #define MDQT_SCHEME_SR7 7  /* 7-level 408 nm pump, MC408L / MC408Q / FZ408L */
 #define MDQT_SCHEME_SR12 12 /* 12-level Sr+ S1/2,P3/2,D5/2 laser cooling, SU / MG */
+#define MDQT_SCHEME_CA5 5  /* 5-level 422 nm pump (S1/2, P1/2, D reservoir), MC422L / FZ422L */
+#define MDQT_SCHEME_V3 3   /* 3-level J=0 <-> J=1 test system without plasma, laserCoolNoPlasmaThreeState.cpp (TS) */
 
 typedef struct mdqt_handle mdqt_handle;
 
@@ -80,6 +82,9 @@ int mdqt_params_su(mdqt_params* p, double Ge, double density, double sig0, doubl
 int mdqt_params_md(mdqt_params* p, int scheme, int n_ions, double kappa, double density, double timeStep,
                    double detuning, double Om, int quad);
 
+/* 3-level test program constants (TS:55-58, 91, 390): dt = 0.01/gamma, velocities already in quantum units. */
+int mdqt_params_ts(mdqt_params* p, int n_ions, double detuning, double Om);
+
 int mdqt_device_count(void);
 const char* mdqt_last_error(void);
 const char* mdqt_version(void);
@@ -117,12 +122,26 @@ int mdqt_populations(mdqt_handle* h, double* pops);
  * collisions (probability dt*collisionFreq, velocities ~ N(0, sigma_v^2)) and the optional laser friction term
  * (laser: 0 none, 1 three-axis MD:494-496, 2 x only MD:491; coefficient = 1.234e-6*beta/sqrt(n)). */
 int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff);
-/* 7-level pump sweeps without kick (MC408L:1227-1232 inner loop): nsub x qstep() at frozen velocities. */
+/* nsub x qstep() without step(): the 7-level (MC408L:555-756, FZ408L:396-598) and 5-level (MC422L:552-727) pump
+ * sweeps at frozen velocities without kick, and the 3-level test system (TS:140-293; V_x += kick, tPart tracked). */
 int mdqt_qsteps(mdqt_handle* h, int nsub);
+/* FZ family: step() (FZ408L:377-390) = step_R(dt/2), step_V(dt) with forces() inside, step_R(dt/2); while t <= 0 the
+ * drifts are the 2nd-order start that recomputes forces() (FZ408L:332-340). Does not advance t. */
+int mdqt_leapfrog_step(mdqt_handle* h, double dt);
+/* FZ family main loop outside the pump window: t += nsub * quantumTimestep by repeated addition (FZ408L:1066). */
+int mdqt_advance_time(mdqt_handle* h, int nsub);
+/* Projective spin measurement after the pump: tagParticles() (MC408L:1022-1067, MC422L:992-1036) ==
+ * measureSpinUps() (FZ408L:600-647, FZ422L:570-611). tagged = int32 [n_traj][n_ions] (may be NULL),
+ * n_tagged = int32 [n_traj]. Two uniforms per ion from the Philox stream at the current substep index. */
+int mdqt_tag_particles(mdqt_handle* h, int32_t* tagged, int32_t* n_tagged);
+/* Zfunc() (FZ408L:938-961): velocity autocorrelation <v_x(t0) v_x(t)>; start != 0 stores v_x(t0) first. vaf[n_traj]. */
+int mdqt_vaf(mdqt_handle* h, int start, double* vaf);
 
 /* Test hook: replace the Philox stream by caller-supplied uniforms u[nsub][n_ions][5] (rand, rand2, randDOrS,
  * randDir, rand3) for the next substeps/qsteps calls (n_traj must be 1). NULL restores Philox. */
 int mdqt_set_forced_uniforms(mdqt_handle* h, const double* u, int nsub);
+/* Test hook: uniforms u[n_ions][2] for the next mdqt_tag_particles calls (n_traj must be 1). NULL restores Philox. */
+int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u);
 /* Test hook for the MD-family Andersen thermostat: per-ion collision uniforms u[n_ions] and the velocities
  * v[n_ions][3] assigned on collision, instead of the Philox/Box-Muller draws. NULL restores Philox. */
 int mdqt_set_forced_collisions(mdqt_handle* h, const double* u, const double* v);

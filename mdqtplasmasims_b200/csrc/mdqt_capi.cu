@@ -29,7 +29,8 @@ struct mdqt_handle {
   mdqt_params p;
   int N, B, S, ld, row0, nrows;
   cudaStream_t stream;
-  double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops;
+  double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops, *vhold, *forced_tag;
+  int* tagged;      // [B][N] spin tags + [B] counts (allocated on first use)
   unsigned* counters;
   long long* Rfix;  // periodic fixed-point copy of R (what the pair kernels read)
   int rfix_dirty;   // R was written by an upload / externally: refresh Rfix before the next pair kernel
@@ -98,6 +99,31 @@ int mdqt_params_md(mdqt_params* p, int scheme, int n_ions, double kappa, double 
   p->vKick = 0.001208 / p->pv2qv;                                 // MC408L:122
   p->density = density; p->sig0 = 1.0;
   p->seed = 12345;
+  if (scheme == MDQT_SCHEME_CA5) {                                // 422 nm constants (MC422L:113-121)
+    p->g2E = 174.07 * .894 / sqrt(density);
+    p->substeps_per_md = (int)round(87 * .894 / sqrt(density));
+    p->dtq = timeStep / p->substeps_per_md;
+    p->pv2qv = 1.1821 * pow(density, 1. / 6) * .967;
+    p->dR = 0.0753;
+    p->vKick = 0.001257 / p->pv2qv;
+  }
+  return MDQT_OK;
+}
+
+int mdqt_params_ts(mdqt_params* p, int n_ions, double detuning, double Om) {
+  if (!p) return fail(MDQT_EINVAL, "null params");
+  memset(p, 0, sizeof(*p));
+  p->struct_bytes = (int32_t)sizeof(*p);
+  p->scheme = MDQT_SCHEME_V3;
+  p->n_ions = n_ions; p->n_traj = 1; p->traj0 = 1; p->device = 0;
+  p->L = 1.0; p->kappa = 0.0; p->rcut = 0.5;                      // no plasma in this program: unused
+  p->substeps_per_md = 1;
+  p->dtq = 0.01;                                                  // dt (TS:390), already in units of 1/gamma
+  p->g2E = 1.0; p->pv2qv = 1.0;                                   // velQuant = V[0][i] (TS:154)
+  p->detuning = detuning; p->Om = Om;
+  p->vKick = 0.0012076;                                           // TS:91
+  p->density = 1.0; p->sig0 = 1.0;
+  p->seed = 12345;
   return MDQT_OK;
 }
 
@@ -147,7 +173,8 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   if (!p || !out) return fail(MDQT_EINVAL, "null argument");
   *out = nullptr;
   if (p->struct_bytes != (int32_t)sizeof(mdqt_params)) return fail(MDQT_EINVAL, "mdqt_params size mismatch (ABI)");
-  if (p->scheme != MDQT_SCHEME_NONE && p->scheme != MDQT_SCHEME_SR7 && p->scheme != MDQT_SCHEME_SR12)
+  if (p->scheme != MDQT_SCHEME_NONE && p->scheme != MDQT_SCHEME_SR7 && p->scheme != MDQT_SCHEME_SR12 &&
+      p->scheme != MDQT_SCHEME_CA5 && p->scheme != MDQT_SCHEME_V3)
     return fail(MDQT_EINVAL, "unknown level scheme");
   if (p->n_ions < 1 || p->n_traj < 1) return fail(MDQT_EINVAL, "n_ions and n_traj must be >= 1");
   if (!(p->L > 0) || !(p->rcut > 0) || !(p->kappa >= 0)) return fail(MDQT_EINVAL, "L, rcut must be > 0 and kappa >= 0");
@@ -168,6 +195,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->ld = (p->n_ions + 31) & ~31;
   h->t = 0.0; h->substep = 0; h->vv_step = 0; h->Rfix = nullptr; h->rfix_dirty = 1;
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
+  h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
   h->timing = false; h->ev_used = 0; h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
   plan_force(h);
   if (h->S) fill_qt_consts(h->qc, h->S, p->Om, p->OmDP, p->dR, p->vKick, p->vKickDP, p->dtq, p->g2E, p->quad);
@@ -209,8 +237,9 @@ int mdqt_destroy(mdqt_handle* h) {
   cudaSetDevice(h->p.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   double* bufs[] = {h->R, h->V, h->F, h->oldF, h->psi, h->psi_stage, h->tPart, h->Fpart, h->epot_partials, h->scalars,
-                    h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn};
+                    h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn, h->vhold, h->forced_tag};
   for (double* b : bufs) if (b) cudaFree(b);
+  if (h->tagged) cudaFree(h->tagged);
   if (h->counters) cudaFree(h->counters);
   if (h->Rfix) cudaFree(h->Rfix);
   for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
@@ -320,14 +349,15 @@ static void refresh_fixed(mdqt_handle* h) {
   h->rfix_dirty = 0;
 }
 
-static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step) {
+static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step, int do_kick) {
   QTArgs a;
   const mdqt_params& p = h->p;
   a.R = h->R; a.V = h->V; a.F = h->F; a.psi = h->psi; a.tPart = h->tPart;
   a.Rfix = h->Rfix; a.invL = 1.0 / p.L; a.invL_lo = fma(-a.invL, p.L, 1.0) * a.invL;
   a.forced_u = h->forced_u ? h->forced_u + (size_t)h->forced_cursor * h->N * 5 : nullptr;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = p.traj0;
-  a.nsub = nsub; a.do_step = do_step; a.renorm = p.renormalize; a.quad = p.quad;
+  a.nsub = nsub; a.do_step = do_step; a.do_kick = do_kick; a.do_tpart = do_kick;  // tPart lives where the kick does (SU, TS)
+  a.scheme = h->S; a.S = h->S; a.renorm = p.renormalize; a.quad = p.quad;
   a.t0 = h->t; a.substep0 = h->substep; a.seed = p.seed;
   a.L = p.L; a.dtq = p.dtq;
   a.detuning = p.detuning; a.detuningDP = p.detuningDP; a.Om = p.Om; a.OmDP = p.OmDP; a.dR = p.dR; a.kRat = p.kRat;
@@ -345,14 +375,14 @@ static cudaEvent_t next_event(mdqt_handle* h) {
   return h->ev[h->ev_used++];
 }
 
-static int enqueue_substeps(mdqt_handle* h, int nsub, int do_step) {
+static int enqueue_substeps(mdqt_handle* h, int nsub, int do_step, int do_kick) {
   if (h->forced_u && h->forced_cursor + nsub > h->forced_nsub) return fail(MDQT_ESTATE, "forced uniforms exhausted");
-  QTArgs a = qt_args(h, nsub, do_step);
+  QTArgs a = qt_args(h, nsub, do_step, do_kick);
   launch_substeps(a, h->qc, h->S, h->stream);
   if (h->forced_u) h->forced_cursor += nsub;
   h->substep += (uint64_t)nsub;
-  if (do_step)
-    for (int s = 0; s < nsub; s++) h->t += h->p.dtq;  // the same repeated addition as SU:716 / the kernel
+  if (do_step || h->S == MDQT_SCHEME_V3)
+    for (int s = 0; s < nsub; s++) h->t += h->p.dtq;  // the same repeated addition as SU:716 / the kernel (TS:387)
   return MDQT_OK;
 }
 
@@ -371,7 +401,7 @@ int mdqt_substeps(mdqt_handle* h, int nsub) {
   if (nsub < 0) return fail(MDQT_EINVAL, "nsub < 0");
   if (nsub == 0) return MDQT_OK;
   CU(cudaSetDevice(h->p.device));
-  int rc = enqueue_substeps(h, nsub, 1);
+  int rc = enqueue_substeps(h, nsub, 1, 1);
   if (rc) return rc;
   CU(cudaGetLastError());
   return MDQT_OK;
@@ -379,11 +409,13 @@ int mdqt_substeps(mdqt_handle* h, int nsub) {
 
 int mdqt_qsteps(mdqt_handle* h, int nsub) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
-  if (h->S != MDQT_SCHEME_SR7) return fail(MDQT_ESTATE, "mdqt_qsteps needs the 7-level scheme");
+  if (h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5 && h->S != MDQT_SCHEME_V3)
+    return fail(MDQT_ESTATE, "mdqt_qsteps needs the 7-, 5- or 3-level scheme");
   if (nsub < 0) return fail(MDQT_EINVAL, "nsub < 0");
   if (nsub == 0) return MDQT_OK;
   CU(cudaSetDevice(h->p.device));
-  int rc = enqueue_substeps(h, nsub, 0);
+  // pump schemes: frozen velocities, no kick (MC408L:754, MC422L:722); 3-level test system: kick, no positions (TS:283)
+  int rc = enqueue_substeps(h, nsub, 0, h->S == MDQT_SCHEME_V3 ? 1 : 0);
   if (rc) return rc;
   CU(cudaGetLastError());
   return MDQT_OK;
@@ -400,7 +432,7 @@ int mdqt_md_steps(mdqt_handle* h, int nsteps) {
     if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
     launch_forces(force_args(h), h->stream);
     if (h->timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
-    int rc = enqueue_substeps(h, h->p.substeps_per_md, 1);
+    int rc = enqueue_substeps(h, h->p.substeps_per_md, 1, 1);
     if (rc) return rc;
     if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
   }
@@ -494,6 +526,81 @@ int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v
   a.A = h->F;
   launch_vv_velocities(a, h->stream);   // stepVelocities (MD:509)
   h->vv_step++;
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_leapfrog_step(mdqt_handle* h, double dt) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!(dt > 0)) return fail(MDQT_EINVAL, "dt must be > 0");
+  CU(cudaSetDevice(h->p.device));
+  LFArgs a;
+  a.R = h->R; a.V = h->V; a.F = h->F; a.Rfix = h->Rfix;
+  a.invL = 1.0 / h->p.L; a.invL_lo = fma(-a.invL, h->p.L, 1.0) * a.invL; a.L = h->p.L;
+  a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
+  a.DT = 0.5 * dt; a.DTV = dt;
+  const int first = !(h->t > 0);  // FZ408L:321: the 2nd-order start recomputes forces() inside step_R
+  refresh_fixed(h);
+  if (first) {
+    launch_forces(force_args(h), h->stream);
+    a.first = 1; a.kick = 0; a.drift = 1; launch_lf(a, h->stream);   // step_R(0.5 dt)
+    launch_forces(force_args(h), h->stream);
+    a.first = 0; a.kick = 1; a.drift = 0; launch_lf(a, h->stream);   // step_V(dt)
+    launch_forces(force_args(h), h->stream);
+    a.first = 1; a.kick = 0; a.drift = 1; launch_lf(a, h->stream);   // step_R(0.5 dt)
+  } else {
+    a.first = 0; a.kick = 0; a.drift = 1; launch_lf(a, h->stream);   // step_R(0.5 dt)
+    launch_forces(force_args(h), h->stream);                         // step_V(dt): forces(); V += dt F
+    a.kick = 1; launch_lf(a, h->stream);                             //   ... fused with the second step_R(0.5 dt)
+  }
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_advance_time(mdqt_handle* h, int nsub) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  for (int s = 0; s < nsub; s++) h->t += h->p.dtq;  // FZ408L:1066: t += quantumTimestep outside the pump window
+  return MDQT_OK;
+}
+
+int mdqt_tag_particles(mdqt_handle* h, int32_t* tagged, int32_t* n_tagged) {
+  if (!h || !n_tagged) return fail(MDQT_EINVAL, "null argument");
+  if (h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5) return fail(MDQT_ESTATE, "tagging needs the 7- or 5-level scheme");
+  CU(cudaSetDevice(h->p.device));
+  const size_t n = (size_t)h->B * h->N;
+  if (!h->tagged) CU(cudaMalloc((void**)&h->tagged, sizeof(int) * (n + h->B)));
+  launch_tag(h->psi, h->S, h->N, h->ld, h->B, h->p.traj0, h->p.seed, h->substep, h->forced_tag, h->tagged, h->tagged + n, h->stream);
+  if (tagged) CU(cudaMemcpyAsync(tagged, h->tagged, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(n_tagged, h->tagged + n, sizeof(int) * h->B, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->forced_tag) { cudaFree(h->forced_tag); h->forced_tag = nullptr; }
+  if (!u) return MDQT_OK;
+  if (h->B != 1) return fail(MDQT_ESTATE, "forced uniforms need n_traj == 1");
+  CU(cudaMalloc((void**)&h->forced_tag, (size_t)h->N * 16));
+  CU(cudaMemcpy(h->forced_tag, u, (size_t)h->N * 16, cudaMemcpyHostToDevice));
+  return MDQT_OK;
+}
+
+int mdqt_vaf(mdqt_handle* h, int start, double* vaf) {
+  if (!h || !vaf) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  if (!h->vhold) {
+    if (!start) return fail(MDQT_ESTATE, "mdqt_vaf: no interval started");
+    CU(cudaMalloc((void**)&h->vhold, (size_t)h->B * h->ld * 8));
+  }
+  if (start)  // Vholder[j] = V[0][j] (FZ408L:949-954)
+    CU(cudaMemcpy2DAsync(h->vhold, (size_t)h->ld * 8, h->V, (size_t)3 * h->ld * 8, (size_t)h->ld * 8, h->B, cudaMemcpyDeviceToDevice, h->stream));
+  launch_vaf(h->V, h->vhold, h->N, h->ld, h->B, h->scalars, h->stream);
+  CU(cudaMemcpyAsync(vaf, h->scalars, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   return MDQT_OK;
 }

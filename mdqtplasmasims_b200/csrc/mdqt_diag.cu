@@ -82,16 +82,35 @@ void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int
   k_vel_dist<<<grid, 256, 0, s>>>(V, diag_out, N, ld, pvel);
 }
 
-// pops[b][i][3] = popS, popP, popD with the reference's state grouping (S: 0,1; P: 2..5; D: 6..S-1)
+// Zfunc() (FZ408L:938-961): out[b] = sum_j (1/N) Vhold_x[j] V_x[j], fixed-order block reduction; one CTA per trajectory
+__global__ void __launch_bounds__(1024) k_vaf(const double* __restrict__ V, const double* __restrict__ Vhold, int N, int ld,
+                                              double* __restrict__ out) {
+  __shared__ double sred[32];
+  const int b = blockIdx.x;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const double* v0 = Vhold + (size_t)b * ld;
+  const double invN = 1 / ((double)N);
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += invN * (v0[i] * vx[i]);
+  s = block_sum_1024(s, sred);
+  if (threadIdx.x == 0) out[b] = s;
+}
+void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s) {
+  k_vaf<<<B, 1024, 0, s>>>(V, Vhold, N, ld, out);
+}
+
+// pops[b][i][3] = popS, popP, popD with the reference's state grouping (12/7-level: S 0,1; P 2..5; D 6..S-1)
 __global__ void k_populations(const double* __restrict__ psi, int S, int N, int ld, double* __restrict__ pops) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double* p = psi + (size_t)b * 2 * S * ld;
   double pop[3] = {0.0, 0.0, 0.0};
+  // ground / excited / reservoir grouping: 12- and 7-level 2+4(+D), 5-level 2+2+1 (MC422L:104-108), 3-level 1+2 (TS:95-97)
+  const int nS = (S == 3) ? 1 : 2, nP = (S >= 7) ? 4 : 2;
   for (int k = 0; k < S; k++) {
     double re = p[(size_t)(2 * k) * ld + i], im = p[(size_t)(2 * k + 1) * ld + i];
-    pop[k < 2 ? 0 : (k < 6 ? 1 : 2)] += re * re + im * im;
+    pop[k < nS ? 0 : (k < nS + nP ? 1 : 2)] += re * re + im * im;
   }
   double* o = pops + ((size_t)b * N + i) * 3;
   o[0] = pop[0]; o[1] = pop[1]; o[2] = pop[2];

@@ -32,7 +32,10 @@ struct QTArgs {
   const double* forced_u;                 // [nsub][N][5] or null
   int N, ld, B, row0, nrows, traj0;
   int nsub;
-  int do_step;                            // 1: step()+qstep() with kick (SU); 0: qstep only, frozen V (MC408L)
+  int scheme, S;                          // level scheme (12, 7, 5, 3) and its number of states (psi stride)
+  int do_step;                            // 1: step() before every qstep(), global t advanced (SU); 0: qstep only
+  int do_kick;                            // 1: V_x += optical-force / recoil kick (SU:705, TS:283); 0: frozen V (MC408L:754)
+  int do_tpart;                           // 1: tPart tracked (+= dtq, reset on a jump; SU:482, TS:155)
   int renorm, quad;
   double t0; uint64_t substep0; uint64_t seed;
   double L, dtq;
@@ -81,6 +84,20 @@ void launch_vv_velocities(const VVArgs& a, cudaStream_t s);
 void launch_diag(const double* V, int N, int ld, int B, double* scratch, double* diag_out, cudaStream_t s);
 void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s);
 void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s);
+// projective spin measurement after the pump (tagParticles MC408L:1022-1067 / MC422L:992-1036; measureSpinUps
+// FZ408L:600-647): tagged[B][N] (0/1), count[B]; u = forced uniforms [N][2] or null (Philox call 6)
+void launch_tag(const double* psi, int S, int N, int ld, int B, int traj0, uint64_t seed, uint64_t substep,
+                const double* forced_u, int* tagged, int* count, cudaStream_t s);
+// FZ-family leap-frog pieces (FZ408L:317-369): R += DT*V [+ DT^2*F when first], single wrap; V += DT*F
+struct LFArgs {
+  double* R; double* V; const double* F; long long* Rfix;
+  double invL, invL_lo, L, DT;
+  int N, ld, B, row0, nrows, first, kick, drift;  // kick: V += DTV*F first; drift: R += DT*V (2nd-order start if first)
+  double DTV;
+};
+void launch_lf(const LFArgs& a, cudaStream_t s);
+// Zfunc (FZ408L:938-961): vaf[B] = 1/N sum_j Vhold_x[j] V_x[j]
+void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s);
 void launch_transpose_psi_in(const double* psi_aos, double* psi_soa, int S, int N, int ld, int B, cudaStream_t s);
 void launch_transpose_psi_out(const double* psi_soa, double* psi_aos, int S, int N, int ld, int B, cudaStream_t s);
 double run_fp64_peak(cudaStream_t s);

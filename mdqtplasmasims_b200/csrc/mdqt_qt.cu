@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   // inactive lanes still run (the shuffles are warp-wide) on a harmless shadow of the first ion; they never store
   const int b = active ? (int)(slot / a.nrows) : 0;
   const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
-  constexpr int S = (NL == 6) ? 12 : 7;
+  const int S = a.S;
 
   double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
   double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     rx = Rb[i]; r2 = Rb[(size_t)c2 * a.ld + i];
     v2 = Vb[(size_t)c2 * a.ld + i];
     fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
-    tp = a.tPart[(size_t)b * a.ld + i];
   }
+  if (a.do_tpart) tp = a.tPart[(size_t)b * a.ld + i];
   double t = a.t0;
   const double DT = 0.5 * a.dtq;
   const double dEDP = -a.detuning + a.detuningDP;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       expDet = 0.0126 * a.fracOfSig * a.Te * t /
                (sqrt(a.density) * a.sig0 * sqrt(1 + 0.00014314 * t * t * a.Te / (a.density * a.sig0 * a.sig0)));
     const double vq = vx * a.pv2qv;
-    if (a.do_step) tp = __dadd_rn(tp, a.dtq);
+    if (a.do_tpart) tp = __dadd_rn(tp, a.dtq);
 
     // the uniforms of this (ion, substep): both lanes of an ion draw the same numbers
     double u0, u1;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     double n2, n3, n4, n5;
     if (NL == 6) {  // 12-level: idx2 = B.P1, idx3 = A.P1, idx4 = B.P2, idx5 = A.P2
       n2 = lane ? nown1 : noth1; n3 = lane ? noth1 : nown1; n4 = lane ? nown2 : noth2; n5 = lane ? noth2 : nown2;
-    } else {        // 7-level:  idx2 = A.P1, idx3 = B.P1, idx4 = A.P2, idx5 = B.P2
+    } else {        // 7-level:  idx2 = A.P1, idx3 = B.P1, idx4 = A.P2, idx5 = B.P2  (5- and 3-level: unused slots hold 0)
       n2 = lane ? noth1 : nown1; n3 = lane ? nown1 : noth1; n4 = lane ? noth2 : nown2; n5 = lane ? nown2 : noth2;
     }
     const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;   // SU:484-485
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     // ---- no-jump branch, evaluated by every lane (jumps are rare, and a warp-uniform flow keeps the cross-lane
     //      exchanges on plain full-mask shuffles); lanes that jump discard the result below ----
     double kick = 0.0;
-    if (a.do_step) {  // optical force from the pre-step coherences (SU:490-503)
+    if (a.do_kick) {  // optical force from the pre-step coherences (SU:490-503; TS:170-174)
       kick = ksA * im_acb(y[0], y[1]) - ksB * im_acb(y[0], y[2]);
       if (NL == 6)
         kick += kd0 * im_acb(y[4], y[2]) + kd1 * im_acb(y[3], y[1]) - kd2 * im_acb(y[5], y[2]) - kd3 * im_acb(y[4], y[1]);
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
       const bool sDecay = !(u2 < C.dfrac);
       kick = 0.0;
-      if (a.do_step && lane == 0) {  // counted once in the cross-lane sum
+      if (a.do_kick && lane == 0) {  // counted once in the cross-lane sum
         double mag = sDecay ? a.vKick : a.vKickDP;
         kick = (u3 < 0.5) ? mag : -mag;
       }
@@ -352,18 +352,25 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
         else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
         else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
         else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
-      } else {
+      } else if (a.scheme == 7) {
         // the 7-level file draws its 4th uniform (rand3) only for S decays out of states 4 and 5; with a
         // counter-based stream the slot is simply left unused otherwise
         if (u1 < p3) dest = sDecay ? 0 : 6;
         else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : 6;
         else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 0 : 1) : 6;
         else dest = sDecay ? 1 : 6;
+      } else if (a.scheme == 5) {
+        // 5-level 422 nm pump (MC422L:660-720): p3 = 0 and p4 = prob3 here, so p3 + p4 is the reference's prob3
+        // exactly; no randDir draw exists in that file (slot 3 unused), rand3 (slot 4) only on S decays
+        if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 1 : 0) : 4;
+        else dest = sDecay ? (u4 < C.tS[1] ? 0 : 1) : 4;
+      } else {
+        dest = 0;  // 3-level: back to the single ground state (TS:272-274); draws rand and randDir only
       }
 #pragma unroll
       for (int k = 0; k < NL; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
     }
-    if (a.do_step) {
+    if (a.do_kick) {
       kick = kick + __shfl_xor_sync(0xffffffffu, kick, 1);
       vx = __dadd_rn(vx, kick);  // SU:705
     }
@@ -389,9 +396,12 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     Vb[(size_t)c2 * a.ld + i] = v2;
     if (lane == 0) {
       Rb[i] = rx; Xf[i] = to_fixed(rx, a.invL, a.invL_lo);
-      Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp;
+      Vb[i] = vx;
     }
+  } else if (a.do_kick && lane == 0) {
+    Vb[i] = vx;
   }
+  if (a.do_tpart && lane == 0) a.tPart[(size_t)b * a.ld + i] = tp;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -753,6 +763,70 @@ void launch_vv_positions(const VVArgs& a, cudaStream_t s) {
 void launch_vv_velocities(const VVArgs& a, cudaStream_t s) {
   long long n = (long long)a.nrows * a.B;
   k_vv_velocities<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Projective spin measurement after the pump: tagParticles() (MC408L:1022-1067, MC422L:992-1036) and
+// measureSpinUps() (FZ408L:600-647, FZ422L:570-611). One thread per ion; the two uniforms of an ion are Philox
+// call 6 of the (substep, ion, trajectory) counter, or u[N][2] when forced.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_tag(const double* __restrict__ psi, int S, int N, int ld, int traj0, uint64_t seed, uint64_t substep,
+                      const double* __restrict__ forced_u, int* __restrict__ tagged, int* __restrict__ count) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* p = psi + (size_t)b * 2 * S * ld;
+  auto nrm = [&](int k) { const double re = p[(size_t)(2 * k) * ld + i], im = p[(size_t)(2 * k + 1) * ld + i]; return __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)); };
+  double ua, ub;
+  if (forced_u) { ua = forced_u[2 * i]; ub = forced_u[2 * i + 1]; }
+  else { uint4 o = philox_call(seed, (unsigned)(traj0 + b), (unsigned)i, substep, 6); ua = u52(o.x, o.y); ub = u52(o.z, o.w); }
+  const double n1 = nrm(0), n3 = nrm(2), n4 = nrm(3);
+  int up;
+  if (S == 7) {  // MC408L:1034-1062
+    const double n5 = nrm(4);
+    const double c1 = __dadd_rn(n1, n3), c2 = __dadd_rn(c1, n4), c3 = __dadd_rn(c2, n5);
+    up = (ua < c1) ? 1 : (ua < c2) ? (ub < 2. / 3) : (ua < c3) ? (ub < 1. / 3) : 0;
+  } else {       // 5-level, MC422L:1004-1031
+    const double c2 = __dadd_rn(n1, n3), c3 = __dadd_rn(c2, n4);
+    up = (ua < n1) ? 1 : (ua < c2) ? (ub < 1. / 3) : (ua < c3) ? (ub < 2. / 3) : 0;
+  }
+  tagged[(size_t)b * N + i] = up;
+  if (up) atomicAdd(&count[b], 1);
+}
+void launch_tag(const double* psi, int S, int N, int ld, int B, int traj0, uint64_t seed, uint64_t substep,
+                const double* forced_u, int* tagged, int* count, cudaStream_t s) {
+  cudaMemsetAsync(count, 0, sizeof(int) * B, s);
+  dim3 grid((N + 255) / 256, B);
+  k_tag<<<grid, 256, 0, s>>>(psi, S, N, ld, traj0, seed, substep, forced_u, tagged, count);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FZ-family leap-frog pieces (FZ408L:317-369): optional kick V += DTV*F, optional drift R += DT*V (+ DT*DT*F while
+// t <= 0), single wrap into [0,L]; every operation rounded as the reference's expression tree.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_lf(LFArgs a) {
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)a.nrows * a.B * 3) return;
+  int b = (int)(g / (3LL * a.nrows));
+  int rem = (int)(g % (3LL * a.nrows));
+  int c = rem / a.nrows, i = a.row0 + rem % a.nrows;
+  size_t idx = ((size_t)b * 3 + c) * a.ld + i;
+  double v = a.V[idx];
+  const double f = a.F[idx];
+  if (a.kick) { v = __dadd_rn(v, __dmul_rn(a.DTV, f)); a.V[idx] = v; }  // FZ408L:364-366
+  if (a.drift) {
+    double r = a.R[idx];
+    if (a.first) r = __dadd_rn(r, __dadd_rn(__dmul_rn(a.DT, v), __dmul_rn(__dmul_rn(a.DT, a.DT), f)));  // FZ408L:336-338
+    else r = __dadd_rn(r, __dmul_rn(a.DT, v));                                                          // FZ408L:325-327
+    if (r < 0) r = __dadd_rn(r, a.L);
+    if (r > a.L) r = __dadd_rn(r, -a.L);
+    a.R[idx] = r;
+    a.Rfix[idx] = to_fixed(r, a.invL, a.invL_lo);
+  }
+}
+void launch_lf(const LFArgs& a, cudaStream_t s) {
+  long long n = 3LL * a.nrows * a.B;
+  k_lf<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
 }
 
 }  // namespace mdqt

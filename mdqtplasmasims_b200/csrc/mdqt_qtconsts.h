@@ -63,6 +63,34 @@ inline void fill_qt_consts(QTConsts& C, int scheme, double Om, double OmDP, doub
     C.tD[6] = gs[8] * gs[8] / dR;   C.tD[7] = gs[8] * gs[8] / dR + gs[7] * gs[7] / dR;
     C.kick_sp = 1 * vKick * Om * dtq * g2E;
     C.kick_dp = vKickDP * (OmDP / dR) * dtq * g2E;
+  } else if (scheme == 5) {  // 5-level 422 nm pump: gs are rates (MC422L:1144-1155); states S-1/2, S+1/2, P+1/2, P-1/2, D
+    double gs[6] = {2. / 3, 1. / 3, 2. / 3, 1. / 3, dR, dR};
+    static const int upper[6] = {2, 3, 3, 2, 2, 3};  // cs[k] = |lower><upper| (MC422L:1144-1149)
+    double gam[5] = {0};
+    for (int k = 0; k < 6; k++) gam[upper[k]] += gs[k];
+    QTLane& A = C.lane[0];
+    QTLane& B = C.lane[1];
+    // lane A: S-1/2 <-> P-1/2 (energy -det + vq: the P2 slot); lane B: S+1/2 <-> P+1/2 (energy -det - vq: the P1 slot)
+    const int mapA[6] = {0, -1, 3, 4, -1, -1}, mapB[6] = {1, 2, -1, -1, -1, -1};
+    for (int k = 0; k < 6; k++) { A.map[k] = mapA[k]; B.map[k] = mapB[k]; }
+    A.c20 = -Om / 2 * sqrt(gs[2]);  // |1><4| (MC422L:594)
+    B.c10 = -Om / 2 * sqrt(gs[0]);  // |2><3|
+    A.gam2 = gam[3]; B.gam1 = gam[2];
+    C.gam[1] = gam[2]; C.gam[2] = gam[3];  // slots (A.P1, B.P1, A.P2, B.P2) = (-, state 2, state 3, -)
+    C.tS[0] = gs[0]; C.tS[1] = gs[2];      // MC422L:685, 701
+  } else if (scheme == 3) {  // 3-level J=0 <-> J=1 sigma+/- test system (TS:95-101, 379-382): ground, m=+1, m=-1
+    double gs[2] = {1, 1};
+    QTLane& A = C.lane[0];
+    QTLane& B = C.lane[1];
+    // one block: ground <-> state 2 (energy -det - v: P1 slot) and ground <-> state 1 (energy -det + v: P2 slot)
+    const int mapA[6] = {0, 2, 1, -1, -1, -1}, mapB[6] = {-1, -1, -1, -1, -1, -1};
+    for (int k = 0; k < 6; k++) { A.map[k] = mapA[k]; B.map[k] = mapB[k]; }
+    A.c10 = -Om / 2 * sqrt(gs[0]);  // |1><3| sqrt(gs[0]) (TS:179)
+    A.c20 = -Om / 2 * sqrt(gs[1]);  // |1><2| sqrt(gs[1])
+    A.gam1 = gs[1]; A.gam2 = gs[0]; // cs[0] = |1><2|, cs[1] = |1><3| (TS:379-380)
+    C.gam[0] = gs[1]; C.gam[2] = gs[0];
+    A.gA = sqrt(gs[0]); A.gB = sqrt(gs[1]);
+    C.kick_sp = 1 * vKick * Om * dtq * g2E;  // TS:174 (dt; the caller passes g2E = 1)
   } else {  // 7-level pump: gs are rates (MC408L:1181-1190)
     double gs[10] = {1, 2. / 3, 1. / 3, 1. / 3, 2. / 3, 1, dR, dR, dR, dR};
     static const int upper[10] = {2, 3, 4, 3, 4, 5, 2, 3, 4, 5};

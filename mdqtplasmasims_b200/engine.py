@@ -15,7 +15,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MDQT_LIB_PATH") or os.path.join(HERE, "libmdqt_b200.so")  # env: kernel A/B builds
 
-SCHEME_NONE, SCHEME_SR7, SCHEME_SR12 = 0, 7, 12
+SCHEME_NONE, SCHEME_SR7, SCHEME_SR12, SCHEME_CA5, SCHEME_V3 = 0, 7, 12, 5, 3
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
@@ -44,7 +44,8 @@ ABI_SYMBOLS = [
     "mdqt_md_steps_host", "mdqt_epot", "mdqt_diagnostics", "mdqt_vel_dist", "mdqt_populations", "mdqt_vv_step",
     "mdqt_qsteps", "mdqt_set_forced_uniforms", "mdqt_set_forced_collisions", "mdqt_philox_uniforms", "mdqt_device_ptr",
     "mdqt_device_ld", "mdqt_stream", "mdqt_mark_wrapped", "mdqt_force_plan", "mdqt_enable_timing",
-    "mdqt_kernel_time_ms", "mdqt_fp64_peak",
+    "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
+    "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms",
 ]
 
 _lib = None
@@ -95,6 +96,12 @@ def load_library():
     L.mdqt_enable_timing.argtypes = [vp, ctypes.c_int]
     L.mdqt_kernel_time_ms.argtypes = [vp, ctypes.c_int, c_double_p, ctypes.POINTER(ctypes.c_int)]
     L.mdqt_fp64_peak.argtypes = [vp, c_double_p]
+    L.mdqt_params_ts.argtypes = [ctypes.POINTER(Params), ctypes.c_int, ctypes.c_double, ctypes.c_double]
+    L.mdqt_leapfrog_step.argtypes = [vp, ctypes.c_double]
+    L.mdqt_advance_time.argtypes = [vp, ctypes.c_int]
+    L.mdqt_tag_particles.argtypes = [vp, vp, vp]
+    L.mdqt_vaf.argtypes = [vp, ctypes.c_int, c_double_p]
+    L.mdqt_set_forced_tag_uniforms.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -117,6 +124,17 @@ def md_params(scheme=SCHEME_NONE, n_ions=4096, kappa=0.5, density=0.4, timeStep=
     """``mdqt_params`` for the MD family (MD:66-88; MC408L:79-122)."""
     p = Params()
     rc = load_library().mdqt_params_md(ctypes.byref(p), scheme, n_ions, kappa, density, timeStep, detuning, Om, quad)
+    if rc:
+        raise MDQTError(load_library().mdqt_last_error().decode())
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def ts_params(n_ions=1000, detuning=-0.5, Om=0.5, **overrides):
+    """``mdqt_params`` of the 3-level test program without plasma (TS:55-58, 91, 390)."""
+    p = Params()
+    rc = load_library().mdqt_params_ts(ctypes.byref(p), n_ions, detuning, Om)
     if rc:
         raise MDQTError(load_library().mdqt_last_error().decode())
     for k, v in overrides.items():
@@ -276,6 +294,33 @@ class Engine:
         """nsub x qstep() of the 7-level pump (MC408L:555-756), velocities frozen, no kick."""
         self._ck(self.lib.mdqt_qsteps(self.h, nsub))
 
+    qstep5 = qstep7  # 5-level 422 nm pump (MC422L:552-727): same call, scheme decides
+    qstep3 = qstep7  # 3-level test system (TS:140-293): V_x kicked, tPart tracked
+
+    def step(self, dt=0.002):
+        """FZ-family step() (FZ408L:377-390): leap-frog with forces() inside; 2nd-order start while t <= 0."""
+        self._ck(self.lib.mdqt_leapfrog_step(self.h, dt))
+
+    def advance_time(self, nsub=1):
+        """t += quantumTimestep, nsub times (FZ408L:1066, outside the pump window)."""
+        self._ck(self.lib.mdqt_advance_time(self.h, nsub))
+
+    def tagParticles(self):
+        """tagParticles() MC408L:1022-1067 / MC422L:992-1036 == measureSpinUps() FZ408L:600-647.
+        Returns (tagged int32 [n_traj?][n_ions], count)."""
+        tagged = np.zeros(self._lead() + (self.N,), dtype=np.int32)
+        cnt = np.zeros(self.B, dtype=np.int32)
+        self._ck(self.lib.mdqt_tag_particles(self.h, ctypes.c_void_p(tagged.ctypes.data), ctypes.c_void_p(cnt.ctypes.data)))
+        return tagged, (cnt if self.B > 1 else int(cnt[0]))
+
+    measureSpinUps = tagParticles
+
+    def Zfunc(self, c1V):
+        """Zfunc() FZ408L:938-961: VAF against the velocities stored when c1V == 0."""
+        v = np.empty(self.B)
+        self._ck(self.lib.mdqt_vaf(self.h, 1 if c1V == 0 else 0, v.ctypes.data_as(c_double_p)))
+        return v if self.B > 1 else float(v[0])
+
     # ---- test hooks / plumbing ---------------------------------------------------------------------------------
     def set_forced_uniforms(self, u):
         if u is None:
@@ -284,6 +329,13 @@ class Engine:
         u = _chk64(u)
         assert u.ndim == 3 and u.shape[1:] == (self.N, 5)
         self._ck(self.lib.mdqt_set_forced_uniforms(self.h, _ptr(u), u.shape[0]))
+
+    def set_forced_tag_uniforms(self, u):
+        if u is None:
+            self._ck(self.lib.mdqt_set_forced_tag_uniforms(self.h, None))
+            return
+        u = _chk64(u, (self.N, 2))
+        self._ck(self.lib.mdqt_set_forced_tag_uniforms(self.h, _ptr(u)))
 
     def set_forced_collisions(self, u, v):
         if u is None:

@@ -234,6 +234,100 @@ def gen_su_ensemble_stats():
     print("su_ensemble_stats: final popS,P,D = %s" % rows[-1][1:4])
 
 
+def gen_schemes():
+    """the 5-level 422 nm pump (MC422L), the 3-level test system (TS) and the FZ408L driver pieces
+    (leap-frog step(), measureSpinUps(), Zfunc()), all produced by the unmodified reference programs."""
+    # ---- MC422L: one pump MD step = ratio no-jump qstep() sweeps; then tagParticles() with an injected stream ----
+    mc = po.RefMC422L()
+    c = mc.consts
+    rng = np.random.default_rng(21)
+    n = mc.N
+    psi = full_psi(rng, n, 5)
+    psi[:16] = 0.0
+    psi[:16, 0, 0] = 1.0
+    V = rng.normal(size=(3, n)) * 0.5
+    mc.set_state(V=V, psi=psi)
+    nsub = int(c["ratio"])
+    for _ in range(nsub):
+        assert mc.qstep(np.full(n, NOJUMP)) == n
+    o = mc.get_state()
+    keep = 512
+    # the tagger consumes 1 or 2 uniforms per ion from one stream; fixtures keep the per-ion pairs actually consumed
+    u_seq = rng.uniform(size=2 * n)
+    tagged, used = mc.tag(u_seq)
+    u_tab = np.zeros((n, 2))
+    cur = 0
+    nr = (o["psi"] ** 2).sum(axis=2)
+    for i in range(n):
+        u_tab[i, 0] = u_seq[cur]; cur += 1
+        if not (u_tab[i, 0] < nr[i, 0]) and (u_tab[i, 0] < nr[i, 0] + nr[i, 2] + nr[i, 3]):
+            u_tab[i, 1] = u_seq[cur]; cur += 1
+    assert cur == used
+    np.savez(os.path.join(OUT, "mc422l_pump.npz"), psi=psi[:keep], Vx=V[0, :keep], psi_out=o["psi"][:keep], nsub=nsub,
+             tag_u=u_tab[:keep], tagged=tagged[:keep], **{k: c[k] for k in c})
+    print("mc422l_pump: %d substeps, %d of %d tagged" % (nsub, tagged[:keep].sum(), keep))
+
+    # ---- TS: 40 no-jump sweeps with the optical-force kick, then one sweep where every 3rd ion jumps ----
+    ts = po.RefTS(detuning=-0.5, Om=0.5)
+    n = ts.N
+    psi = full_psi(rng, n, 3)
+    psi[:8] = 0.0
+    psi[:8, 0, 0] = 1.0
+    Vx = rng.normal(size=n) * 0.1
+    tp = rng.uniform(size=n)
+    ts.set_state(Vx=Vx, psi=psi, tPart=tp)
+    for _ in range(40):
+        assert ts.qstep(np.full(n, NOJUMP)) == n
+    s1 = ts.get_state()
+    # per-ion table (slot 0 rand, slot 3 randDir): as a stream, a jumping ion consumes 2 numbers, the others 1
+    u5 = rng.uniform(size=(n, 5))
+    u5[:, 0] = NOJUMP
+    u5[::3, 0] = 1e-9
+    seq = []
+    for i in range(n):
+        seq.append(u5[i, 0])
+        if u5[i, 0] < 1e-6:
+            seq.append(u5[i, 3])
+    used = ts.qstep(np.array(seq))
+    assert used == len(seq)
+    s2 = ts.get_state()
+    np.savez(os.path.join(OUT, "ts_three_state.npz"), psi=psi, Vx=Vx, tPart=tp, psi1=s1["psi"], Vx1=s1["Vx"], tPart1=s1["tPart"],
+             u5=u5, psi2=s2["psi"], Vx2=s2["Vx"], tPart2=s2["tPart"], detuning=-0.5, Om=0.5, nsub=40)
+    print("ts_three_state: %d jumps in the last sweep" % int((u5[:, 0] < 1e-6).sum()))
+
+    # ---- FZ408L: init(), the first step() (t = 0, 2nd-order start), a later step(), measureSpinUps, Zfunc ----
+    fz = po.RefFZ408L()
+    c = fz.consts
+    n = fz.init(4242)
+    s0 = fz.get_state()
+    fz.step()
+    s1 = fz.get_state()
+    fz.set_state(R=s1["R"], V=s1["V"], t=0.002)
+    fz.step()
+    s2 = fz.get_state()
+    psi = full_psi(rng, n, 7)
+    fz.set_state(psi=psi, n=n)
+    u_seq = rng.uniform(size=2 * n)
+    tagged, cnt, used = fz.measure(u_seq)
+    u_tab = np.zeros((n, 2))
+    cur = 0
+    nr = (psi ** 2).sum(axis=2)
+    for i in range(n):
+        u_tab[i, 0] = u_seq[cur]; cur += 1
+        c1 = nr[i, 0] + nr[i, 2]
+        if not (u_tab[i, 0] < c1) and (u_tab[i, 0] < c1 + nr[i, 3] + nr[i, 4]):
+            u_tab[i, 1] = u_seq[cur]; cur += 1
+    assert cur == used
+    vaf0 = fz.zfunc(0)
+    Vb = s2["V"] * 0.5 + 1e-3
+    fz.set_state(V=Vb, n=n)
+    vaf1 = fz.zfunc(1)
+    np.savez(os.path.join(OUT, "fz408l_driver.npz"), R0=s0["R"], V0=s0["V"], R1=s1["R"], V1=s1["V"], R2=s2["R"], V2=s2["V"],
+             F2=s2["F"], psi=psi, tag_u=u_tab, tagged=tagged, n_tagged=cnt, vaf0=vaf0, vaf1=vaf1, Vb=Vb,
+             **{k: c[k] for k in c})
+    print("fz408l_driver: N=%d, %d spin-up, VAF %g -> %g" % (n, cnt, vaf0, vaf1))
+
+
 def seed_stream(ref, seed):
     """srand48(seed) inside the harness process (the reference's drand48 stream is then its own, un-injected)."""
     import ctypes
@@ -247,6 +341,9 @@ if __name__ == "__main__":
     if "--mainloop" in sys.argv:
         gen_su_mainloop()
         sys.exit(0)
+    if "--schemes" in sys.argv:
+        gen_schemes()
+        sys.exit(0)
     if "--ensemble" in sys.argv:
         gen_su_ensemble_stats()
         sys.exit(0)
@@ -256,3 +353,4 @@ if __name__ == "__main__":
     gen_su_stream()
     gen_md()
     gen_mc408()
+    gen_schemes()

@@ -371,3 +371,151 @@ void orc_qstep7(int n, double* psi, const double* Vx, const orc_qt_params* p,
     if (used) used[i] = nu;
   }
 }
+
+/* 5-level 422 nm pump (MonteCarloFollowedByQTTagging422Linear.cpp:552-727; tables MC422L:1144-1155): states
+ * 0 S-1/2, 1 S+1/2, 2 P+1/2, 3 P-1/2, 4 D. gs are rates; draws: rand, rand2, randDOrS, [rand3 on S decays] -- there is
+ * no randDir draw in this file. In the per-ion table mode (umode 0) the slots are u[0]=rand, u[1]=rand2, u[2]=randDOrS,
+ * u[4]=rand3 (slot 3 unused), matching the engine's Philox layout. */
+static double u_slot(const double* u, int umode, long* cursor, int i, int slot, int* count) {
+  (*count)++;
+  return (umode == 0) ? u[5 * i + slot] : u[(*cursor)++];
+}
+void orc_qstep5(int n, double* psi, const double* Vx, const orc_qt_params* p,
+                const double* u, int umode, long* cursor, int* used) {
+  static const int up5[6] = {2, 3, 3, 2, 2, 3}; /* cs[k]=|lower><upper| (MC422L:1144-1149) */
+  double gs[6] = {2. / 3, 1. / 3, 2. / 3, 1. / 3, p->dR, p->dR};
+  const double h = p->dtq * p->g2E;
+  sparse_h H;
+  memset(&H, 0, sizeof(H));
+  H.S = 5;
+  for (int k = 0; k < 6; k++) H.gam[up5[k]] += gs[k];
+  for (int i = 0; i < n; i++) {
+    cplx y[12];
+    int nu = 0;
+    for (int s = 0; s < 5; s++) { y[s].re = psi[(i * 5 + s) * 2]; y[s].im = psi[(i * 5 + s) * 2 + 1]; }
+    double vq = Vx[i] * p->pv2qv;
+    double dp = dp_of(&H, y, h);
+    double rnd = u_slot(u, umode, cursor, i, 0, &nu); /* MC422L:586 */
+    if (rnd > dp) {
+      double detR = -p->detuning - vq, detL = -p->detuning + vq; /* MC422L:592-593 */
+      for (int s = 0; s < 5; s++) { H.diag[s].re = 0; H.diag[s].im = -1. / 2 * H.gam[s]; }
+      H.diag[2].re = detR; H.diag[3].re = detL; /* MC422L:595 */
+      H.nent = 0;
+      cplx v;
+      v.im = 0;
+      v.re = -p->Om / 2 * sqrt(gs[0]); add_pair(&H, 1, 2, v); /* -Om/2 |2><3| sqrt(gs0) (MC422L:594) */
+      v.re = -p->Om / 2 * sqrt(gs[2]); add_pair(&H, 0, 3, v); /* -Om/2 |1><4| sqrt(gs2) */
+      rk_step(&H, y, h);
+    } else { /* MC422L:660-720 */
+      double rand2 = u_slot(u, umode, cursor, i, 1, &nu);
+      double n3 = cnorm(y[2]), n4 = cnorm(y[3]);
+      double tot = n3 + n4;
+      double p3 = n3 / tot;
+      double randDOrS = u_slot(u, umode, cursor, i, 2, &nu);
+      int sDecay = !(randDOrS < (p->dR / (p->dR + 1))), dest;
+      if (rand2 < p3) {
+        if (sDecay) { double r3 = u_slot(u, umode, cursor, i, 4, &nu); dest = (r3 < gs[0]) ? 1 : 0; } else dest = 4;
+      } else {
+        if (sDecay) { double r3 = u_slot(u, umode, cursor, i, 4, &nu); dest = (r3 < gs[2]) ? 0 : 1; } else dest = 4;
+      }
+      for (int s = 0; s < 5; s++) { y[s].re = 0; y[s].im = 0; }
+      y[dest].re = 1;
+    }
+    for (int s = 0; s < 5; s++) { psi[(i * 5 + s) * 2] = y[s].re; psi[(i * 5 + s) * 2 + 1] = y[s].im; }
+    if (used) used[i] = nu;
+  }
+}
+
+/* 3-level test system (laserCoolNoPlasmaThreeState.cpp:140-293; tables TS:379-382): states 0 ground (J=0), 1 m=+1,
+ * 2 m=-1; gs = {1,1}; cs[0] = |0><1|, cs[1] = |0><2|. dt is used directly (velocities and times already in quantum
+ * units: pass dtq = dt, g2E = 1, pv2qv = 1). Draws: rand, and randDir on a jump (slots 0 and 3 of the 5-table). */
+void orc_qstep3(int n, double* psi, double* Vx, double* tPart, const orc_qt_params* p, int applyForce,
+                const double* u, int umode, long* cursor, int* used) {
+  double gs[2] = {1, 1};
+  const double dt = p->dtq * p->g2E;
+  sparse_h H;
+  memset(&H, 0, sizeof(H));
+  H.S = 3;
+  H.gam[1] += gs[0]; H.gam[2] += gs[1];
+  for (int i = 0; i < n; i++) {
+    cplx y[12];
+    int nu = 0;
+    double kick;
+    for (int s = 0; s < 3; s++) { y[s].re = psi[(i * 3 + s) * 2]; y[s].im = psi[(i * 3 + s) * 2 + 1]; }
+    double vq = Vx[i] * p->pv2qv; /* TS:154 */
+    tPart[i] += dt;               /* TS:155 */
+    double dp = dp_of(&H, y, dt);
+    double rnd = u_slot(u, umode, cursor, i, 0, &nu); /* TS:165 */
+    if (rnd > dp) {
+      /* p13 = <1|rho|3> = y0 conj(y2), p12 = y0 conj(y1) (TS:170-171) */
+      double im13 = y[0].im * y[2].re - y[0].re * y[2].im, im12 = y[0].im * y[1].re - y[0].re * y[1].im;
+      kick = 1 * p->vKick * p->Om * (im13 * sqrt(gs[0]) - im12 * sqrt(gs[1])) * dt; /* TS:174 */
+      double detR = -p->detuning - vq, detL = -p->detuning + vq; /* TS:177-178 */
+      for (int s = 0; s < 3; s++) { H.diag[s].re = 0; H.diag[s].im = -1. / 2 * H.gam[s]; }
+      H.diag[2].re = detR; H.diag[1].re = detL; /* TS:181 */
+      H.nent = 0;
+      cplx v;
+      v.im = 0;
+      v.re = -p->Om / 2 * sqrt(gs[0]); add_pair(&H, 0, 2, v); /* -Om/2 |1><3| sqrt(gs0) (TS:179) */
+      v.re = -p->Om / 2 * sqrt(gs[1]); add_pair(&H, 0, 1, v); /* -Om/2 |1><2| sqrt(gs1) */
+      rk_step(&H, y, dt);
+    } else { /* TS:270-282 */
+      tPart[i] = 0;
+      for (int s = 0; s < 3; s++) { y[s].re = 0; y[s].im = 0; }
+      y[0].re = 1;
+      double randDir = u_slot(u, umode, cursor, i, 3, &nu);
+      kick = (randDir < 0.5) ? p->vKick : -p->vKick;
+    }
+    if (applyForce) Vx[i] = Vx[i] + kick; /* TS:283-285 */
+    for (int s = 0; s < 3; s++) { psi[(i * 3 + s) * 2] = y[s].re; psi[(i * 3 + s) * 2 + 1] = y[s].im; }
+    if (used) used[i] = nu;
+  }
+}
+
+/* projective spin measurement: tagParticles (MC408L:1022-1067 for S = 7, MC422L:992-1036 for S = 5) ==
+ * measureSpinUps (FZ408L:600-647). umode 0: u[n][2] (second slot used only on the mixed branches);
+ * umode 1: one sequential stream. Returns the number tagged. */
+int orc_tag(int n, int S, const double* psi, const double* u, int umode, long* cursor, int* tagged) {
+  int count = 0;
+  for (int i = 0; i < n; i++) {
+    double nrm[5];
+    for (int k = 0; k < 5 && k < S; k++) {
+      double re = psi[(i * S + k) * 2], im = psi[(i * S + k) * 2 + 1];
+      nrm[k] = re * re + im * im;
+    }
+    double rnd = (umode == 0) ? u[2 * i] : u[(*cursor)++];
+    int up;
+    if (S == 7) {
+      if (rnd < nrm[0] + nrm[2]) up = 1;
+      else if (rnd < nrm[0] + nrm[2] + nrm[3]) { double r2 = (umode == 0) ? u[2 * i + 1] : u[(*cursor)++]; up = r2 < 2. / 3; }
+      else if (rnd < nrm[0] + nrm[2] + nrm[3] + nrm[4]) { double r3 = (umode == 0) ? u[2 * i + 1] : u[(*cursor)++]; up = r3 < 1. / 3; }
+      else up = 0;
+    } else {
+      if (rnd < nrm[0]) up = 1;
+      else if (rnd < nrm[0] + nrm[2]) { double r2 = (umode == 0) ? u[2 * i + 1] : u[(*cursor)++]; up = r2 < 1. / 3; }
+      else if (rnd < nrm[0] + nrm[2] + nrm[3]) { double r3 = (umode == 0) ? u[2 * i + 1] : u[(*cursor)++]; up = r3 < 2. / 3; }
+      else up = 0;
+    }
+    tagged[i] = up;
+    count += up;
+  }
+  return count;
+}
+
+/* FZ-family leap-frog pieces (FZ408L:317-369); the caller supplies F = forces() where the reference recomputes it */
+void orc_lf_drift(int n, double* R, const double* V, const double* F, double L, double DT, int first) {
+  for (int k = 0; k < 3 * n; k++) {
+    if (first) R[k] += DT * V[k] + DT * DT * F[k]; /* FZ408L:336-338 */
+    else R[k] += DT * V[k];                        /* FZ408L:325-327 */
+    if (R[k] < 0) R[k] += L;
+    if (R[k] > L) R[k] -= L;
+  }
+}
+void orc_lf_kick(int n, double* V, const double* F, double DT) { /* FZ408L:364-366 */
+  for (int k = 0; k < 3 * n; k++) V[k] += DT * F[k];
+}
+double orc_vaf(int n, const double* Vhold, const double* Vx) { /* FZ408L:955-960 */
+  double vaf = 0.0;
+  for (int j = 0; j < n; j++) vaf += 1 / ((double)(n)) * (Vhold[j] * Vx[j]);
+  return vaf;
+}

@@ -60,6 +60,16 @@ void orc_qstep12(int n, double* psi, double* Vx, double* tPart, double* t, const
 void orc_qstep7(int n, double* psi, const double* Vx, const orc_qt_params* p,
                 const double* u, int umode, long* cursor, int* used);                          /* MC408L:555-756, 1171-1190 */
 
+void orc_qstep5(int n, double* psi, const double* Vx, const orc_qt_params* p,
+                const double* u, int umode, long* cursor, int* used);                          /* MC422L:552-727, 1144-1155 */
+
+void orc_qstep3(int n, double* psi, double* Vx, double* tPart, const orc_qt_params* p, int applyForce,
+                const double* u, int umode, long* cursor, int* used);                          /* TS:140-293, 379-382 */
+int orc_tag(int n, int S, const double* psi, const double* u, int umode, long* cursor, int* tagged); /* MC408L:1022-1067, MC422L:992-1036 */
+void orc_lf_drift(int n, double* R, const double* V, const double* F, double L, double DT, int first); /* FZ408L:317-350 */
+void orc_lf_kick(int n, double* V, const double* F, double DT);                                 /* FZ408L:358-369 */
+double orc_vaf(int n, const double* Vhold, const double* Vx);                                   /* FZ408L:938-961 */
+
 #ifdef __cplusplus
 }
 #endif

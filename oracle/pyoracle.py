@@ -65,6 +65,23 @@ def mc408_params(n=2.0, detuning=-2.5, Om=0.7, quad=0, timeStep=0.005):
     return p, ratio
 
 
+def mc422_params(n=2.0, detuning=-1.0, Om=1.3, timeStep=0.005):
+    """Derived constants of the 5-level 422 nm pump stage (MC422L:84-86, 113-121)."""
+    import math
+    ratio = int(round(87 * .894 / math.sqrt(n)))
+    pv2qv = 1.1821 * math.pow(n, 1. / 6) * .967
+    p = QTParams(detuning=detuning, detuningDP=0.0, Om=Om, OmDP=0.0, dR=0.0753, kRat=0.0, vKick=0.001257 / pv2qv,
+                 vKickDP=0.0, g2E=174.07 * .894 / math.sqrt(n), pv2qv=pv2qv, dtq=timeStep / ratio, fracOfSig=0.0, Te=0.0,
+                 sig0=1.0, density=n, renorm=0, quad=0)
+    return p, ratio
+
+
+def ts_params(detuning=-0.5, Om=0.5, dt=0.01):
+    """The 3-level test program (TS:55-58, 91, 390): everything already in quantum units."""
+    return QTParams(detuning=detuning, detuningDP=0.0, Om=Om, OmDP=0.0, dR=0.0, kRat=0.0, vKick=0.0012076, vKickDP=0.0,
+                    g2E=1.0, pv2qv=1.0, dtq=dt, fracOfSig=0.0, Te=0.0, sig0=1.0, density=1.0, renorm=0, quad=0)
+
+
 class Oracle:
     """The independent restatement (liboracle.so)."""
 
@@ -85,6 +102,15 @@ class Oracle:
                                   c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_long), c_int_p]
         L.orc_qstep7.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.POINTER(QTParams), c_double_p, ctypes.c_int,
                                  ctypes.POINTER(ctypes.c_long), c_int_p]
+        L.orc_qstep5.argtypes = L.orc_qstep7.argtypes
+        L.orc_qstep3.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.POINTER(QTParams), ctypes.c_int,
+                                 c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_long), c_int_p]
+        L.orc_tag.argtypes = [ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int,
+                              ctypes.POINTER(ctypes.c_long), c_int_p]
+        L.orc_lf_drift.argtypes = [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]
+        L.orc_lf_kick.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_double]
+        L.orc_vaf.argtypes = [ctypes.c_int, c_double_p, c_double_p]
+        L.orc_vaf.restype = ctypes.c_double
         L.orc_uniforms5.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p]
         L.orc_collision_draws.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p, c_double_p]
 
@@ -151,6 +177,50 @@ class Oracle:
         self.lib.orc_qstep7(n, _dp(psi), _dp(Vx), ctypes.byref(p), _dp(u), 1 if sequential else 0, ctypes.byref(cur),
                             used.ctypes.data_as(c_int_p))
         return used
+
+    def qstep5(self, psi, Vx, p, u, sequential=False):
+        """5-level 422 nm pump sweep (MC422L:552-727); table slots: 0 rand, 1 rand2, 2 randDOrS, 4 rand3."""
+        n = psi.shape[0]
+        cur = ctypes.c_long(0)
+        used = np.zeros(n, dtype=np.int32)
+        self.lib.orc_qstep5(n, _dp(psi), _dp(Vx), ctypes.byref(p), _dp(u), 1 if sequential else 0, ctypes.byref(cur),
+                            used.ctypes.data_as(c_int_p))
+        return used
+
+    def qstep3(self, psi, Vx, tPart, p, u, sequential=False, applyForce=True):
+        """3-level sweep (TS:140-293), Vx and tPart updated in place; table slots: 0 rand, 3 randDir."""
+        n = psi.shape[0]
+        cur = ctypes.c_long(0)
+        used = np.zeros(n, dtype=np.int32)
+        self.lib.orc_qstep3(n, _dp(psi), _dp(Vx), _dp(tPart), ctypes.byref(p), 1 if applyForce else 0, _dp(u),
+                            1 if sequential else 0, ctypes.byref(cur), used.ctypes.data_as(c_int_p))
+        return used
+
+    def tag(self, psi, u, sequential=False):
+        """tagParticles / measureSpinUps; returns (tagged[n] int32, draws consumed when sequential)."""
+        n, S = psi.shape[0], psi.shape[1]
+        cur = ctypes.c_long(0)
+        tagged = np.zeros(n, dtype=np.int32)
+        cnt = self.lib.orc_tag(n, S, _dp(psi), _dp(u), 1 if sequential else 0, ctypes.byref(cur), tagged.ctypes.data_as(c_int_p))
+        assert cnt == tagged.sum()
+        return tagged, cur.value
+
+    def lf_step(self, R, V, L, lDeb, dt, first):
+        """FZ-family step() (FZ408L:377-390) with the restated force routine; returns the last F."""
+        n = R.shape[1]
+        if first:
+            self.lib.orc_lf_drift(n, _dp(R), _dp(V), _dp(self.forces_su(R, L, lDeb)), L, 0.5 * dt, 1)
+        else:
+            self.lib.orc_lf_drift(n, _dp(R), _dp(V), _dp(V), L, 0.5 * dt, 0)
+        F = self.forces_su(R, L, lDeb)
+        self.lib.orc_lf_kick(n, _dp(V), _dp(F), dt)
+        if first:
+            F = self.forces_su(R, L, lDeb)
+        self.lib.orc_lf_drift(n, _dp(R), _dp(V), _dp(F), L, 0.5 * dt, 1 if first else 0)
+        return F
+
+    def vaf(self, Vhold, Vx):
+        return self.lib.orc_vaf(Vx.shape[0], _dp(np.ascontiguousarray(Vhold)), _dp(np.ascontiguousarray(Vx)))
 
 
 def ref_available(name="su"):
@@ -356,3 +426,155 @@ class RefMC408L:
 
     def mdstep(self):
         self.lib.ref_mc_mdstep()
+
+    def tag(self, uniforms):
+        """tagParticles() (MC408L:1022-1067) on the current wavefunctions with one sequential uniform stream."""
+        self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        self.lib.ref_mc_set_uniforms(_dp(self._u), self._u.size)
+        out = np.zeros(self.N, dtype=np.int32)
+        self.lib.ref_mc_tag(out.ctypes.data_as(c_int_p))
+        used = self.lib.ref_mc_uniforms_used()
+        self.lib.ref_mc_set_uniforms(None, 0)
+        return out, used
+
+
+class RefMC422L:
+    """The unmodified reference MC422L program (5-level 422 nm pump; oracle/_ref/libref_mc422l.so); N=4096 fixed."""
+
+    def __init__(self, detuning=-1.0, Om=1.3, scratch="/tmp/mdqt_ref_scratch422/"):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_mc422l.so"))
+        L.ref_m422_setup.argtypes = [c_double_p, ctypes.c_char_p]
+        L.ref_m422_set_state.argtypes = [c_double_p] * 4
+        L.ref_m422_get_state.argtypes = [c_double_p] * 4
+        L.ref_m422_set_uniforms.argtypes = [c_double_p, ctypes.c_long]
+        L.ref_m422_uniforms_used.restype = ctypes.c_long
+        p = (ctypes.c_double * 2)(detuning, Om)
+        assert L.ref_m422_setup(p, scratch.encode()) == 0
+        c = (ctypes.c_double * 12)()
+        L.ref_m422_get_consts(c)
+        keys = ["L", "rCut", "kappa", "Gamma", "n", "timeStep", "g2E", "ratio", "dtq", "pv2qv", "dR", "pumpMDTimeSteps"]
+        self.consts = dict(zip(keys, list(c)))
+        self.N = L.ref_m422_N()
+
+    def set_state(self, R=None, V=None, A=None, psi=None):
+        self.lib.ref_m422_set_state(_dp(R), _dp(V), _dp(A), _dp(psi))
+
+    def get_state(self):
+        R, V, A = (np.empty((3, self.N)) for _ in range(3))
+        psi = np.empty((self.N, 5, 2))
+        self.lib.ref_m422_get_state(_dp(R), _dp(V), _dp(A), _dp(psi))
+        return dict(R=R, V=V, A=A, psi=psi)
+
+    def _with_u(self, uniforms, fn):
+        self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        self.lib.ref_m422_set_uniforms(_dp(self._u), self._u.size)
+        r = fn()
+        used = self.lib.ref_m422_uniforms_used()
+        self.lib.ref_m422_set_uniforms(None, 0)
+        return r, used
+
+    def qstep(self, uniforms):
+        return self._with_u(uniforms, self.lib.ref_m422_qstep)[1]
+
+    def tag(self, uniforms):
+        out = np.zeros(self.N, dtype=np.int32)
+        _, used = self._with_u(uniforms, lambda: self.lib.ref_m422_tag(out.ctypes.data_as(c_int_p)))
+        return out, used
+
+
+class RefTS:
+    """The unmodified reference 3-level program (oracle/_ref/libref_ts.so); N0=1000 fixed."""
+
+    def __init__(self, detuning=-0.5, Om=0.5, dt=0.01, applyForce=True):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_ts.so"))
+        L.ref_ts_setup.argtypes = [ctypes.c_double] * 3 + [ctypes.c_int]
+        L.ref_ts_set_state.argtypes = [c_double_p] * 3
+        L.ref_ts_get_state.argtypes = [c_double_p] * 3
+        L.ref_ts_set_uniforms.argtypes = [c_double_p, ctypes.c_long]
+        L.ref_ts_uniforms_used.restype = ctypes.c_long
+        L.ref_ts_vkick.restype = ctypes.c_double
+        assert L.ref_ts_setup(detuning, Om, dt, 1 if applyForce else 0) == 0
+        self.N = L.ref_ts_N()
+        self.vKick = L.ref_ts_vkick()
+
+    def set_state(self, Vx=None, psi=None, tPart=None):
+        self.lib.ref_ts_set_state(_dp(Vx), _dp(psi), _dp(tPart))
+
+    def get_state(self):
+        Vx, tp, psi = np.empty(self.N), np.empty(self.N), np.empty((self.N, 3, 2))
+        self.lib.ref_ts_get_state(_dp(Vx), _dp(psi), _dp(tp))
+        return dict(Vx=Vx, psi=psi, tPart=tp)
+
+    def qstep(self, uniforms):
+        self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        self.lib.ref_ts_set_uniforms(_dp(self._u), self._u.size)
+        self.lib.ref_ts_qstep()
+        used = self.lib.ref_ts_uniforms_used()
+        self.lib.ref_ts_set_uniforms(None, 0)
+        return used
+
+
+class RefFZ408L:
+    """The unmodified reference frozen-start pump-window program FZ408L (oracle/_ref/libref_fz408l.so)."""
+
+    def __init__(self, detuning=-2.5, Om=0.7, scratch="/tmp/mdqt_ref_scratch_fz/"):
+        self.lib = L = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_fz408l.so"))
+        L.ref_fz_setup.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.c_char_p]
+        L.ref_fz_init.argtypes = [ctypes.c_long]
+        L.ref_fz_get_t.restype = ctypes.c_double
+        L.ref_fz_set_t.argtypes = [ctypes.c_double]
+        L.ref_fz_set_state.argtypes = [ctypes.c_int] + [c_double_p] * 3
+        L.ref_fz_get_state.argtypes = [c_double_p] * 4
+        L.ref_fz_set_uniforms.argtypes = [c_double_p, ctypes.c_long]
+        L.ref_fz_uniforms_used.restype = ctypes.c_long
+        L.ref_fz_measure.argtypes = [c_int_p]
+        L.ref_fz_zfunc.argtypes = [ctypes.c_int]
+        L.ref_fz_zfunc.restype = ctypes.c_double
+        assert L.ref_fz_setup(detuning, Om, scratch.encode()) == 0
+        c = (ctypes.c_double * 10)()
+        L.ref_fz_get_consts(c)
+        keys = ["L", "lDeb", "dtq", "g2E", "pv2qv", "ratio", "dR", "tpump", "tendV0", "TIMESTEP"]
+        self.consts = dict(zip(keys, list(c)))
+
+    @property
+    def N(self):
+        return self.lib.ref_fz_get_N()
+
+    def init(self, seed):
+        return self.lib.ref_fz_init(seed)
+
+    def set_state(self, R=None, V=None, psi=None, t=None, n=None):
+        if n is None:
+            n = R.shape[1] if R is not None else (V.shape[1] if V is not None else psi.shape[0])
+        self.lib.ref_fz_set_state(n, _dp(R), _dp(V), _dp(psi))
+        if t is not None:
+            self.lib.ref_fz_set_t(t)
+
+    def get_state(self):
+        n = self.N
+        R, V, F = (np.empty((3, n)) for _ in range(3))
+        psi = np.empty((n, 7, 2))
+        self.lib.ref_fz_get_state(_dp(R), _dp(V), _dp(F), _dp(psi))
+        return dict(R=R, V=V, F=F, psi=psi, t=self.lib.ref_fz_get_t())
+
+    def step(self):
+        self.lib.ref_fz_step()
+
+    def _with_u(self, uniforms, fn):
+        self._u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        self.lib.ref_fz_set_uniforms(_dp(self._u), self._u.size)
+        r = fn()
+        used = self.lib.ref_fz_uniforms_used()
+        self.lib.ref_fz_set_uniforms(None, 0)
+        return r, used
+
+    def qstep(self, uniforms):
+        return self._with_u(uniforms, self.lib.ref_fz_qstep)[1]
+
+    def measure(self, uniforms):
+        out = np.zeros(self.N, dtype=np.int32)
+        cnt, used = self._with_u(uniforms, lambda: self.lib.ref_fz_measure(out.ctypes.data_as(c_int_p)))
+        return out, cnt, used
+
+    def zfunc(self, c1V):
+        return self.lib.ref_fz_zfunc(c1V)

@@ -1,0 +1,150 @@
+"""GPU parity tests for SURVEY §8(f) rank 3 -- the other level schemes and driver pieces -- through the C ABI:
+the 5-level 422 nm pump (MC422L), the 3-level test system (TS), the FZ-family leap-frog step(), the spin taggers and
+Zfunc. Golden vectors come from the unmodified reference programs (oracle/gen_golden.py --schemes); jump branches are
+compared with the oracle restatement, itself pinned to the live reference in the CPU suite.
+
+Tolerances: amplitudes <= 1e-10, positions/velocities <= 1e-12 (BASELINE.json north_star); integer outcomes exact."""
+import os
+
+import numpy as np
+import pytest
+
+from mdqtplasmasims_b200 import (Engine, SCHEME_CA5, SCHEME_NONE, SCHEME_SR7, md_params, su_params, ts_params)
+
+pytestmark = pytest.mark.gpu
+
+AMP_TOL = 1e-10
+RV_TOL = 1e-12
+NOJUMP = 0.99999
+
+
+def test_qstep5_golden_jumps_and_tagging(golden_dir, oracle):
+    from oracle import pyoracle as po
+    g = np.load(os.path.join(golden_dir, "mc422l_pump.npz"))
+    n, nsub = g["psi"].shape[0], int(g["nsub"])
+    p = md_params(scheme=SCHEME_CA5, n_ions=n, kappa=float(g["kappa"]), density=float(g["n"]), timeStep=float(g["timeStep"]),
+                  detuning=-1.0, Om=1.3)
+    assert p.substeps_per_md == int(g["ratio"]) and p.dtq == float(g["dtq"]) and p.g2E == float(g["g2E"])
+    assert p.pv2qv == float(g["pv2qv"]) and p.dR == float(g["dR"])
+    V = np.zeros((3, n)); V[0] = g["Vx"]
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=g["psi"])
+    eng.set_forced_uniforms(np.full((nsub, n, 5), NOJUMP))
+    eng.qstep5(nsub)
+    s = eng.download(("psi", "V"))
+    assert np.abs(s["psi"] - g["psi_out"]).max() <= AMP_TOL
+    assert np.array_equal(s["V"], V)  # the pump stage never kicks (MC422L:722)
+    # tagParticles with the reference's own uniforms
+    eng.set_forced_tag_uniforms(g["tag_u"])
+    tagged, cnt = eng.tagParticles()
+    assert np.array_equal(tagged, g["tagged"]) and cnt == int(g["tagged"].sum())
+    # S/P/D grouping of the 5-level scheme: 2 + 2 + 1
+    pops = eng.populations()
+    nr = (s["psi"] ** 2).sum(axis=2)
+    assert np.abs(pops[:, 0] - nr[:, :2].sum(axis=1)).max() <= 1e-15 and np.abs(pops[:, 2] - nr[:, 4]).max() <= 1e-15
+    # jumps: every branch of MC422L:660-720 against the restatement
+    qp, _ = po.mc422_params(n=float(g["n"]))
+    rng = np.random.default_rng(4)
+    u5 = rng.uniform(size=(1, n, 5)); u5[0, ::2, 0] = 1e-12
+    psi0 = s["psi"].copy()
+    eng.set_forced_uniforms(u5)
+    eng.qstep5(1)
+    s2 = eng.download(("psi",))
+    psi_o = psi0.copy()
+    oracle.qstep5(psi_o, V[0].copy(), qp, u5[0])
+    assert np.abs(s2["psi"] - psi_o).max() <= AMP_TOL
+    jumped = (np.abs(psi_o) == 1.0).any(axis=(1, 2))
+    assert jumped[::2].all() and np.array_equal(s2["psi"][jumped], psi_o[jumped])
+    dest = np.abs(psi_o[jumped][:, :, 0]).argmax(axis=1)
+    assert set(dest.tolist()) == {0, 1, 4}  # both S sublevels and the D reservoir are reached
+    # Philox-driven tagging: count is consistent with the list and with the spin-up probability
+    eng.set_forced_tag_uniforms(None)
+    tagged, cnt = eng.tagParticles()
+    assert cnt == tagged.sum() and set(np.unique(tagged).tolist()) <= {0, 1}
+
+
+def test_three_state_golden(golden_dir, oracle):
+    g = np.load(os.path.join(golden_dir, "ts_three_state.npz"))
+    n, nsub = g["psi"].shape[0], int(g["nsub"])
+    p = ts_params(n_ions=n, detuning=float(g["detuning"]), Om=float(g["Om"]))
+    V = np.zeros((3, n)); V[0] = g["Vx"]; V[1] = 0.25
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=g["psi"], tPart=g["tPart"], t=0.0)
+    eng.set_forced_uniforms(np.full((nsub, n, 5), NOJUMP))
+    eng.qstep3(nsub)
+    s = eng.download(("psi", "V", "tPart"))
+    assert np.abs(s["psi"] - g["psi1"]).max() <= AMP_TOL
+    assert np.abs(s["V"][0] - g["Vx1"]).max() <= RV_TOL * np.abs(g["Vx1"]).max()
+    assert np.array_equal(s["V"][1], V[1])  # only v_x is touched (TS:283)
+    assert np.abs(s["tPart"] - g["tPart1"]).max() <= 1e-13
+    tt = 0.0
+    for _ in range(nsub):
+        tt += 0.01
+    assert s["t"] == tt
+    # one sweep in which every third ion jumps (rand, randDir = table slots 0 and 3)
+    eng.set_forced_uniforms(g["u5"][None])
+    eng.qstep3(1)
+    s2 = eng.download(("psi", "V", "tPart"))
+    assert np.abs(s2["psi"] - g["psi2"]).max() <= AMP_TOL
+    assert np.abs(s2["V"][0] - g["Vx2"]).max() <= RV_TOL * np.abs(g["Vx2"]).max()
+    jumped = g["u5"][:, 0] < 1e-6
+    assert (s2["tPart"][jumped] == 0).all() and np.array_equal(s2["psi"][jumped], g["psi2"][jumped])
+
+
+def test_fz_leapfrog_tag_vaf_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fz408l_driver.npz"))
+    n = g["R0"].shape[1]
+    p = su_params(n_ions=n, scheme=SCHEME_SR7, detuning=-2.5, Om=0.7)
+    p.substeps_per_md = int(g["ratio"])       # FZ408L:73 uses round() where SU uses ceil(): same value at n = 2
+    assert p.L == float(g["L"]) and p.dtq == float(g["dtq"]) and abs(1 / p.kappa - float(g["lDeb"])) < 1e-15
+    dt = float(g["dtq"]) * float(g["ratio"])
+    eng = Engine(p)
+    eng.upload(R=g["R0"], V=g["V0"], psi=g["psi"], t=0.0)
+    eng.step(dt)                               # first step: t = 0 -> 2nd-order start, forces() three times
+    s1 = eng.download(("R", "V"))
+    assert np.abs(s1["R"] - g["R1"]).max() <= RV_TOL * p.L
+    assert np.abs(s1["V"] - g["V1"]).max() <= RV_TOL * np.abs(g["V1"]).max()
+    eng.upload(R=g["R1"], V=g["V1"], t=0.002)
+    eng.step(dt)
+    s2 = eng.download(("R", "V"))
+    assert np.abs(s2["R"] - g["R2"]).max() <= RV_TOL * p.L
+    assert np.abs(s2["V"] - g["V2"]).max() <= RV_TOL * np.abs(g["V2"]).max()
+    F = eng.download_forces()
+    assert np.abs(F - g["F2"]).max() <= 1e-12 * np.abs(g["F2"]).max()
+    # measureSpinUps with the reference's own uniforms; Zfunc
+    eng.set_forced_tag_uniforms(g["tag_u"])
+    tagged, cnt = eng.measureSpinUps()
+    assert np.array_equal(tagged, g["tagged"]) and cnt == int(g["n_tagged"])
+    eng.upload(V=g["V2"])
+    assert abs(eng.Zfunc(0) - float(g["vaf0"])) <= 1e-14 * abs(float(g["vaf0"]))
+    eng.upload(V=g["Vb"])
+    assert abs(eng.Zfunc(1) - float(g["vaf1"])) <= 1e-14 * abs(float(g["vaf0"]))
+    # outside the pump window the FZ loop only advances time (FZ408L:1066)
+    t0, _ = eng.time()
+    eng.advance_time(25)
+    tt = t0
+    for _ in range(25):
+        tt += p.dtq
+    assert eng.time()[0] == tt
+
+
+def test_fz_pump_window_qstep7_matches_oracle(oracle):
+    """FZ408L's qstep() = the 7-level body with h = (0.002/25) g2E (FZ408L:396-598)."""
+    from oracle import pyoracle as po
+    from mdqtplasmasims_b200 import synthetic
+    n = 300
+    p = su_params(n_ions=n, scheme=SCHEME_SR7, detuning=-2.5, Om=0.7)
+    qp, _ = po.mc408_params(n=2.0)
+    qp.dtq = p.dtq
+    psi = synthetic.random_full_state(n, 7, seed=3)
+    V = synthetic.maxwellian(n, 0.3, seed=3)
+    eng = Engine(p)
+    eng.upload(R=np.zeros((3, n)), V=V, psi=psi)
+    rng = np.random.default_rng(5)
+    u5 = rng.uniform(size=(6, n, 5)); u5[2, ::3, 0] = 1e-12
+    eng.set_forced_uniforms(u5)
+    eng.qstep7(6)
+    psi_o = psi.copy()
+    for k in range(6):
+        oracle.qstep7(psi_o, V[0].copy(), qp, u5[k])
+    assert np.abs(eng.download(("psi",))["psi"] - psi_o).max() <= AMP_TOL
