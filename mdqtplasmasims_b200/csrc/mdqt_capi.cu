@@ -38,7 +38,7 @@ struct mdqt_handle {
   double *forced_cu, *forced_cn;
   QTConsts qc;
   double t; uint64_t substep, vv_step;
-  int nsplit, jlen, itiles, ipt, jsub;
+  int nsplit, jlen, itiles, ipt, jsub, rg;
   bool timing;
   std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
   size_t ev_used;
@@ -155,18 +155,47 @@ static void plan_force(mdqt_handle* h) {
     const long long tiles1 = ((long long)N + kForceThreads - 1) / kForceThreads * B;
     h->jsub = (ipt == 1 && tiles1 * h->nsplit < 148LL * 7) ? 2 : 1;
   }
+  h->rg = kForceThreads;
+  // Small systems (the CTAs of the plan above do not fill every SM seven times over): compare that plan with 32-row
+  // groups, whose rows are split over 4x fewer CTAs. Model from the per-CTA phase trace on B200 (profiles/): time =
+  // (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue cycles / 4 sub-partitions + 2.8 us of CTA
+  // prologue/epilogue + one L2 round trip (~0.9 us) per 8 partial sums in the final cross-CTA reduction.
+  if (h->jsub == 2 && !getenv("MDQT_FORCE_IPT") && !getenv("MDQT_FORCE_NSPLIT")) {
+    auto model = [&](long long ctas, int warps, double pairs_per_warp, int ns) {
+      const double per_sm = (double)((ctas + 147) / 148);
+      const double starve = per_sm * warps >= 24.0 ? 1.0 : 24.0 / (per_sm * warps);  // < 6 warps per sub-partition
+      return per_sm * warps * pairs_per_warp * 81.0 / (4 * 1965.0) * starve + 2.8 + (ns > 1 ? 0.5 + 0.9 * ((ns + 7) / 8) : 0.0);
+    };
+    const long long tiles128 = ((long long)N + 127) / 128 * B, tiles32 = ((long long)N + 31) / 32 * B;
+    double best_t = model(tiles128 * h->nsplit, 8, h->jlen / 2.0, h->nsplit);
+    for (int js = 8; js >= 4; js /= 2)
+      for (int ns = 1; ns <= 16; ns++) {
+        const int jlen = ((N + ns - 1) / ns + 7) & ~7;
+        const int real_ns = (N + jlen - 1) / jlen;
+        if (real_ns != ns) continue;
+        const long long ctas = tiles32 * ns;
+        if ((ctas + 147) / 148 * js > 32) continue;  // keep every CTA resident (64 registers x 1024 threads per SM)
+        const double t = model(ctas, js, (double)jlen / js, ns);
+        if (t < best_t * 0.98) { best_t = t; h->rg = 32; h->jsub = js; h->nsplit = ns; h->jlen = jlen; h->ipt = 1; }
+      }
+  }
+  if (const char* e = getenv("MDQT_FORCE_RG")) {  // developer knob: MDQT_FORCE_RG=32 with MDQT_FORCE_JSUB=4|8 and MDQT_FORCE_NSPLIT
+    if (atoi(e) == 32) { h->rg = 32; h->ipt = 1; h->jsub = 8; }
+    else h->rg = kForceThreads;
+  }
   if (const char* e = getenv("MDQT_FORCE_JSUB")) {
     int js = atoi(e);
-    h->jsub = (js == 2 || (js == 4 && getenv("MDQT_FORCE_IPT") && atoi(getenv("MDQT_FORCE_IPT")) == 2)) ? js : 1;
+    if (h->rg == 32) h->jsub = js == 4 ? 4 : 8;
+    else h->jsub = (js == 2 || (js == 4 && getenv("MDQT_FORCE_IPT") && atoi(getenv("MDQT_FORCE_IPT")) == 2)) ? js : 1;
   }
   // developer tuning knobs (kernel A/B runs): override the plan
-  if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = (atoi(e) == 2 && h->rg != 32) ? 2 : 1;
   if (const char* e = getenv("MDQT_FORCE_NSPLIT")) {
     int ns = std::max(1, std::min(1024, atoi(e)));
     h->jlen = ((N + ns - 1) / ns + 7) & ~7;
     h->nsplit = (N + h->jlen - 1) / h->jlen;
   }
-  h->itiles = (h->nrows + kForceThreads - 1) / kForceThreads;  // upper bound on i-tiles of this handle
+  h->itiles = (h->nrows + 31) / 32;  // upper bound on i-tiles of this handle (32-row groups)
 }
 
 int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
@@ -335,9 +364,10 @@ static ForceArgs force_args(mdqt_handle* h) {
   ForceArgs a;
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
-  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.Rfix = h->Rfix;
+  a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
+  a.half_l = (h->p.rcut == h->p.L / 2.) ? 1 : 0;
   return a;
 }
 

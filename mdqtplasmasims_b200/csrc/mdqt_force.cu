@@ -25,7 +25,21 @@
 
 namespace mdqt {
 
-__constant__ double c_exp2tab[kExpTable];
+// Build-time variants of the pair arithmetic (A/B'd on B200, scripts/ab_pairs.py; defaults = the measured best):
+//   MDQT_EXP_SCALED 1: the exp argument is reduced in units of ln2/T directly from r (one FMA less than forming x = -kappa r)
+//   MDQT_VALID_INT  1: when rcut == L/2 the test 0 < r^2 < rcut^2 is ONE unsigned compare of the high word of r^2
+//                      (r^2 < 2^126 in fixed-point units), no FP64-pipe DSETP
+//   kExpTable 1024 (mdqt_internal.h): degree-3 polynomial instead of degree-5 (two FMAs less)
+#ifndef MDQT_EXP_SCALED
+#define MDQT_EXP_SCALED 1
+#endif
+#ifndef MDQT_VALID_INT
+#define MDQT_VALID_INT 1
+#endif
+constexpr int kExpShift = (kExpTable == 1024) ? 10 : 13;  // 20 - log2(kExpTable)
+static_assert(kExpTable == 128 || kExpTable == 1024, "exp table must have 128 or 1024 entries");
+
+__device__ double c_exp2tab[kExpTable];  // global (L2-resident), not __constant__: the CTA prologue reads it with a per-thread index
 
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER on B200 at N=3500 (114 vs 74 us per MD step)
@@ -34,13 +48,13 @@ bool pdl_enabled() {
 
 void upload_exp_table() {
   double tab[kExpTable];
-  // entry j holds the bit pattern of 2^(j/128) with (j << 13) pre-subtracted from its high word, so that the kernel
-  // patches the exponent with a single add of (n << 13), n = 128 q + j  (high word += q << 20)
+  // entry j holds the bit pattern of 2^(j/T) with (j << kExpShift) pre-subtracted from its high word, so that the kernel
+  // patches the exponent with a single add of (n << kExpShift), n = T q + j  (high word += q << 20)
   for (int j = 0; j < kExpTable; j++) {
     tab[j] = (double)exp2l((long double)j / (long double)kExpTable);
     unsigned long long bits;
     memcpy(&bits, &tab[j], 8);
-    bits -= (unsigned long long)((unsigned)j << 13) << 32;
+    bits -= (unsigned long long)((unsigned)j << kExpShift) << 32;
     memcpy(&tab[j], &bits, 8);
   }
   cudaMemcpyToSymbol(c_exp2tab, tab, sizeof(tab));
@@ -51,6 +65,7 @@ void upload_exp_table() {
 struct PairConsts {
   double L, invL, invL_lo;
   double kappa_u, negkappa_u, nk_scale, negc, rc2_u;
+  double c1, c2, c3, c4, c5;  // exp polynomial coefficients in the reduced variable
   double out_scale;  // 1/u^2 for forces, 1/u for the potential energy
 };
 
@@ -59,18 +74,27 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
   c.L = a.L; c.invL = a.invL; c.invL_lo = a.invL_lo;
   const double u = a.L / MDQT_2P64;
   c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
-  c.nk_scale = -c.kappa_u * 184.66496523378731614207035916824219;  // 128 * log2(e)
-  c.negc = -0.0054152123481245727298221259488920044;               // -ln2 / 128
+  const double T = (double)kExpTable;
+  c.nk_scale = -c.kappa_u * (T * 1.4426950408889634073599246810018921);  // T * log2(e)
+  c.negc = -0.69314718055994530941723212145817657 / T;                   // -ln2 / T
+#if MDQT_EXP_SCALED
+  const double w = 0.69314718055994530941723212145817657 / T;            // polynomial in rr' = rr / w
+  c.c1 = w; c.c2 = w * w / 2; c.c3 = w * w * w / 6; c.c4 = w * w * w * w / 24; c.c5 = w * w * w * w * w / 120;
+#else
+  c.c1 = 1.0; c.c2 = 0.5; c.c3 = 1.6666666666666666e-01; c.c4 = 4.1666666666666664e-02; c.c5 = 8.3333333333333332e-03;
+#endif
   const double rc_u = sqrt(a.rc2) / u;
-  c.rc2_u = rc_u * rc_u;
+  c.rc2_u = a.half_l ? 85070591730234615865843651857942052864.0 /* 2^126 = (L/2)^2 */ : rc_u * rc_u;
   c.out_scale = epot ? 1.0 / u : (1.0 / u) * (1.0 / u);
   return c;
 }
 
 // From r2 (in units u^2): rinv = 1/r, ef = exp(-kappa r), valid = 0 < r2 < rcut^2.
+template <bool HL>
 __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const double* tab, double& rinv, double& ef,
                                           bool& valid) {
-  valid = (r2 < c.rc2_u) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0; SU:222)
+  if (HL) valid = (unsigned)(__double2hiint(r2) - 1) < 0x47D00000u - 1u;  // 0 < r2 < 2^126 on the high word alone
+  else valid = (r2 < c.rc2_u) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0; SU:222)
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));  // MUFU.RSQ64H seed
   double t = r2 * y;
@@ -83,26 +107,55 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
   double tt = fma(r, c.nk_scale, MDQT_MAGIC);
   int n = __double2loint(tt);
   double nd = tt - MDQT_MAGIC;
+#if MDQT_EXP_SCALED
+  double rr = fma(r, c.nk_scale, -nd);        // exact: the reduced argument in units of ln2/T, |rr| <= 1/2
+#else
   double x = c.negkappa_u * r;
   double rr = fma(nd, c.negc, x);
-  double q = fma(rr, 8.3333333333333332e-03, 4.1666666666666664e-02);
-  q = fma(q, rr, 1.6666666666666666e-01);
-  q = fma(q, rr, 0.5);
-  q = fma(q, rr, 1.0);
+#endif
+  double q;
+  if (kExpTable == 1024) {
+    q = fma(rr, c.c3, c.c2);                  // |x| <= ln2/2048: x^4/24 < 6e-16
+  } else {
+    q = fma(rr, c.c5, c.c4);
+    q = fma(q, rr, c.c3);
+    q = fma(q, rr, c.c2);
+  }
+  q = fma(q, rr, c.c1);
   q = fma(q, rr, 1.0);
   double T = tab[n & (kExpTable - 1)];
-  int hi = __double2hiint(T) + (n << 13);  // table high words carry -(idx << 13): net += floor(n/128) << 20
+  int hi = __double2hiint(T) + (n << kExpShift);  // table high words carry -(idx << kExpShift): net += floor(n/T) << 20
   ef = __hiloint2double(hi, __double2loint(T)) * q;
   rinv = y;
 }
 
 constexpr int kTJ = 512;  // j positions staged per pass
 
-// IPT rows per thread; JS = intra-CTA split of every staged j tile over JS groups of 128 threads (more resident warps
-// at small N without more partial sums: the groups' sums are combined through shared memory in ascending group order);
-// UNR = unroll of the j loop.
-template <int IPT, int JS, bool EPOT, int UNR>
-__global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
+#ifdef MDQT_K1_TRACE  // developer build: per-CTA phase time stamps (scripts/k1_trace.py)
+__device__ long long g_trace[8 * 8192];
+#define TRACE(slot)                                                                                              \
+  if (threadIdx.x == 0) {                                                                                        \
+    const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                             \
+    if (cta_ < 8192) {                                                                                           \
+      long long gt_;                                                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                    \
+      g_trace[cta_ * 8 + slot] = gt_;                                                                            \
+      if (slot == 0) { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); g_trace[cta_ * 8 + 7] = sm_; }      \
+    }                                                                                                            \
+  }
+#else
+#define TRACE(slot)
+#endif
+
+// RG = ion rows per thread group (128, or 32 for small systems); IPT rows per thread; JS = intra-CTA split of every staged
+// j tile over JS groups of RG threads (more resident warps at small N WITHOUT more partial sums in global memory: the
+// groups' sums are combined through shared memory in ascending group order); UNR = unroll of the j loop.
+// Small N wants RG = 32, JS = 8: the same 256-thread CTAs and the same work per warp as RG = 128, JS = 2, but a row's
+// force is split over 4x fewer CTAs, so the final cross-CTA reduction (a chain of dependent L2 loads executed by the
+// last CTA of a tile while the rest of the chip idles) shrinks from 20 partials to 5 at N = 3500.
+template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG>
+__global__ void __launch_bounds__(RG * JS) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
+  constexpr int kForceThreads = RG;  // shadows the namespace constant: rows per group in this instantiation
   __shared__ longlong2 sxy[kTJ];
   __shared__ long long sz[kTJ];
   __shared__ double stab[kExpTable];
@@ -111,6 +164,7 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
   __shared__ int s_last;
   constexpr int NT = kForceThreads * JS;
 
+  TRACE(0)
   const int tid = threadIdx.x;
   const int ti = tid % kForceThreads, jh = tid / kForceThreads;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
@@ -118,7 +172,6 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
   const long long* __restrict__ X = a.Rfix + (size_t)b * 3 * a.ld;
   const long long* __restrict__ Y = X + a.ld;
   const long long* __restrict__ Z = Y + a.ld;
-  pdl_launch_dependents();
   for (int k = tid; k < kExpTable; k += NT) stab[k] = c_exp2tab[k];
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
 
@@ -143,6 +196,7 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
       sz[k] = Z[j];
     }
     __syncthreads();
+    if (jc == jbeg) { TRACE(1) }
     const int lo = (cnt * jh) / JS, hi = (cnt * (jh + 1)) / JS;
 #pragma unroll UNR
     for (int jj = lo; jj < hi; jj++) {
@@ -157,15 +211,19 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
         const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
         double rinv, ef;
         bool valid;
-        pair_core(r2, c, stab, rinv, ef, valid);
+        pair_core<HL>(r2, c, stab, rinv, ef, valid);
         if (EPOT) {
           double u = ef * rinv;                       // exp(-r/lDeb)/r (SU:268)
           ax[k] += valid ? u : 0.0;
         } else {
           double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
           // 0 < r2 < rc2 as ONE predicate (DSETP, then ISETP chained with .and) and one select
-          asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %2;\n\tsetp.ne.and.s32 q, %3, 0, p;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
-              : "+d"(f) : "d"(r2), "d"(c.rc2_u), "r"(__double2hiint(r2)));
+          if (HL)
+            asm("{\n\t.reg .pred q;\n\t.reg .u32 t;\n\tadd.u32 t, %1, -1;\n\tsetp.lt.u32 q, t, 0x47CFFFFF;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+                : "+d"(f) : "r"(__double2hiint(r2)));
+          else
+            asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %2;\n\tsetp.ne.and.s32 q, %3, 0, p;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+                : "+d"(f) : "d"(r2), "d"(c.rc2_u), "r"(__double2hiint(r2)));
           ax[k] = fma(f, dx, ax[k]);
           ay[k] = fma(f, dy, ay[k]);
           az[k] = fma(f, dz, az[k]);
@@ -173,6 +231,10 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
       }
     }
   }
+  TRACE(2)
+  // programmatic dependent launch: the next kernel may be scheduled now, so that its launch latency and prologue
+  // overlap this kernel's epilogue (triggering at kernel START instead piles up waiting grids and was slower)
+  pdl_launch_dependents();
   if (JS > 1) {  // combine the thread groups: group 0 adds the others' sums in ascending group order
     if (jh > 0) {
 #pragma unroll
@@ -239,6 +301,7 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
     if (s_last) *ctr = 0;  // self-reset for the next call
   }
   __syncthreads();
+  TRACE(3)
   if (!s_last) return;
   __threadfence();
   // the last CTA: all NT threads share the final reduction (thread -> (row slot, component) round robin)
@@ -248,30 +311,56 @@ __global__ void __launch_bounds__(kForceThreads * JS) k_pairs(ForceArgs a, doubl
     if (row < a.row0 + a.nrows) {
       const double* src = a.Fpart + ((size_t)b * 3 + comp) * a.ld + row;
       const size_t stride = (size_t)a.B * 3 * a.ld;
+      // the partials of a row are fetched as batches of 8 independent loads (one L2 round trip per batch; the
+      // 4-per-batch version cost 4 us at N = 3500 with 20 splits, profiles/), then added in ascending split order
       double sum = 0.0;
-      // (a 16-wide batched variant of this loop measured 4 us SLOWER per launch on B200; keep it simple)
-#pragma unroll 4
-      for (int s = 0; s < a.nsplit; s++) sum += __ldcg(src + (size_t)s * stride);
+      for (int s0 = 0; s0 < a.nsplit; s0 += 8) {  // (wider batches raise the register count of the WHOLE kernel)
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (s0 + k < a.nsplit) ? __ldcg(src + (size_t)(s0 + k) * stride) : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += v[k];  // + 0.0 for the absent splits: exact
+      }
       a.F[((size_t)b * 3 + comp) * a.ld + row] = sum;
     }
   }
+  TRACE(4)
+}
+
+template <bool EPOT, bool HL>
+static void launch_pairs_hl(const ForceArgs& a, double* partials, cudaStream_t s, dim3 grid, int ipt, int jsub, bool pdl) {
+  // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
+  if (a.rg == 32) {
+    if (jsub == 8) launch_kernel(k_pairs<1, 8, EPOT, 8, HL, 32>, grid, dim3(256), s, pdl, a, partials);
+    else launch_kernel(k_pairs<1, 4, EPOT, 8, HL, 32>, grid, dim3(128), s, pdl, a, partials);
+    return;
+  }
+  if (ipt == 2 && jsub == 4) launch_kernel(k_pairs<2, 4, EPOT, 4, HL, 128>, grid, dim3(kForceThreads * 4), s, pdl, a, partials);
+  else if (ipt == 2 && jsub == 2) launch_kernel(k_pairs<2, 2, EPOT, 4, HL, 128>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
+  else if (ipt == 2) launch_kernel(k_pairs<2, 1, EPOT, 4, HL, 128>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  else if (jsub == 2) launch_kernel(k_pairs<1, 2, EPOT, 8, HL, 128>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
+  else launch_kernel(k_pairs<1, 1, EPOT, 4, HL, 128>, grid, dim3(kForceThreads), s, pdl, a, partials);
 }
 
 template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
-  const int ipt = a.ipt == 2 ? 2 : 1;  // rows per thread and intra-CTA split: decided by the planner from (N, B) only
-  const int jsub = (a.jsub == 2 || a.jsub == 4) ? a.jsub : 1;
-  dim3 grid((a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt), a.nsplit, a.B);
+  // rows per group / per thread and the intra-CTA split: decided by the planner from (N, B) only
+  const int rg = a.rg == 32 ? 32 : kForceThreads;
+  const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
+  const int jsub = (rg == 32) ? (a.jsub == 8 ? 8 : 4) : ((a.jsub == 2 || a.jsub == 4) ? a.jsub : 1);
+  dim3 grid((a.nrows + rg * ipt - 1) / (rg * ipt), a.nsplit, a.B);
   const bool pdl = !EPOT && pdl_enabled();
-  // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
-  if (ipt == 2 && jsub == 4) launch_kernel(k_pairs<2, 4, EPOT, 4>, grid, dim3(kForceThreads * 4), s, pdl, a, partials);
-  else if (ipt == 2 && jsub == 2) launch_kernel(k_pairs<2, 2, EPOT, 4>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
-  else if (ipt == 2) launch_kernel(k_pairs<2, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
-  else if (jsub == 2) launch_kernel(k_pairs<1, 2, EPOT, 8>, grid, dim3(kForceThreads * 2), s, pdl, a, partials);
-  else launch_kernel(k_pairs<1, 1, EPOT, 4>, grid, dim3(kForceThreads), s, pdl, a, partials);
+  if (a.half_l && MDQT_VALID_INT) launch_pairs_hl<EPOT, true>(a, partials, s, grid, ipt, jsub, pdl);
+  else launch_pairs_hl<EPOT, false>(a, partials, s, grid, ipt, jsub, pdl);
 }
 
 void launch_forces(const ForceArgs& a, cudaStream_t s) { launch_pairs<false>(a, nullptr, s); }
+
+#ifdef MDQT_K1_TRACE
+extern "C" int mdqt_debug_read_trace(long long* out, int n) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * (size_t)n);
+}
+#endif
 
 __global__ void k_to_fixed(const double* __restrict__ R, long long* __restrict__ Rfix, size_t n, double invL, double invL_lo) {
   size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +371,7 @@ void launch_to_fixed(const double* R, long long* Rfix, size_t n, double invL, do
 }
 
 int epot_partials_needed(const ForceArgs& a) {
-  int tiles = (a.nrows + kForceThreads - 1) / kForceThreads;  // upper bound (IPT = 1)
+  int tiles = (a.nrows + 31) / 32;  // upper bound (32-row groups, IPT = 1)
   return tiles * a.nsplit * a.B;
 }
 
@@ -302,8 +391,9 @@ __global__ void k_epot_final(const double* __restrict__ partials, int per_traj, 
 
 void launch_epot(const ForceArgs& a, double* partials, double* result, cudaStream_t s) {
   launch_pairs<true>(a, partials, s);
-  const int ipt = a.ipt == 2 ? 2 : 1;
-  int tiles = (a.nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt);
+  const int rg = a.rg == 32 ? 32 : kForceThreads;
+  const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
+  int tiles = (a.nrows + rg * ipt - 1) / (rg * ipt);
   // ordered pairs counted twice -> 1/2; per particle -> 1/N (SU:272)
   k_epot_final<<<a.B, 256, 0, s>>>(partials, tiles * a.nsplit, 0.5 / (double)a.N, result);
 }

@@ -6,7 +6,10 @@
 namespace mdqt {
 
 constexpr int kForceThreads = 128;   // threads per CTA of the pair kernels
-constexpr int kExpTable = 128;       // entries of the 2^(j/128) table used by the fp64 exp
+#ifndef MDQT_EXP_T
+#define MDQT_EXP_T 1024
+#endif
+constexpr int kExpTable = MDQT_EXP_T; // entries of the 2^(j/T) table used by the fp64 exp (128: degree-5 polynomial, 1024: degree-3)
 constexpr int kVelBins = 2001;       // KDE bins of output() (SU:120-123)
 
 struct ForceArgs {
@@ -19,7 +22,9 @@ struct ForceArgs {
   int row0, nrows;   // rows owned by this handle
   int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
   int ipt;           // ion rows per thread (1 or 2)
-  int jsub;          // intra-CTA split of each j tile over 128-thread groups (1 or 2)
+  int jsub;          // intra-CTA split of each j tile over thread groups (1, 2, 4; 4 or 8 with 32-row groups)
+  int rg;            // ion rows per thread group: 128 (default) or 32 (small systems)
+  int half_l;        // rcut == L/2 exactly (every reference program): the cut-off is a power of two in fixed-point units
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
 };
 

@@ -169,7 +169,6 @@ __device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g) {
 // ------------------------------------------------------------------------------------------------------------
 template <int NL, bool FORCED>
 __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
-  pdl_launch_dependents();
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = gid & 1;
   const long long slot = gid >> 1;
@@ -177,7 +176,10 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   // inactive lanes still run (the shuffles are warp-wide) on a harmless shadow of the first ion; they never store
   const int b = active ? (int)(slot / a.nrows) : 0;
   const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
-  const int S = a.S;
+  const int S = (NL == 6) ? 12 : a.S;  // compile-time stride for the 12-level hot path
+  // the 12-level scheme always kicks and tracks tPart together with step() (SU); the small schemes choose at run time
+  const bool do_kick = (NL == 6) ? (a.do_step != 0) : (a.do_kick != 0);
+  const bool do_tpart = (NL == 6) ? (a.do_step != 0) : (a.do_tpart != 0);
 
   double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
   double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     v2 = Vb[(size_t)c2 * a.ld + i];
     fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
   }
-  if (a.do_tpart) tp = a.tPart[(size_t)b * a.ld + i];
+  if (do_tpart) tp = a.tPart[(size_t)b * a.ld + i];
   double t = a.t0;
   const double DT = 0.5 * a.dtq;
   const double dEDP = -a.detuning + a.detuningDP;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       expDet = 0.0126 * a.fracOfSig * a.Te * t /
                (sqrt(a.density) * a.sig0 * sqrt(1 + 0.00014314 * t * t * a.Te / (a.density * a.sig0 * a.sig0)));
     const double vq = vx * a.pv2qv;
-    if (a.do_tpart) tp = __dadd_rn(tp, a.dtq);
+    if (do_tpart) tp = __dadd_rn(tp, a.dtq);
 
     // the uniforms of this (ion, substep): both lanes of an ion draw the same numbers
     double u0, u1;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     // ---- no-jump branch, evaluated by every lane (jumps are rare, and a warp-uniform flow keeps the cross-lane
     //      exchanges on plain full-mask shuffles); lanes that jump discard the result below ----
     double kick = 0.0;
-    if (a.do_kick) {  // optical force from the pre-step coherences (SU:490-503; TS:170-174)
+    if (do_kick) {  // optical force from the pre-step coherences (SU:490-503; TS:170-174)
       kick = ksA * im_acb(y[0], y[1]) - ksB * im_acb(y[0], y[2]);
       if (NL == 6)
         kick += kd0 * im_acb(y[4], y[2]) + kd1 * im_acb(y[3], y[1]) - kd2 * im_acb(y[5], y[2]) - kd3 * im_acb(y[4], y[1]);
@@ -342,7 +344,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
       const bool sDecay = !(u2 < C.dfrac);
       kick = 0.0;
-      if (a.do_kick && lane == 0) {  // counted once in the cross-lane sum
+      if (do_kick && lane == 0) {  // counted once in the cross-lane sum
         double mag = sDecay ? a.vKick : a.vKickDP;
         kick = (u3 < 0.5) ? mag : -mag;
       }
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
 #pragma unroll
       for (int k = 0; k < NL; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
     }
-    if (a.do_kick) {
+    if (do_kick) {
       kick = kick + __shfl_xor_sync(0xffffffffu, kick, 1);
       vx = __dadd_rn(vx, kick);  // SU:705
     }
@@ -385,6 +387,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     if (a.do_step) t = __dadd_rn(t, a.dtq);  // SU:716
   }
 
+  pdl_launch_dependents();  // the force kernel's launch + prologue may overlap the stores below (it waits before reading)
   if (!active) return;
 #pragma unroll
   for (int k = 0; k < NL; k++)
@@ -398,10 +401,10 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       Rb[i] = rx; Xf[i] = to_fixed(rx, a.invL, a.invL_lo);
       Vb[i] = vx;
     }
-  } else if (a.do_kick && lane == 0) {
+  } else if (do_kick && lane == 0) {
     Vb[i] = vx;
   }
-  if (a.do_tpart && lane == 0) a.tPart[(size_t)b * a.ld + i] = tp;
+  if (do_tpart && lane == 0) a.tPart[(size_t)b * a.ld + i] = tp;
 }
 
 // ------------------------------------------------------------------------------------------------------------
