@@ -140,6 +140,18 @@ int mdqt_vaf(mdqt_handle* h, int start, double* vaf);
 /* Test hook: replace the Philox stream by caller-supplied uniforms u[nsub][n_ions][5] (rand, rand2, randDOrS,
  * randDir, rand3) for the next substeps/qsteps calls (n_traj must be 1). NULL restores Philox. */
 int mdqt_set_forced_uniforms(mdqt_handle* h, const double* u, int nsub);
+/* recordPairPairCorr() (MD:584-652): g(r) over the N(N-1) ordered minimum-image pairs in bins of `step` up to
+ * rmax (the reference: 0.05 and L/2); nbins must equal (int)(rmax/step). g = double [n_traj][nbins] normalised as
+ * the reference does (MD:627-635), counts = uint64 [n_traj][nbins] raw pair counts; either may be NULL. */
+int mdqt_pair_correlation(mdqt_handle* h, double step, double rmax, int nbins, double* g, uint64_t* counts);
+/* Velocity store vStore[3][N][T] (MD:121) on the device: begin(T) allocates and zeroes it, record(tS) is
+ * recordVelsForAutocorrelations(tS) (MD:513-520), upload() replaces it from a host array [n_traj][3][n_ions][T]. */
+int mdqt_vstore_begin(mdqt_handle* h, int T);
+int mdqt_vstore_record(mdqt_handle* h, int tS);
+int mdqt_vstore_upload(mdqt_handle* h, const double* v);
+/* recordVAF / recordLongViscAutoCorr / recordVCubeAutoCorr / recordVFourthAutoCorr (MD:654-823) over the stored
+ * velocities: each output is double [n_traj][T] (NULL = skip); Gamma enters the subtracted constants (MD:710, 785). */
+int mdqt_autocorrelations(mdqt_handle* h, double Gamma, double* vaf, double* longvisc, double* vcube, double* vfourth);
 /* Test hook: uniforms u[n_ions][2] for the next mdqt_tag_particles calls (n_traj must be 1). NULL restores Philox. */
 int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u);
 /* Test hook for the MD-family Andersen thermostat: per-ion collision uniforms u[n_ions] and the velocities

@@ -31,6 +31,8 @@ struct mdqt_handle {
   cudaStream_t stream;
   double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops, *vhold, *forced_tag;
   int* tagged;      // [B][N] spin tags + [B] counts (allocated on first use)
+  unsigned long long* gr_counts;  // [B][gr_max_bins]
+  double *vstore, *ac_partials, *ac_out; int vstore_T;  // vStore[B][3][N][T] and autocorrelation scratch
   unsigned* counters;
   long long* Rfix;  // periodic fixed-point copy of R (what the pair kernels read)
   int rfix_dirty;   // R was written by an upload / externally: refresh Rfix before the next pair kernel
@@ -225,6 +227,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->t = 0.0; h->substep = 0; h->vv_step = 0; h->Rfix = nullptr; h->rfix_dirty = 1;
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
   h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
+  h->gr_counts = nullptr; h->vstore = h->ac_partials = h->ac_out = nullptr; h->vstore_T = 0;
   h->timing = false; h->ev_used = 0; h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
   plan_force(h);
   if (h->S) fill_qt_consts(h->qc, h->S, p->Om, p->OmDP, p->dR, p->vKick, p->vKickDP, p->dtq, p->g2E, p->quad);
@@ -269,6 +272,10 @@ int mdqt_destroy(mdqt_handle* h) {
                     h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn, h->vhold, h->forced_tag};
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->tagged) cudaFree(h->tagged);
+  if (h->gr_counts) cudaFree(h->gr_counts);
+  if (h->vstore) cudaFree(h->vstore);
+  if (h->ac_partials) cudaFree(h->ac_partials);
+  if (h->ac_out) cudaFree(h->ac_out);
   if (h->counters) cudaFree(h->counters);
   if (h->Rfix) cudaFree(h->Rfix);
   for (cudaEvent_t ev : h->ev) cudaEventDestroy(ev);
@@ -632,6 +639,83 @@ int mdqt_vaf(mdqt_handle* h, int start, double* vaf) {
   CU(cudaMemcpyAsync(vaf, h->scalars, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_pair_correlation(mdqt_handle* h, double step, double rmax, int nbins, double* g, uint64_t* counts) {
+  if (!h || (!g && !counts)) return fail(MDQT_EINVAL, "null argument");
+  if (!(step > 0) || nbins != (int)(rmax / step) || nbins < 1 || nbins > gr_max_bins())
+    return fail(MDQT_EINVAL, "nbins must equal (int)(rmax/step) and lie in [1, 2048]");
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "pair correlation needs a handle that owns all rows");
+  CU(cudaSetDevice(h->p.device));
+  if (!h->gr_counts) CU(cudaMalloc((void**)&h->gr_counts, sizeof(unsigned long long) * (size_t)h->B * gr_max_bins()));
+  launch_gr(h->R, h->N, h->ld, h->B, h->p.L, step, nbins, h->gr_counts, h->stream);
+  std::vector<unsigned long long> c((size_t)h->B * nbins);
+  CU(cudaMemcpyAsync(c.data(), h->gr_counts, c.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  const int N = h->N;
+  for (int b = 0; b < h->B; b++)
+    for (int i = 0; i < nbins; i++) {
+      const double cnt = (double)c[(size_t)b * nbins + i];
+      if (counts) counts[(size_t)b * nbins + i] = c[(size_t)b * nbins + i];
+      // the reference's normalisation, integer sub-expressions included (MD:627-635)
+      if (g) g[(size_t)b * nbins + i] = (i == 0) ? cnt / (N * 4 / 3 * M_PI * step * step * step)
+                                                  : cnt / (N * 3 * step * step * step * i * i);
+    }
+  return MDQT_OK;
+}
+
+int mdqt_vstore_begin(mdqt_handle* h, int T) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (T < 1 || T > 5000) return fail(MDQT_EINVAL, "T must lie in [1, 5000]");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (double** ptr : {&h->vstore, &h->ac_partials, &h->ac_out}) if (*ptr) { cudaFree(*ptr); *ptr = nullptr; }
+  const size_t n = (size_t)h->B * 3 * h->N * T;
+  CU(cudaMalloc((void**)&h->vstore, n * 8));
+  CU(cudaMemsetAsync(h->vstore, 0, n * 8, h->stream));
+  CU(cudaMalloc((void**)&h->ac_partials, (size_t)h->B * autocorr_chunks(3 * h->N) * 4 * T * 8));
+  CU(cudaMalloc((void**)&h->ac_out, (size_t)h->B * 4 * T * 8));
+  h->vstore_T = T;
+  return MDQT_OK;
+}
+
+int mdqt_vstore_record(mdqt_handle* h, int tS) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!h->vstore) return fail(MDQT_ESTATE, "mdqt_vstore_begin not called");
+  if (tS < 0 || tS >= h->vstore_T) return fail(MDQT_EINVAL, "time slot outside [0,T)");
+  CU(cudaSetDevice(h->p.device));
+  launch_vstore_record(h->V, h->vstore, h->N, h->ld, h->B, h->vstore_T, tS, h->stream);
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_vstore_upload(mdqt_handle* h, const double* v) {
+  if (!h || !v) return fail(MDQT_EINVAL, "null argument");
+  if (!h->vstore) return fail(MDQT_ESTATE, "mdqt_vstore_begin not called");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaMemcpy(h->vstore, v, (size_t)h->B * 3 * h->N * h->vstore_T * 8, cudaMemcpyHostToDevice));
+  return MDQT_OK;
+}
+
+int mdqt_autocorrelations(mdqt_handle* h, double Gamma, double* vaf, double* longvisc, double* vcube, double* vfourth) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!h->vstore) return fail(MDQT_ESTATE, "mdqt_vstore_begin not called");
+  if (!(Gamma > 0)) return fail(MDQT_EINVAL, "Gamma must be > 0");
+  CU(cudaSetDevice(h->p.device));
+  const int T = h->vstore_T;
+  // subtracted constants as the reference writes them (MD:710, 785)
+  launch_autocorr(h->vstore, h->N, h->B, T, 3 / (Gamma * Gamma), 3 * 9 / (Gamma * Gamma * Gamma * Gamma), h->ac_partials,
+                  h->ac_out, h->stream);
+  std::vector<double> o((size_t)h->B * 4 * T);
+  CU(cudaMemcpyAsync(o.data(), h->ac_out, o.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  double* dst[4] = {vaf, longvisc, vcube, vfourth};
+  for (int b = 0; b < h->B; b++)
+    for (int p = 0; p < 4; p++)
+      if (dst[p]) memcpy(dst[p] + (size_t)b * T, o.data() + ((size_t)b * 4 + p) * T, (size_t)T * 8);
   return MDQT_OK;
 }
 

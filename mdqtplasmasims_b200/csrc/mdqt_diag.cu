@@ -99,6 +99,128 @@ void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, doub
   k_vaf<<<B, 1024, 0, s>>>(V, Vhold, N, ld, out);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// recordPairPairCorr() (MD:584-625): histogram of the N(N-1) ordered minimum-image distances in bins of `step`.
+// A diagnostic called every 100 MD steps, so it is written for IDENTICAL bins rather than speed: plain fp64 with the
+// reference's own operations and roundings (round(), one rounding per product/sum, sqrt, division). Counts are
+// integers -> order-independent. grid (i tiles of 256, j splits, B).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGrMaxBins = 2048;
+__global__ void __launch_bounds__(256) k_gr(const double* __restrict__ R, int N, int ld, double L, double step, int nbins,
+                                            int jlen, unsigned long long* __restrict__ counts) {
+  __shared__ double sx[256], sy[256], sz[256];
+  __shared__ unsigned hist[kGrMaxBins];
+  const int b = blockIdx.z;
+  const double* X = R + (size_t)b * 3 * ld;
+  const double* Y = X + ld;
+  const double* Z = Y + ld;
+  for (int k = threadIdx.x; k < nbins; k += 256) hist[k] = 0;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const bool live = i < N;
+  const double xi = live ? X[i] : 0.0, yi = live ? Y[i] : 0.0, zi = live ? Z[i] : 0.0;
+  const int jbeg = blockIdx.y * jlen, jend = min(N, jbeg + jlen);
+  for (int jc = jbeg; jc < jend; jc += 256) {
+    __syncthreads();
+    const int j = jc + threadIdx.x;
+    if (j < jend) { sx[threadIdx.x] = X[j]; sy[threadIdx.x] = Y[j]; sz[threadIdx.x] = Z[j]; }
+    __syncthreads();
+    const int cnt = min(256, jend - jc);
+    if (live)
+      for (int k = 0; k < cnt; k++) {
+        if (jc + k == i) continue;                                    // MD:597
+        double dx = xi - sx[k], dy = yi - sy[k], dz = zi - sz[k];
+        dx = __dadd_rn(dx, -__dmul_rn(L, round(__ddiv_rn(dx, L))));   // MD:608-610
+        dy = __dadd_rn(dy, -__dmul_rn(L, round(__ddiv_rn(dy, L))));
+        dz = __dadd_rn(dz, -__dmul_rn(L, round(__ddiv_rn(dz, L))));
+        const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        const int bin = (int)__ddiv_rn(__dsqrt_rn(d2), step);         // MD:613-615
+        if (bin < nbins) atomicAdd(&hist[bin], 1u);
+      }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nbins; k += 256)
+    if (hist[k]) atomicAdd(&counts[(size_t)b * nbins + k], (unsigned long long)hist[k]);
+}
+int gr_max_bins() { return kGrMaxBins; }
+void launch_gr(const double* R, int N, int ld, int B, double L, double step, int nbins, unsigned long long* counts, cudaStream_t s) {
+  cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * (size_t)B * nbins, s);
+  const int tiles = (N + 255) / 256;
+  int nsplit = (148 * 4 + tiles * B - 1) / (tiles * B);  // enough CTAs to fill the chip at small N
+  nsplit = max(1, min(nsplit, (N + 255) / 256));
+  const int jlen = ((N + nsplit - 1) / nsplit + 255) & ~255;
+  dim3 grid(tiles, (N + jlen - 1) / jlen, B);
+  k_gr<<<grid, 256, 0, s>>>(R, N, ld, L, step, nbins, jlen, counts);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Velocity store and the four power autocorrelations recordVAF / recordLongViscAutoCorr / recordVCubeAutoCorr /
+// recordVFourthAutoCorr (MD:654-823): C_p[t] = 1/(N (T-t)) sum_i sum_c sum_{j<T-t} (v(j) v(j+t))^p, p = 1..4 (the
+// reference writes the p-th powers out as products of pow(.,2) factors), minus 3/Gamma^2 (p = 2) and 27/Gamma^4 (p = 4).
+// vstore = [B][3][N][T] like the reference's vStore[3][N][T]. One CTA = (chunk of series, tile of 256 lags): the series
+// is staged in shared memory, thread <-> lag, s[j] is a broadcast read and s[j+t] a conflict-free one. Chunk partials
+// are summed in ascending chunk order by a second kernel -> reproducible.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_vstore_record(const double* __restrict__ V, double* __restrict__ vstore, int N, int ld, int T, int tS) {
+  const int b = blockIdx.y;
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 3LL * N) return;
+  const int c = (int)(g / N), i = (int)(g % N);
+  vstore[(((size_t)b * 3 + c) * N + i) * T + tS] = V[((size_t)b * 3 + c) * ld + i];  // MD:513-520
+}
+void launch_vstore_record(const double* V, double* vstore, int N, int ld, int B, int T, int tS, cudaStream_t s) {
+  dim3 grid((unsigned)((3LL * N + 255) / 256), B);
+  k_vstore_record<<<grid, 256, 0, s>>>(V, vstore, N, ld, T, tS);
+}
+
+constexpr int kAcSeries = 32;  // series per CTA chunk
+__global__ void __launch_bounds__(256) k_autocorr(const double* __restrict__ vstore, int nseries, int T,
+                                                  double* __restrict__ partials) {
+  extern __shared__ double sser[];  // [T]
+  const int b = blockIdx.z;
+  const int t = blockIdx.y * 256 + threadIdx.x;  // this thread's lag
+  const int s0 = blockIdx.x * kAcSeries, s1 = min(nseries, s0 + kAcSeries);
+  const double* base = vstore + (size_t)b * nseries * T;
+  double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+  for (int s = s0; s < s1; s++) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < T; k += 256) sser[k] = base[(size_t)s * T + k];
+    __syncthreads();
+    if (t < T) {
+      const int n = T - t;
+#pragma unroll 4
+      for (int j = 0; j < n; j++) {
+        const double p = sser[j] * sser[j + t];
+        const double p2 = p * p;
+        a1 += p; a2 += p2; a3 = fma(p2, p, a3); a4 = fma(p2, p2, a4);
+      }
+    }
+  }
+  if (t < T) {
+    double* o = partials + (((size_t)b * gridDim.x + blockIdx.x) * 4) * T + t;
+    o[0] = a1; o[T] = a2; o[2 * (size_t)T] = a3; o[3 * (size_t)T] = a4;
+  }
+}
+// out[b][p][t] = sum over chunks (ascending) / (N (T - t)) - sub[p]
+__global__ void k_autocorr_final(const double* __restrict__ partials, int nchunks, int T, int N, double sub2, double sub4,
+                                 double* __restrict__ out) {
+  const int b = blockIdx.z, p = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; c++) s += partials[(((size_t)b * nchunks + c) * 4 + p) * T + t];
+  const double sub = (p == 1) ? sub2 : (p == 3) ? sub4 : 0.0;
+  out[((size_t)b * 4 + p) * T + t] = s / ((double)N * (double)(T - t)) - sub;
+}
+int autocorr_chunks(int nseries) { return (nseries + kAcSeries - 1) / kAcSeries; }
+void launch_autocorr(const double* vstore, int N, int B, int T, double sub2, double sub4, double* partials, double* out,
+                     cudaStream_t s) {
+  const int nseries = 3 * N, nchunks = autocorr_chunks(nseries);
+  dim3 grid(nchunks, (T + 255) / 256, B);
+  k_autocorr<<<grid, 256, (size_t)T * sizeof(double), s>>>(vstore, nseries, T, partials);
+  dim3 g2((T + 255) / 256, 4, B);
+  k_autocorr_final<<<g2, 256, 0, s>>>(partials, nchunks, T, N, sub2, sub4, out);
+}
+
 // pops[b][i][3] = popS, popP, popD with the reference's state grouping (12/7-level: S 0,1; P 2..5; D 6..S-1)
 __global__ void k_populations(const double* __restrict__ psi, int S, int N, int ld, double* __restrict__ pops) {
   const int b = blockIdx.y;

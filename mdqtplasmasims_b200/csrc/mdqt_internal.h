@@ -105,6 +105,13 @@ void launch_lf(const LFArgs& a, cudaStream_t s);
 void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s);
 void launch_transpose_psi_in(const double* psi_aos, double* psi_soa, int S, int N, int ld, int B, cudaStream_t s);
 void launch_transpose_psi_out(const double* psi_soa, double* psi_aos, int S, int N, int ld, int B, cudaStream_t s);
+// recordPairPairCorr (MD:584-625): counts[B][nbins] of ordered pairs per distance bin (nbins <= gr_max_bins())
+int gr_max_bins();
+void launch_gr(const double* R, int N, int ld, int B, double L, double step, int nbins, unsigned long long* counts, cudaStream_t s);
+// vStore (MD:121, 513-520) and the four power autocorrelations (MD:654-823); T*8 bytes of dynamic shared memory (T <= 5000)
+void launch_vstore_record(const double* V, double* vstore, int N, int ld, int B, int T, int tS, cudaStream_t s);
+int autocorr_chunks(int nseries);
+void launch_autocorr(const double* vstore, int N, int B, int T, double sub2, double sub4, double* partials, double* out, cudaStream_t s);
 double run_fp64_peak(cudaStream_t s);
 void upload_exp_table();
 

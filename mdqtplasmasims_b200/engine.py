@@ -45,7 +45,8 @@ ABI_SYMBOLS = [
     "mdqt_qsteps", "mdqt_set_forced_uniforms", "mdqt_set_forced_collisions", "mdqt_philox_uniforms", "mdqt_device_ptr",
     "mdqt_device_ld", "mdqt_stream", "mdqt_mark_wrapped", "mdqt_force_plan", "mdqt_enable_timing",
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
-    "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms",
+    "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
+    "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations",
 ]
 
 _lib = None
@@ -102,6 +103,11 @@ def load_library():
     L.mdqt_tag_particles.argtypes = [vp, vp, vp]
     L.mdqt_vaf.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_forced_tag_uniforms.argtypes = [vp, vp]
+    L.mdqt_pair_correlation.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, vp, vp]
+    L.mdqt_vstore_begin.argtypes = [vp, ctypes.c_int]
+    L.mdqt_vstore_record.argtypes = [vp, ctypes.c_int]
+    L.mdqt_vstore_upload.argtypes = [vp, vp]
+    L.mdqt_autocorrelations.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp]
     _lib = L
     return L
 
@@ -320,6 +326,33 @@ class Engine:
         v = np.empty(self.B)
         self._ck(self.lib.mdqt_vaf(self.h, 1 if c1V == 0 else 0, v.ctypes.data_as(c_double_p)))
         return v if self.B > 1 else float(v[0])
+
+    def recordPairPairCorr(self, pairPairStep=0.05, pairPairMax=None):
+        """recordPairPairCorr() MD:584-652 without the file: returns (r bins, g(r), raw ordered-pair counts)."""
+        rmax = self.params.L / 2 if pairPairMax is None else pairPairMax
+        nb = int(rmax / pairPairStep)
+        g = np.empty(self._lead() + (nb,))
+        cnt = np.zeros(self._lead() + (nb,), dtype=np.uint64)
+        self._ck(self.lib.mdqt_pair_correlation(self.h, pairPairStep, rmax, nb, _ptr(g), ctypes.c_void_p(cnt.ctypes.data)))
+        return np.arange(nb) * pairPairStep, g, cnt
+
+    def vstore_begin(self, T):
+        self._ck(self.lib.mdqt_vstore_begin(self.h, T))
+        self._T = T
+
+    def recordVelsForAutocorrelations(self, tS):
+        """MD:513-520: vStore[:, :, tS] = V."""
+        self._ck(self.lib.mdqt_vstore_record(self.h, tS))
+
+    def vstore_upload(self, v):
+        v = _chk64(v, self._lead() + (3, self.N, self._T))
+        self._ck(self.lib.mdqt_vstore_upload(self.h, _ptr(v)))
+
+    def autocorrelations(self, Gamma):
+        """recordVAF, recordLongViscAutoCorr, recordVCubeAutoCorr, recordVFourthAutoCorr (MD:654-823): [4][T]."""
+        out = [np.empty(self._lead() + (self._T,)) for _ in range(4)]
+        self._ck(self.lib.mdqt_autocorrelations(self.h, Gamma, *[_ptr(o) for o in out]))
+        return out
 
     # ---- test hooks / plumbing ---------------------------------------------------------------------------------
     def set_forced_uniforms(self, u):

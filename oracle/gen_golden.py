@@ -328,6 +328,41 @@ def gen_schemes():
     print("fz408l_driver: N=%d, %d spin-up, VAF %g -> %g" % (n, cnt, vaf0, vaf1))
 
 
+def gen_recorders():
+    """g(r) and the four power autocorrelations of the MD program, by the reference itself.
+    The reference's loops always run over its compile-time N = 4096 and T = 2500 (about a minute per recorder): only
+    the first 48 ions carry non-zero series, the rest are zeros, so the committed fixture stays small."""
+    md = po.RefMD()
+    c = md.consts
+    md.seed(2024)
+    md.init()
+    rng = np.random.default_rng(31)
+    R = rng.uniform(0, c["L"], size=(3, md.N))
+    md.set_state(R=R)
+    r, g, step, rmax = md.pair_correlation()
+    T, n = md.T, 48
+    v = rng.normal(size=(3, n, T)) / np.sqrt(c["Gamma"])
+    # give the series some memory so that the lag dependence is not flat
+    for k in range(1, T):
+        v[:, :, k] = 0.9 * v[:, :, k - 1] + 0.436 * v[:, :, k]
+    md.set_vstore(v)
+    ac = [md.autocorr(w) for w in (1, 2, 3, 4)]
+    np.savez_compressed(os.path.join(OUT, "md_recorders.npz"), R=R, gr_r=r, gr_g=g, pairPairStep=step, pairPairMax=rmax,
+                        v_seed=31, n_series=n, T=T, vaf=ac[0], longvisc=ac[1], vcube=ac[2], vfourth=ac[3],
+                        **{k: c[k] for k in c})
+    print("md_recorders: %d g(r) bins, g max %.3f; VAF[0]=%.6g VAF[100]=%.6g" % (len(r), g.max(), ac[0][0], ac[0][100]))
+
+
+def recorder_series(seed, n, T, Gamma):
+    """The velocity series of the md_recorders fixture (regenerated from the seed instead of storing 2.9 MB)."""
+    rng = np.random.default_rng(seed)
+    rng.uniform(0, 1.0, size=(3, 4096))  # the positions drawn first in gen_recorders (same stream position)
+    v = rng.normal(size=(3, n, T)) / np.sqrt(Gamma)
+    for k in range(1, T):
+        v[:, :, k] = 0.9 * v[:, :, k - 1] + 0.436 * v[:, :, k]
+    return v
+
+
 def seed_stream(ref, seed):
     """srand48(seed) inside the harness process (the reference's drand48 stream is then its own, un-injected)."""
     import ctypes
@@ -340,6 +375,9 @@ if __name__ == "__main__":
     po.build()
     if "--mainloop" in sys.argv:
         gen_su_mainloop()
+        sys.exit(0)
+    if "--recorders" in sys.argv:
+        gen_recorders()
         sys.exit(0)
     if "--schemes" in sys.argv:
         gen_schemes()

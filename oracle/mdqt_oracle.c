@@ -1,6 +1,7 @@
 /* oracle/mdqt_oracle.c -- TEST INFRASTRUCTURE ONLY (see mdqt_oracle.h for scope, pinning and usage rules).
  * Plain scalar C99; build with -ffp-contract=off so that every operation rounds once, like the x86-64
  * reference build. Arrays: R,V,F,A = [3][n] contiguous; psi = [n][S][2] (re,im); S = 12 or 7. */
+#define _GNU_SOURCE /* M_PI under -std=c99 */
 #include "mdqt_oracle.h"
 #include <math.h>
 #include <string.h>
@@ -518,4 +519,54 @@ double orc_vaf(int n, const double* Vhold, const double* Vx) { /* FZ408L:955-960
   double vaf = 0.0;
   for (int j = 0; j < n; j++) vaf += 1 / ((double)(n)) * (Vhold[j] * Vx[j]);
   return vaf;
+}
+
+/* recordPairPairCorr (MD:584-652): counts[nbins] of ordered pairs, then the reference's normalisation (with its
+ * integer sub-expressions N*4/3 and N*3). nbins = (int)(rmax/step). */
+void orc_pair_correlation(int n, const double* R, double L, double step, double rmax, double* counts, double* g) {
+  const int nbins = (int)(rmax / step);
+  const double* X = R; const double* Y = R + n; const double* Z = R + 2 * n;
+  for (int k = 0; k < nbins; k++) counts[k] = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      if (j == i) continue;
+      double xd = X[i] - X[j], yd = Y[i] - Y[j], zd = Z[i] - Z[j];
+      xd -= L * round(xd / L); yd -= L * round(yd / L); zd -= L * round(zd / L);
+      double dist = sqrt(xd * xd + yd * yd + zd * zd);
+      int bin = (int)floor((int)(dist / step));
+      if (bin < nbins) counts[bin]++;
+    }
+  if (g)
+    for (int i = 0; i < nbins; i++)
+      g[i] = (i == 0) ? counts[i] / (n * 4 / 3 * M_PI * step * step * step) : counts[i] / (n * 3 * step * step * step * i * i);
+}
+
+/* recordVAF / recordLongViscAutoCorr / recordVCubeAutoCorr / recordVFourthAutoCorr (MD:654-823) on vStore[3][n][T];
+ * nnorm = the N used in the normalisation (the reference's compile-time N; series beyond n are taken as zero).
+ * which: 1 VAF, 2 long. viscosity, 3 v^3, 4 v^4. */
+void orc_autocorr(int which, int n, int nnorm, int T, const double* vstore, double Gamma, double* out) {
+  for (int tDiff = 0; tDiff < T; tDiff++) {
+    double sum = 0;
+    /* all-zero series beyond n contribute only the subtracted constant: added in closed form (test speed) */
+    if (which == 2) sum += (double)(nnorm - n) * (T - tDiff) * (0.0 - 3 / (Gamma * Gamma));
+    if (which == 4) sum += (double)(nnorm - n) * (T - tDiff) * (0.0 - 3 * 9 / (Gamma * Gamma * Gamma * Gamma));
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < T - tDiff; j++) {
+        double a[3], b[3];
+        for (int c = 0; c < 3; c++) {
+          a[c] = vstore[((size_t)c * n + i) * T + j];
+          b[c] = vstore[((size_t)c * n + i) * T + j + tDiff];
+        }
+        if (which == 1) sum += a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+        else if (which == 2)
+          sum += pow(a[0], 2) * pow(b[0], 2) + pow(a[1], 2) * pow(b[1], 2) + pow(a[2], 2) * pow(b[2], 2) - 3 / (Gamma * Gamma);
+        else if (which == 3)
+          sum += pow(a[0], 2) * pow(b[0], 2) * a[0] * b[0] + pow(a[1], 2) * pow(b[1], 2) * a[1] * b[1] +
+                 pow(a[2], 2) * pow(b[2], 2) * a[2] * b[2];
+        else
+          sum += pow(a[0], 2) * pow(b[0], 2) * pow(a[0], 2) * pow(b[0], 2) + pow(a[1], 2) * pow(b[1], 2) * pow(a[1], 2) * pow(b[1], 2) +
+                 pow(a[2], 2) * pow(b[2], 2) * pow(a[2], 2) * pow(b[2], 2) - 3 * 9 / (Gamma * Gamma * Gamma * Gamma);
+      }
+    out[tDiff] = sum / (nnorm * (T - tDiff));
+  }
 }

@@ -70,6 +70,9 @@ void orc_lf_drift(int n, double* R, const double* V, const double* F, double L, 
 void orc_lf_kick(int n, double* V, const double* F, double DT);                                 /* FZ408L:358-369 */
 double orc_vaf(int n, const double* Vhold, const double* Vx);                                   /* FZ408L:938-961 */
 
+void orc_pair_correlation(int n, const double* R, double L, double step, double rmax, double* counts, double* g); /* MD:584-652 */
+void orc_autocorr(int which, int n, int nnorm, int T, const double* vstore, double Gamma, double* out);         /* MD:654-823 */
+
 #ifdef __cplusplus
 }
 #endif

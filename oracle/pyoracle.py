@@ -111,6 +111,8 @@ class Oracle:
         L.orc_lf_kick.argtypes = [ctypes.c_int, c_double_p, c_double_p, ctypes.c_double]
         L.orc_vaf.argtypes = [ctypes.c_int, c_double_p, c_double_p]
         L.orc_vaf.restype = ctypes.c_double
+        L.orc_pair_correlation.argtypes = [ctypes.c_int, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_double_p, c_double_p]
+        L.orc_autocorr.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_double, c_double_p]
         L.orc_uniforms5.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p]
         L.orc_collision_draws.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64, c_double_p, c_double_p]
 
@@ -218,6 +220,20 @@ class Oracle:
             F = self.forces_su(R, L, lDeb)
         self.lib.orc_lf_drift(n, _dp(R), _dp(V), _dp(F), L, 0.5 * dt, 1 if first else 0)
         return F
+
+    def pair_correlation(self, R, L, step, rmax):
+        """recordPairPairCorr (MD:584-652): (raw ordered-pair counts, normalised g)."""
+        nb = int(rmax / step)
+        counts, g = np.zeros(nb), np.zeros(nb)
+        self.lib.orc_pair_correlation(R.shape[1], _dp(R), L, step, rmax, _dp(counts), _dp(g))
+        return counts, g
+
+    def autocorr(self, which, vstore, Gamma, nnorm=None):
+        """MD:654-823 on vstore[3][n][T]; nnorm = N of the normalisation (series beyond n count as zeros)."""
+        _, n, T = vstore.shape
+        out = np.empty(T)
+        self.lib.orc_autocorr(which, n, n if nnorm is None else nnorm, T, _dp(np.ascontiguousarray(vstore)), Gamma, _dp(out))
+        return out
 
     def vaf(self, Vhold, Vx):
         return self.lib.orc_vaf(Vx.shape[0], _dp(np.ascontiguousarray(Vhold)), _dp(np.ascontiguousarray(Vx)))
@@ -383,6 +399,31 @@ class RefMD:
 
     def accelerations(self):
         self.lib.ref_md_accelerations()
+
+    def pair_correlation(self, scratch="/tmp/mdqt_ref_scratch_md/"):
+        """recordPairPairCorr() through its output file (values carry the 6 significant digits of %lg)."""
+        self.lib.ref_md_pair_correlation.argtypes = [ctypes.c_char_p, c_double_p, c_double_p, ctypes.c_int]
+        self.lib.ref_md_pair_step.restype = ctypes.c_double
+        self.lib.ref_md_pair_max.restype = ctypes.c_double
+        r, g = np.zeros(4096), np.zeros(4096)
+        k = self.lib.ref_md_pair_correlation(scratch.encode(), _dp(r), _dp(g), 4096)
+        assert k > 0
+        return r[:k].copy(), g[:k].copy(), self.lib.ref_md_pair_step(), self.lib.ref_md_pair_max()
+
+    @property
+    def T(self):
+        return self.lib.ref_md_autocorr_steps()
+
+    def set_vstore(self, v):
+        """vStore[3][N][T]: the first v.shape[1] ions from v, zeros beyond."""
+        self.lib.ref_md_set_vstore.argtypes = [ctypes.c_int, c_double_p]
+        self.lib.ref_md_set_vstore(v.shape[1], _dp(np.ascontiguousarray(v)))
+
+    def autocorr(self, which, scratch="/tmp/mdqt_ref_scratch_md/"):
+        self.lib.ref_md_autocorr.argtypes = [ctypes.c_int, ctypes.c_char_p, c_double_p]
+        out = np.empty(self.T)
+        self.lib.ref_md_autocorr(which, scratch.encode(), _dp(out))
+        return out
 
     def mdstep(self):
         self.lib.ref_md_mdstep()

@@ -49,4 +49,40 @@ void ref_md_get_state(double* R_, double* V_, double* A_) {
 void ref_md_accelerations() { calculateAccelerations(0); }
 void ref_md_step_positions() { stepPositions(); }
 void ref_md_mdstep() { MDStep(0); }
+// recordPairPairCorr(stepNum) (MD:584-652) writes <saveDirectory>pairPairCorrStepNum<k>.dat: run it into `scratch`
+// (must end with '/') and read the two columns back; returns the number of rows
+int ref_md_pair_correlation(const char* scratch, double* r_out, double* g_out, int cap) {
+  ::mkdir(scratch, 0777);
+  strcpy(saveDirectory, scratch);
+  recordPairPairCorr(7);
+  char fn[512];
+  snprintf(fn, sizeof fn, "%spairPairCorrStepNum7.dat", scratch);
+  FILE* f = fopen(fn, "r");
+  if (!f) return -1;
+  int k = 0;
+  while (k < cap && fscanf(f, "%lg %lg", &r_out[k], &g_out[k]) == 2) k++;
+  fclose(f);
+  return k;
+}
+int ref_md_autocorr_steps() { return numVelAutoCorrsSteps; }
+double ref_md_pair_step() { return pairPairStep; }
+double ref_md_pair_max() { return pairPairMax; }
+// vStore[c][i][:] = v[c][i][:] for i < n, zero beyond (MD:121)
+void ref_md_set_vstore(int n, const double* v) {
+  const int T = numVelAutoCorrsSteps;
+  for (int c = 0; c < 3; c++)
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < T; j++) vStore[c][i][j] = (i < n) ? v[((size_t)c * n + i) * T + j] : 0.0;
+}
+// which: 1 recordVAF, 2 recordLongViscAutoCorr, 3 recordVCubeAutoCorr, 4 recordVFourthAutoCorr (MD:654-823); the files go to scratch
+void ref_md_autocorr(int which, const char* scratch, double* out) {
+  ::mkdir(scratch, 0777);
+  strcpy(saveDirectory, scratch);
+  const double* src = 0;
+  if (which == 1) { recordVAF(); src = VAF; }
+  else if (which == 2) { recordLongViscAutoCorr(); src = longViscAutoCorr; }
+  else if (which == 3) { recordVCubeAutoCorr(); src = vCubeAutoCorr; }
+  else { recordVFourthAutoCorr(); src = vFourthAutoCorr; }
+  for (int j = 0; j < numVelAutoCorrsSteps; j++) out[j] = src[j];
+}
 }

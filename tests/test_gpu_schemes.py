@@ -148,3 +148,54 @@ def test_fz_pump_window_qstep7_matches_oracle(oracle):
     for k in range(6):
         oracle.qstep7(psi_o, V[0].copy(), qp, u5[k])
     assert np.abs(eng.download(("psi",))["psi"] - psi_o).max() <= AMP_TOL
+
+
+def test_pair_correlation_counts_exact(golden_dir, oracle):
+    """g(r): the device histogram equals the restatement's integer counts bin by bin, and the reference's file."""
+    g = np.load(os.path.join(golden_dir, "md_recorders.npz"))
+    n = g["R"].shape[1]
+    p = md_params(scheme=SCHEME_NONE, n_ions=n, kappa=float(g["kappa"]), density=float(g["n"]), timeStep=float(g["timeStep"]))
+    assert p.L == float(g["L"])
+    eng = Engine(p)
+    eng.upload(R=g["R"], V=np.zeros((3, n)))
+    r, gr, cnt = eng.recordPairPairCorr(float(g["pairPairStep"]), float(g["pairPairMax"]))
+    counts_o, gr_o = oracle.pair_correlation(np.ascontiguousarray(g["R"]), p.L, float(g["pairPairStep"]), float(g["pairPairMax"]))
+    assert np.array_equal(cnt.astype(np.float64), counts_o)
+    assert np.array_equal(gr, gr_o)
+    assert np.allclose(gr, g["gr_g"], rtol=6e-6, atol=0)
+    # ragged / tiny systems
+    for m in (1, 2, 300):
+        pm = md_params(scheme=SCHEME_NONE, n_ions=m)
+        e2 = Engine(pm)
+        Rm = np.ascontiguousarray(g["R"][:, :m]) * (pm.L / p.L)
+        e2.upload(R=Rm, V=np.zeros((3, m)))
+        _, _, c2 = e2.recordPairPairCorr(0.05, pm.L / 2)
+        c_o, _ = oracle.pair_correlation(Rm, pm.L, 0.05, pm.L / 2)
+        assert np.array_equal(c2.astype(np.float64), c_o)
+
+
+def test_autocorrelations_golden(golden_dir, oracle):
+    from oracle.gen_golden import recorder_series
+    g = np.load(os.path.join(golden_dir, "md_recorders.npz"))
+    T, n, Gamma = int(g["T"]), int(g["n_series"]), float(g["Gamma"])
+    v = recorder_series(int(g["v_seed"]), n, T, Gamma)
+    p = md_params(scheme=SCHEME_NONE, n_ions=n)
+    eng = Engine(p)
+    eng.vstore_begin(T)
+    eng.vstore_upload(v)
+    out = eng.autocorrelations(Gamma)
+    sub = (0.0, 3 / Gamma ** 2, 0.0, 27 / Gamma ** 4)
+    for k, key in enumerate(("vaf", "longvisc", "vcube", "vfourth")):
+        # the fixture was produced with N = 4096 in the normalisation and zeros beyond the first n ions
+        mine = (out[k] + sub[k]) * n / 4096 - sub[k]
+        scale = np.abs(g[key] + sub[k]).max() + sub[k]
+        assert np.abs(mine - g[key]).max() <= 1e-12 * scale, key
+    # recordVelsForAutocorrelations writes the current velocities into one time slot
+    eng2 = Engine(md_params(scheme=SCHEME_NONE, n_ions=n))
+    eng2.vstore_begin(4)
+    for tS in range(4):
+        eng2.upload(R=np.zeros((3, n)), V=np.ascontiguousarray(v[:, :, tS]))
+        eng2.recordVelsForAutocorrelations(tS)
+    o2 = eng2.autocorrelations(Gamma)
+    ref = oracle.autocorr(1, np.ascontiguousarray(v[:, :, :4]), Gamma)
+    assert np.abs(o2[0] - ref).max() <= 1e-13 * np.abs(ref).max()

@@ -153,3 +153,22 @@ def test_fz_qstep_measure_and_vaf(oracle):
     V2 = V * 0.9 + 0.01
     fz.set_state(V=V2, n=n)
     assert fz.zfunc(1) == oracle.vaf(V[0], V2[0])
+
+
+@pytest.mark.skipif(not po.ref_available("md"), reason="oracle/_ref/libref_md.so not built")
+def test_pair_correlation_matches_reference_file(oracle):
+    """recordPairPairCorr() (MD:584-652) through its output file: every bin to the file's 6 digits, and the integer
+    pair counts recovered from the file equal the restatement's."""
+    md = po.RefMD()
+    c = md.consts
+    rng = np.random.default_rng(77)
+    R = rng.uniform(0, c["L"], size=(3, md.N))
+    md.set_state(R=R)
+    r, g, step, rmax = md.pair_correlation()
+    counts, gr = oracle.pair_correlation(R, c["L"], step, rmax)
+    assert len(g) == len(gr)
+    assert np.allclose(gr, g, rtol=6e-6, atol=0)
+    norm = np.where(np.arange(len(g)) == 0, md.N * 4 // 3 * np.pi * step ** 3, md.N * 3 * step ** 3 * np.arange(len(g)) ** 2.0)
+    rec = g * norm
+    big = counts > 0
+    assert np.abs(rec[big] - counts[big]).max() <= 6e-6 * counts.max()
