@@ -189,7 +189,11 @@ def test_autocorrelations_golden(golden_dir, oracle):
         # the fixture was produced with N = 4096 in the normalisation and zeros beyond the first n ions
         mine = (out[k] + sub[k]) * n / 4096 - sub[k]
         scale = np.abs(g[key] + sub[k]).max() + sub[k]
-        assert np.abs(mine - g[key]).max() <= 1e-12 * scale, key
+        # p = 2 and 4: the reference adds the constant -3/Gamma^2 (-27/Gamma^4) ten million times to one running sum
+        # (MD:710, 785); that naive summation leaves ~1e-10 of biased rounding in ITS result (the fixture), the device
+        # subtracts the constant once. The unbiased p = 1, 3 sums agree to 1e-12.
+        tol = 1e-12 if k in (0, 2) else 1e-9
+        assert np.abs(mine - g[key]).max() <= tol * scale, key
     # recordVelsForAutocorrelations writes the current velocities into one time slot
     eng2 = Engine(md_params(scheme=SCHEME_NONE, n_ions=n))
     eng2.vstore_begin(4)
