@@ -158,26 +158,28 @@ static void plan_force(mdqt_handle* h) {
     h->jsub = (ipt == 1 && tiles1 * h->nsplit < 148LL * 7) ? 2 : 1;
   }
   h->rg = kForceThreads;
-  // Small systems (the CTAs of the plan above do not fill every SM seven times over): compare that plan with 32-row
-  // groups, whose rows are split over 4x fewer CTAs. Model from the per-CTA phase trace on B200 (profiles/): time =
-  // (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue cycles / 4 sub-partitions + 2.8 us of CTA
-  // prologue/epilogue + one L2 round trip (~0.9 us) per 8 partial sums in the final cross-CTA reduction.
-  if (h->jsub == 2 && !getenv("MDQT_FORCE_IPT") && !getenv("MDQT_FORCE_NSPLIT")) {
+  // Small and medium systems (one row per thread in the plan above): compare that plan with 32-row groups whose j range
+  // is split over 4 or 8 warps INSIDE the CTA, so a row's force is spread over 4-8x fewer CTAs (often over one: no partial
+  // sums, no arrival counter, no final reduction at all). Model from the per-CTA phase trace and the plan timings on
+  // B200 (profiles/README.md): time = (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue cycles / 4
+  // sub-partitions + CTA prologue/epilogue (2.8 us exposed in a single wave, about half of it hidden with several
+  // waves) + one L2 round trip (~0.9 us) per 8 partial sums in the final cross-CTA reduction.
+  if (h->ipt == 1 && !getenv("MDQT_FORCE_IPT") && !getenv("MDQT_FORCE_NSPLIT")) {
     auto model = [&](long long ctas, int warps, double pairs_per_warp, int ns) {
       const double per_sm = (double)((ctas + 147) / 148);
-      const double starve = per_sm * warps >= 24.0 ? 1.0 : 24.0 / (per_sm * warps);  // < 6 warps per sub-partition
-      return per_sm * warps * pairs_per_warp * 81.0 / (4 * 1965.0) * starve + 2.8 + (ns > 1 ? 0.5 + 0.9 * ((ns + 7) / 8) : 0.0);
+      const double resident = std::min(per_sm * warps, 32.0);
+      const double starve = resident >= 24.0 ? 1.0 : 24.0 / resident;  // < 6 warps per sub-partition
+      const double fixed = per_sm * warps > 32.0 ? 1.4 : 2.8;
+      return per_sm * warps * pairs_per_warp * 81.0 / (4 * 1965.0) * starve + fixed + (ns > 1 ? 0.5 + 0.9 * ((ns + 7) / 8) : 0.0);
     };
     const long long tiles128 = ((long long)N + 127) / 128 * B, tiles32 = ((long long)N + 31) / 32 * B;
-    double best_t = model(tiles128 * h->nsplit, 8, h->jlen / 2.0, h->nsplit);
+    double best_t = model(tiles128 * h->nsplit, 4 * h->jsub, (double)h->jlen / h->jsub, h->nsplit);
     for (int js = 8; js >= 4; js /= 2)
       for (int ns = 1; ns <= 16; ns++) {
         const int jlen = ((N + ns - 1) / ns + 7) & ~7;
         const int real_ns = (N + jlen - 1) / jlen;
         if (real_ns != ns) continue;
-        const long long ctas = tiles32 * ns;
-        if ((ctas + 147) / 148 * js > 32) continue;  // keep every CTA resident (64 registers x 1024 threads per SM)
-        const double t = model(ctas, js, (double)jlen / js, ns);
+        const double t = model(tiles32 * ns, js, (double)jlen / js, ns);
         if (t < best_t * 0.98) { best_t = t; h->rg = 32; h->jsub = js; h->nsplit = ns; h->jlen = jlen; h->ipt = 1; }
       }
   }
