@@ -271,7 +271,13 @@ def run_ours(args):
         b_.record(ls)
         el.sync(); torch.cuda.synchronize(); barrier()
         ms = max_over_ranks(a.elapsed_time(b_)) / nl
-        extras["large_n"] = {"n_ions": NL, "scaling": "strong", "rows_per_gpu": rows, "ms_per_md_step": ms,
+        # output() observables of the row-decomposed run (outside the timed region): partial sums + two small all-reduces
+        obs = None
+        if world > 1:
+            with torch.cuda.device(local):
+                dd = sharding.distributed_diagnostics(el, NL, dist)
+            obs = {"epot_per_ion": float(dd["epot"]), "ekin_x": float(dd["ekin_x"]), "collective": "2 x ncclAllReduce of 5 fp64"}
+        extras["large_n"] = {"n_ions": NL, "scaling": "strong", "rows_per_gpu": rows, "ms_per_md_step": ms, "observables": obs,
                              "pair_interactions_per_s": float(NL) * NL / (ms * 1e-3),
                              "ion_steps_per_s": float(NL) * 25 / (ms * 1e-3),
                              "fp64_frac": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (fp64_peak * world),

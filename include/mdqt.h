@@ -118,6 +118,13 @@ int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out);
 int mdqt_vel_dist(mdqt_handle* h, double* pvel);
 int mdqt_populations(mdqt_handle* h, double* pops);
 
+/* Row-decomposed runs (n_rows < n_ions): the observables of output() as partial sums over the handle's own rows, to be
+ * completed by an all-reduce (SUM) over the ranks. sums = double [n_traj][5]: sum v_x, sum (v_x - mean)^2/2, sum v_y^2/2,
+ * sum v_z^2/2 (none divided by N) and the handle's share of Epotential() (already divided by N). vx_mean = double
+ * [n_traj] or NULL (0): call once with NULL, all-reduce sums[0]/N into the mean, call again. pvel as mdqt_vel_dist. */
+int mdqt_diag_partial(mdqt_handle* h, const double* vx_mean, double* sums);
+int mdqt_vel_dist_partial(mdqt_handle* h, const double* vx_mean, double* pvel);
+
 /* MD family: MDStep() (MD:504-511) = stepPositions, calculateAccelerations, stepVelocities with Andersen
  * collisions (probability dt*collisionFreq, velocities ~ N(0, sigma_v^2)) and the optional laser friction term
  * (laser: 0 none, 1 three-axis MD:494-496, 2 x only MD:491; coefficient = 1.234e-6*beta/sqrt(n)). */

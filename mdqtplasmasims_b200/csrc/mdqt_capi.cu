@@ -511,6 +511,7 @@ int mdqt_epot(mdqt_handle* h, double* epot) {
 
 int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
   if (!h || !out) return fail(MDQT_EINVAL, "null argument");
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_diag_partial and all-reduce the sums");
   CU(cudaSetDevice(h->p.device));
   refresh_fixed(h);
   launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
@@ -526,8 +527,44 @@ int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
   return MDQT_OK;
 }
 
+int mdqt_diag_partial(mdqt_handle* h, const double* vx_mean, double* sums) {
+  if (!h || !sums) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  refresh_fixed(h);
+  double* mean_dev = nullptr;
+  if (vx_mean) {
+    mean_dev = h->scalars + (size_t)h->B * 12;  // scratch behind the [B][8] sums and the [B] potential energies
+    CU(cudaMemcpyAsync(mean_dev, vx_mean, (size_t)h->B * 8, cudaMemcpyHostToDevice, h->stream));
+  }
+  launch_diag_partial(h->V, h->row0, h->nrows, h->ld, h->B, mean_dev, h->scalars, h->stream);
+  launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);  // owned rows x all j, already / N
+  std::vector<double> s((size_t)h->B * 9);
+  CU(cudaMemcpyAsync(s.data(), h->scalars, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  for (int b = 0; b < h->B; b++) {
+    for (int k = 0; k < 4; k++) sums[b * 5 + k] = s[b * 8 + k];
+    sums[b * 5 + 4] = s[(size_t)h->B * 8 + b];
+  }
+  return MDQT_OK;
+}
+
+int mdqt_vel_dist_partial(mdqt_handle* h, const double* vx_mean, double* pvel) {
+  if (!h || !pvel || !vx_mean) return fail(MDQT_EINVAL, "null argument");
+  CU(cudaSetDevice(h->p.device));
+  std::vector<double> m((size_t)h->B * 8, 0.0);
+  for (int b = 0; b < h->B; b++) m[(size_t)b * 8] = vx_mean[b];
+  CU(cudaMemcpyAsync(h->scalars, m.data(), m.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  launch_vel_dist_rows(h->V, h->scalars, h->row0, h->nrows, h->ld, h->B, h->pvel, h->stream);
+  CU(cudaMemcpyAsync(pvel, h->pvel, (size_t)h->B * 3 * kVelBins * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
 int mdqt_vel_dist(mdqt_handle* h, double* pvel) {
   if (!h || !pvel) return fail(MDQT_EINVAL, "null argument");
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_vel_dist_partial and all-reduce the bins");
   CU(cudaSetDevice(h->p.device));
   launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
   launch_vel_dist(h->V, h->scalars, h->N, h->ld, h->B, h->pvel, h->stream);

@@ -55,13 +55,36 @@ void launch_diag(const double* V, int N, int ld, int B, double*, double* diag_ou
   k_diag<<<B, 1024, 0, s>>>(V, N, ld, diag_out);
 }
 
-// grid: (ceil(2001/8), 3, B); 256 threads = 8 bins x 32 lanes; lanes stride over ions
+// Row-decomposed runs: every rank owns the velocities of its rows only, so output() needs partial sums that
+// an all-reduce completes. out[b][0..3] = sum vx, sum (vx - mean)^2/2, sum vy^2/2, sum vz^2/2 over rows [row0,row0+nrows),
+// NOT normalised; mean[b] comes from the caller (the all-reduced sum vx / N of a first call with mean = 0).
+__global__ void __launch_bounds__(1024) k_diag_partial(const double* __restrict__ V, int row0, int nrows, int ld,
+                                                       const double* __restrict__ mean, double* __restrict__ out) {
+  __shared__ double sred[32];
+  const int b = blockIdx.x;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const double* vy = vx + ld;
+  const double* vz = vy + ld;
+  const double avg = mean ? mean[b] : 0.0;
+  double s = 0.0, ex = 0.0, ey = 0.0, ez = 0.0;
+  for (int i = row0 + threadIdx.x; i < row0 + nrows; i += blockDim.x) {
+    const double d = vx[i] - avg;
+    s += vx[i]; ex += 0.5 * (d * d); ey += 0.5 * (vy[i] * vy[i]); ez += 0.5 * (vz[i] * vz[i]);
+  }
+  s = block_sum_1024(s, sred); ex = block_sum_1024(ex, sred); ey = block_sum_1024(ey, sred); ez = block_sum_1024(ez, sred);
+  if (threadIdx.x == 0) { out[b * 8 + 0] = s; out[b * 8 + 1] = ex; out[b * 8 + 2] = ey; out[b * 8 + 3] = ez; }
+}
+void launch_diag_partial(const double* V, int row0, int nrows, int ld, int B, const double* mean, double* out, cudaStream_t s) {
+  k_diag_partial<<<B, 1024, 0, s>>>(V, row0, nrows, ld, mean, out);
+}
+
+// grid: (ceil(2001/8), 3, B); 256 threads = 8 bins x 32 lanes; lanes stride over ions [row0, row0 + nrows)
 __global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, const double* __restrict__ diag, int N, int ld,
-                                                  double* __restrict__ pvel) {
+                                                  double* __restrict__ pvel, int row0 = 0) {
   const int b = blockIdx.z, c = blockIdx.y;
   const int bin = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  const double* v = V + ((size_t)b * 3 + c) * ld;
+  const double* v = V + ((size_t)b * 3 + c) * ld + row0;
   const double avg = (c == 0) ? diag[b * 8] : 0.0;
   const double V2 = 1. / (2. * 0.002 * 0.002);
   const double vb = (double)bin * 0.0025;
@@ -80,6 +103,11 @@ __global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, 
 void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s) {
   dim3 grid((kVelBins + 7) / 8, 3, B);
   k_vel_dist<<<grid, 256, 0, s>>>(V, diag_out, N, ld, pvel);
+}
+// the same KDE restricted to rows [row0,row0+nrows) about an externally supplied <v_x> (diag[b*8]): additive over ranks
+void launch_vel_dist_rows(const double* V, const double* diag, int row0, int nrows, int ld, int B, double* pvel, cudaStream_t s) {
+  dim3 grid((kVelBins + 7) / 8, 3, B);
+  k_vel_dist<<<grid, 256, 0, s>>>(V, diag, nrows, ld, pvel, row0);
 }
 
 // Zfunc() (FZ408L:938-961): out[b] = sum_j (1/N) Vhold_x[j] V_x[j], fixed-order block reduction; one CTA per trajectory

@@ -88,6 +88,8 @@ void launch_vv_velocities(const VVArgs& a, cudaStream_t s);
 // diag_out[B][8]: vx_avg, ekin_x, ekin_y, ekin_z; pvel[B][3][2001]; pops[B][N][3]
 void launch_diag(const double* V, int N, int ld, int B, double* scratch, double* diag_out, cudaStream_t s);
 void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s);
+void launch_diag_partial(const double* V, int row0, int nrows, int ld, int B, const double* mean, double* out, cudaStream_t s);
+void launch_vel_dist_rows(const double* V, const double* diag, int row0, int nrows, int ld, int B, double* pvel, cudaStream_t s);
 void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s);
 // projective spin measurement after the pump (tagParticles MC408L:1022-1067 / MC422L:992-1036; measureSpinUps
 // FZ408L:600-647): tagged[B][N] (0/1), count[B]; u = forced uniforms [N][2] or null (Philox call 6)

@@ -46,7 +46,7 @@ ABI_SYMBOLS = [
     "mdqt_device_ld", "mdqt_stream", "mdqt_mark_wrapped", "mdqt_force_plan", "mdqt_enable_timing",
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
-    "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations",
+    "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
 ]
 
 _lib = None
@@ -108,6 +108,8 @@ def load_library():
     L.mdqt_vstore_record.argtypes = [vp, ctypes.c_int]
     L.mdqt_vstore_upload.argtypes = [vp, vp]
     L.mdqt_autocorrelations.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp]
+    L.mdqt_diag_partial.argtypes = [vp, vp, vp]
+    L.mdqt_vel_dist_partial.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -281,6 +283,20 @@ class Engine:
         self._ck(self.lib.mdqt_diagnostics(self.h, d))
         out = [{k: getattr(x, k) for k, _ in Diag._fields_} for x in d]
         return out if self.B > 1 else out[0]
+
+    def diag_partial(self, vx_mean=None):
+        """Partial sums of output()'s observables over this handle's rows: [sum vx, sum (vx-mean)^2/2, sum vy^2/2,
+        sum vz^2/2, Epot share] per trajectory (row-decomposed runs; all-reduce over the ranks completes them)."""
+        s = np.empty((self.B, 5))
+        m = None if vx_mean is None else np.ascontiguousarray(np.broadcast_to(np.asarray(vx_mean, dtype=np.float64), (self.B,)))
+        self._ck(self.lib.mdqt_diag_partial(self.h, _ptr(m), _ptr(s)))
+        return s if self.B > 1 else s[0]
+
+    def vel_dist_partial(self, vx_mean):
+        p = np.empty(self._lead() + (3, 2001))
+        m = np.ascontiguousarray(np.broadcast_to(np.asarray(vx_mean, dtype=np.float64), (self.B,)))
+        self._ck(self.lib.mdqt_vel_dist_partial(self.h, _ptr(m), _ptr(p)))
+        return p
 
     def vel_dist(self):
         p = np.empty(self._lead() + (3, 2001))

@@ -47,9 +47,27 @@ def allgather_positions(R, n_ions, world, rank, dist):
     return R
 
 
-def allreduce_scalars(values, dist):
-    """Sum of per-rank partial observables (E_pot partial sums, kinetic sums, KDE bins) on output steps."""
+def allreduce_scalars(values, dist, device=None):
+    """Sum of per-rank partial observables (E_pot partial sums, kinetic sums, KDE bins) on output steps.
+    NCCL needs device tensors: with that backend the values travel through the current CUDA device."""
     import torch
     t = torch.as_tensor(np.asarray(values, dtype=np.float64))
+    if device is None and dist.get_backend() == "nccl":
+        device = torch.device("cuda", torch.cuda.current_device())
+    if device is not None:
+        t = t.to(device)
     dist.all_reduce(t)
-    return t.numpy()
+    return t.cpu().numpy()
+
+
+def distributed_diagnostics(engine, n_ions, dist, want_vel_dist=False):
+    """output()'s observables (SU:934-979) of a row-decomposed run: two small all-reduces on output steps only.
+
+    ``engine`` owns rows [row0,row0+n_rows) of one trajectory; returns the same dict on every rank."""
+    s0 = allreduce_scalars(engine.diag_partial(None), dist)       # sum v_x (the energy slots of this call are unused)
+    mean = s0[0] / n_ions
+    s1 = allreduce_scalars(engine.diag_partial(mean), dist)
+    out = {"vx_avg": mean, "ekin_x": s1[1] / n_ions, "ekin_y": s1[2] / n_ions, "ekin_z": s1[3] / n_ions, "epot": s1[4]}
+    if want_vel_dist:
+        out["pvel"] = allreduce_scalars(engine.vel_dist_partial(mean), dist)
+    return out

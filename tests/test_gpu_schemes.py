@@ -203,3 +203,34 @@ def test_autocorrelations_golden(golden_dir, oracle):
     o2 = eng2.autocorrelations(Gamma)
     ref = oracle.autocorr(1, np.ascontiguousarray(v[:, :, :4]), Gamma)
     assert np.abs(o2[0] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def test_row_decomposed_diagnostics_sum_to_the_full_ones():
+    """on output() steps a row-decomposed run all-reduces partial sums. Four row-owning handles on one GPU
+    play the ranks; their partial sums (added in rank order = what a SUM all-reduce delivers) equal the full handle's."""
+    from mdqtplasmasims_b200 import synthetic
+    n, G = 1024, 4
+    p = su_params(n_ions=n, N0=n)
+    R = synthetic.random_positions(n, p.L, seed=9)
+    V = synthetic.maxwellian(n, 0.2, seed=9)
+    psi = synthetic.random_s_state(n, 12, seed=9)
+    full = Engine(p)
+    full.upload(R=R, V=V, psi=psi, tPart=np.zeros(n))
+    d = full.diagnostics()
+    pv = full.vel_dist()
+    parts = []
+    for g in range(G):
+        e = Engine(su_params(n_ions=n, N0=n, row0=g * n // G, n_rows=n // G))
+        e.upload(R=R, V=V, psi=psi, tPart=np.zeros(n))
+        with pytest.raises(Exception):
+            e.diagnostics()  # a row-decomposed handle refuses the whole-system call
+        parts.append(e)
+    s0 = sum(e.diag_partial(None) for e in parts)
+    mean = s0[0] / n
+    s1 = sum(e.diag_partial(mean) for e in parts)
+    assert abs(mean - d["vx_avg"]) <= 1e-15
+    for k, key in ((1, "ekin_x"), (2, "ekin_y"), (3, "ekin_z")):
+        assert abs(s1[k] / n - d[key]) <= 1e-14 * d[key]
+    assert abs(s1[4] - d["epot"]) <= 1e-12 * d["epot"]
+    pvp = sum(e.vel_dist_partial(mean) for e in parts)
+    assert np.abs(pvp - pv).max() <= 1e-11 * pv.max()

@@ -58,6 +58,21 @@ def _worker(rank, world, port, n, out_dir):
     ekin_part = float((Rg[:, row0:row0 + rows] ** 2).sum())
     tot = sharding.allreduce_scalars([ekin_part, rows], dist)
     assert abs(tot[0] - (Rg ** 2).sum()) < 1e-9 * (Rg ** 2).sum() and tot[1] == n
+    # output() observables of a row-decomposed run: two small all-reduces (a numpy stand-in plays the engine's partial sums)
+    Vg = np.random.default_rng(7).normal(size=(3, n))
+
+    class _Rows:
+        def diag_partial(self, vx_mean=None):
+            m = 0.0 if vx_mean is None else float(vx_mean)
+            v = Vg[:, row0:row0 + rows]
+            return np.array([v[0].sum(), 0.5 * ((v[0] - m) ** 2).sum(), 0.5 * (v[1] ** 2).sum(), 0.5 * (v[2] ** 2).sum(), rows / n])
+
+        def vel_dist_partial(self, vx_mean):
+            return np.full((3, 2001), float(rows))
+
+    d = sharding.distributed_diagnostics(_Rows(), n, dist, want_vel_dist=True)
+    assert abs(d["vx_avg"] - Vg[0].mean()) < 1e-15 and abs(d["ekin_x"] - 0.5 * ((Vg[0] - Vg[0].mean()) ** 2).mean()) < 1e-14
+    assert abs(d["ekin_y"] - 0.5 * (Vg[1] ** 2).mean()) < 1e-14 and abs(d["epot"] - 1.0) < 1e-15 and (d["pvel"] == n).all()
     jobs = sharding.ensemble_jobs(10, world, rank)
     all_jobs = [None] * world
     dist.all_gather_object(all_jobs, jobs)
