@@ -67,48 +67,50 @@ struct LaneH {
 
 template <int NL>
 __device__ __forceinline__ void apply_M(const LaneH& H, const cplx* w, cplx* m) {
-  // m = w - i h (H w):  m.re = w.re + h (Hw).im ;  m.im = w.im - h (Hw).re
+  // m = w - i h (H w):  m.re = w.re + h Im(Hw) ;  m.im = w.im - h Re(Hw). Every row is ONE fma chain that starts from
+  // the amplitude itself (no separate Hw, no final add): with z = x + i y and a diagonal E - i g,
+  //   m.re = x + hE y - hg x + sum_c hc y_c ,   m.im = y - hE x - hg y - sum_c hc x_c .
   // S
   m[0].re = fma(H.hc10, w[1].im, fma(H.hc20, w[2].im, w[0].re));
   m[0].im = fma(-H.hc10, w[1].re, fma(-H.hc20, w[2].re, w[0].im));
   // P1: (E1 - i g1) w1 + c10 w0 + c13 w3 + c14 w4
   {
-    double hr = fma(H.hE1, w[1].re, H.hg1 * w[1].im);   // h Re
-    double hi = fma(H.hE1, w[1].im, -(H.hg1 * w[1].re));// h Im
-    hr = fma(H.hc10, w[0].re, hr); hi = fma(H.hc10, w[0].im, hi);
+    double re = fma(H.hE1, w[1].im, fma(-H.hg1, w[1].re, w[1].re));
+    double im = fma(-H.hE1, w[1].re, fma(-H.hg1, w[1].im, w[1].im));
+    re = fma(H.hc10, w[0].im, re); im = fma(-H.hc10, w[0].re, im);
     if (NL == 6) {
-      hr = fma(H.hc13, w[3].re, hr); hi = fma(H.hc13, w[3].im, hi);
-      hr = fma(H.hc14, w[4].re, hr); hi = fma(H.hc14, w[4].im, hi);
+      re = fma(H.hc13, w[3].im, re); im = fma(-H.hc13, w[3].re, im);
+      re = fma(H.hc14, w[4].im, re); im = fma(-H.hc14, w[4].re, im);
     }
-    m[1].re = w[1].re + hi; m[1].im = w[1].im - hr;
+    m[1].re = re; m[1].im = im;
   }
-  // P2: (E2 - i g2) w2 + c20 w0 + c25 w5 + conj(rot) w4
+  // P2: (E2 - i g2) w2 + c20 w0 + c25 w5 + conj(rot) w4 ; conj(rot) w4 = (rr x4 + ri y4) + i (rr y4 - ri x4)
   {
-    double hr = fma(H.hE2, w[2].re, H.hg2 * w[2].im);
-    double hi = fma(H.hE2, w[2].im, -(H.hg2 * w[2].re));
-    hr = fma(H.hc20, w[0].re, hr); hi = fma(H.hc20, w[0].im, hi);
+    double re = fma(H.hE2, w[2].im, fma(-H.hg2, w[2].re, w[2].re));
+    double im = fma(-H.hE2, w[2].re, fma(-H.hg2, w[2].im, w[2].im));
+    re = fma(H.hc20, w[0].im, re); im = fma(-H.hc20, w[0].re, im);
     if (NL == 6) {
-      hr = fma(H.hc25, w[5].re, hr); hi = fma(H.hc25, w[5].im, hi);
-      // conj(rot) * w4 = (rr - i ri)(x + i y) = rr x + ri y + i (rr y - ri x)
-      hr = fma(H.hrr, w[4].re, fma(H.hri, w[4].im, hr));
-      hi = fma(H.hrr, w[4].im, fma(-H.hri, w[4].re, hi));
+      re = fma(H.hc25, w[5].im, re); im = fma(-H.hc25, w[5].re, im);
+      re = fma(H.hrr, w[4].im, fma(-H.hri, w[4].re, re));
+      im = fma(-H.hrr, w[4].re, fma(-H.hri, w[4].im, im));
     }
-    m[2].re = w[2].re + hi; m[2].im = w[2].im - hr;
+    m[2].re = re; m[2].im = im;
   }
   if (NL == 6) {
     {  // D(3): E3 w3 + c13 w1
-      double hr = fma(H.hE3, w[3].re, H.hc13 * w[1].re), hi = fma(H.hE3, w[3].im, H.hc13 * w[1].im);
-      m[3].re = w[3].re + hi; m[3].im = w[3].im - hr;
+      m[3].re = fma(H.hE3, w[3].im, fma(H.hc13, w[1].im, w[3].re));
+      m[3].im = fma(-H.hE3, w[3].re, fma(-H.hc13, w[1].re, w[3].im));
     }
-    {  // D(4): E4 w4 + c14 w1 + rot w2 ; rot w2 = (rr + i ri)(x + i y) = rr x - ri y + i (rr y + ri x)
-      double hr = fma(H.hE4, w[4].re, H.hc14 * w[1].re), hi = fma(H.hE4, w[4].im, H.hc14 * w[1].im);
-      hr = fma(H.hrr, w[2].re, fma(-H.hri, w[2].im, hr));
-      hi = fma(H.hrr, w[2].im, fma(H.hri, w[2].re, hi));
-      m[4].re = w[4].re + hi; m[4].im = w[4].im - hr;
+    {  // D(4): E4 w4 + c14 w1 + rot w2 ; rot w2 = (rr x2 - ri y2) + i (rr y2 + ri x2)
+      double re = fma(H.hE4, w[4].im, fma(H.hc14, w[1].im, w[4].re));
+      double im = fma(-H.hE4, w[4].re, fma(-H.hc14, w[1].re, w[4].im));
+      re = fma(H.hrr, w[2].im, fma(H.hri, w[2].re, re));
+      im = fma(-H.hrr, w[2].re, fma(H.hri, w[2].im, im));
+      m[4].re = re; m[4].im = im;
     }
     {  // D(5): E5 w5 + c25 w2
-      double hr = fma(H.hE5, w[5].re, H.hc25 * w[2].re), hi = fma(H.hE5, w[5].im, H.hc25 * w[2].im);
-      m[5].re = w[5].re + hi; m[5].im = w[5].im - hr;
+      m[5].re = fma(H.hE5, w[5].im, fma(H.hc25, w[2].im, w[5].re));
+      m[5].im = fma(-H.hE5, w[5].re, fma(-H.hc25, w[2].re, w[5].im));
     }
   } else {
     m[3] = w[3];  // 7-level D reservoir: zero energy, no coupling
