@@ -161,16 +161,17 @@ static void plan_force(mdqt_handle* h) {
   // Small and medium systems (one row per thread in the plan above): compare that plan with 32-row groups whose j range
   // is split over 4 or 8 warps INSIDE the CTA, so a row's force is spread over 4-8x fewer CTAs (often over one: no partial
   // sums, no arrival counter, no final reduction at all). Model from the per-CTA phase trace and the plan timings on
-  // B200 (profiles/README.md): time = (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue cycles / 4
-  // sub-partitions + CTA prologue/epilogue (2.8 us exposed in a single wave, about half of it hidden with several
-  // waves) + one L2 round trip (~0.9 us) per 8 partial sums in the final cross-CTA reduction.
+  // B200 (profiles/r01c_k1_trace.txt): time = (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue
+  // cycles / 4 sub-partitions + a plan-independent ~5.5 us; what separates plans is almost only the first term, i.e.
+  // how evenly the CTA count divides over 148 SMs (measured launch times move in ~2 us steps).
   if (h->ipt == 1 && !getenv("MDQT_FORCE_IPT") && !getenv("MDQT_FORCE_NSPLIT")) {
     auto model = [&](long long ctas, int warps, double pairs_per_warp, int ns) {
       const double per_sm = (double)((ctas + 147) / 148);
       const double resident = std::min(per_sm * warps, 32.0);
-      const double starve = resident >= 24.0 ? 1.0 : 24.0 / resident;  // < 6 warps per sub-partition
-      const double fixed = per_sm * warps > 32.0 ? 1.4 : 2.8;
-      return per_sm * warps * pairs_per_warp * 81.0 / (4 * 1965.0) * starve + fixed + (ns > 1 ? 0.5 + 0.9 * ((ns + 7) / 8) : 0.0);
+      const double starve = resident >= 16.0 ? 1.0 : 16.0 / resident;  // fewer than 4 warps per sub-partition
+      // + launch gap and CTA prologue/epilogue (~5.5 us whatever the plan), a mild cost per CTA wave, and one L2 round
+      // trip per 8 partial sums in the final reduction
+      return per_sm * warps * pairs_per_warp * 81.0 / (4 * 1965.0) * starve + 5.5 + 0.15 * per_sm + (ns > 1 ? 0.9 * ((ns + 7) / 8) : 0.0);
     };
     const long long tiles128 = ((long long)N + 127) / 128 * B, tiles32 = ((long long)N + 31) / 32 * B;
     double best_t = model(tiles128 * h->nsplit, 4 * h->jsub, (double)h->jlen / h->jsub, h->nsplit);

@@ -131,6 +131,14 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
 
 constexpr int kTJ = 512;  // j positions staged per pass
 
+// 8-byte asynchronous global -> shared copies (LDGSTS): the exp table, the first j tile and the thread's own rows are all
+// in flight together in the CTA prologue (one L2 round trip instead of three), and tiles never pass through registers
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 #ifdef MDQT_K1_TRACE  // developer build: per-CTA phase time stamps (scripts/k1_trace.py)
 __device__ long long g_trace[8 * 8192];
 #define TRACE(slot)                                                                                              \
@@ -153,8 +161,11 @@ __device__ long long g_trace[8 * 8192];
 // Small N wants RG = 32, JS = 8: the same 256-thread CTAs and the same work per warp as RG = 128, JS = 2, but a row's
 // force is split over 4x fewer CTAs, so the final cross-CTA reduction (a chain of dependent L2 loads executed by the
 // last CTA of a tile while the rest of the chip idles) shrinks from 20 partials to 5 at N = 3500.
+#ifndef MDQT_K1_MINB32
+#define MDQT_K1_MINB32 1
+#endif
 template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG>
-__global__ void __launch_bounds__(RG * JS) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
+__global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB32 : 1) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
   constexpr int kForceThreads = RG;  // shadows the namespace constant: rows per group in this instantiation
   __shared__ longlong2 sxy[kTJ];
   __shared__ long long sz[kTJ];
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(RG * JS) k_pairs(ForceArgs a, double* __restri
   const long long* __restrict__ X = a.Rfix + (size_t)b * 3 * a.ld;
   const long long* __restrict__ Y = X + a.ld;
   const long long* __restrict__ Z = Y + a.ld;
-  for (int k = tid; k < kExpTable; k += NT) stab[k] = c_exp2tab[k];
+  for (int k = tid; k < kExpTable; k += NT) cp_async8(&stab[k], &c_exp2tab[k]);
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
 
   int irow[IPT];
@@ -192,9 +203,9 @@ __global__ void __launch_bounds__(RG * JS) k_pairs(ForceArgs a, double* __restri
     __syncthreads();
     for (int k = tid; k < cnt; k += NT) {
       const int j = jc + k;
-      sxy[k] = make_longlong2(X[j], Y[j]);
-      sz[k] = Z[j];
+      cp_async8(&sxy[k].x, X + j); cp_async8(&sxy[k].y, Y + j); cp_async8(&sz[k], Z + j);
     }
+    cp_async_wait_all();  // also covers the exp table on the first pass
     __syncthreads();
     if (jc == jbeg) { TRACE(1) }
     const int lo = (cnt * jh) / JS, hi = (cnt * (jh + 1)) / JS;
