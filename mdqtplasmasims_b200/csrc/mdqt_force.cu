@@ -161,11 +161,17 @@ __device__ long long g_trace[8 * 8192];
 // Small N wants RG = 32, JS = 8: the same 256-thread CTAs and the same work per warp as RG = 128, JS = 2, but a row's
 // force is split over 4x fewer CTAs, so the final cross-CTA reduction (a chain of dependent L2 loads executed by the
 // last CTA of a tile while the rest of the chip idles) shrinks from 20 partials to 5 at N = 3500.
+// Register budget (A/B'd on B200, profiles/r01c_k1_trace.txt): the pair loop likes registers more than resident warps. With an
+// explicit minimum of 4 CTAs/SM the 128-thread large-N kernel may use up to 128 registers (16 warps/SM): 5.20e11 pairs/s at
+// N = 1e5 against 5.03-5.07e11 when capped at 80 or 64 registers (24-32 warps/SM). The 256-thread small-N kernel is best uncapped.
 #ifndef MDQT_K1_MINB32
 #define MDQT_K1_MINB32 1
 #endif
+#ifndef MDQT_K1_MINB128
+#define MDQT_K1_MINB128 4
+#endif
 template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG>
-__global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB32 : 1) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
+__global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB32 : (RG == 128 && JS == 1) ? MDQT_K1_MINB128 : 1) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
   constexpr int kForceThreads = RG;  // shadows the namespace constant: rows per group in this instantiation
   __shared__ longlong2 sxy[kTJ];
   __shared__ long long sz[kTJ];
