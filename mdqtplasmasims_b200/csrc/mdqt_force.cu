@@ -225,7 +225,11 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
         const double dx = __ll2double_rn((long long)((unsigned long long)xi[k] - (unsigned long long)pxy.x));
         const double dy = __ll2double_rn((long long)((unsigned long long)yi[k] - (unsigned long long)pxy.y));
         const double dz = __ll2double_rn((long long)((unsigned long long)zi[k] - (unsigned long long)pz));
-        const double r2 = fma(dx, dx, fma(dy, dy, dz * dz));
+        // Force path: + 1 (one fixed-point unit squared, L^2 2^-128) keeps the self / coincident pair finite -- its
+        // f is then multiplied by dx = dy = dz = 0, contributing exactly 0 like the reference's `dr > 0` test
+        // (SU:222) -- without a separate r2 != 0 predicate; for any physical separation (r > L 2^-37) the 1 is below
+        // the rounding of r2 and changes nothing. The potential-energy path keeps the explicit test.
+        const double r2 = EPOT ? fma(dx, dx, fma(dy, dy, dz * dz)) : fma(dx, dx, fma(dy, dy, fma(dz, dz, 1.0)));
         double rinv, ef;
         bool valid;
         pair_core<HL>(r2, c, stab, rinv, ef, valid);
@@ -235,12 +239,12 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
         } else {
           double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
           // 0 < r2 < rc2 as ONE predicate (DSETP, then ISETP chained with .and) and one select
-          if (HL)
-            asm("{\n\t.reg .pred q;\n\t.reg .u32 t;\n\tadd.u32 t, %1, -1;\n\tsetp.lt.u32 q, t, 0x47CFFFFF;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+          if (HL)  // r2 < 2^126 on the high word alone
+            asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
                 : "+d"(f) : "r"(__double2hiint(r2)));
           else
-            asm("{\n\t.reg .pred p, q;\n\tsetp.lt.f64 p, %1, %2;\n\tsetp.ne.and.s32 q, %3, 0, p;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
-                : "+d"(f) : "d"(r2), "d"(c.rc2_u), "r"(__double2hiint(r2)));
+            asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
+                : "+d"(f) : "d"(r2), "d"(c.rc2_u));
           ax[k] = fma(f, dx, ax[k]);
           ay[k] = fma(f, dy, ay[k]);
           az[k] = fma(f, dz, az[k]);
