@@ -359,11 +359,11 @@ def run_ours(args):
                          "peak_source": "measured live: DFMA-chain probe kernel (mdqt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch, "launch_ms": k1_ms, "launches_timed": k1_n,
                          "timing": "second pass over the same steps with a CUDA-event pair around every launch",
-                         "note": "HBM/tensor do not bound this kernel. Per ordered pair the inner loop issues 23 FP64-pipe + ~21.6 other "
+                         "note": "HBM/tensor do not bound this kernel. Per ordered pair the inner loop issues 23 FP64-pipe + ~20.5 other "
                                  "instructions (cuobjdump; exp and rsqrt expand). An FP64 warp instruction holds the sub-partition's issue "
-                                 "port 2 cycles on sm_100, so the issue-bound ceiling is 34 flop x 32 lanes / (2*23+21.6 cycles) = 0.50 of "
-                                 "the nominal DFMA rate (0.55 of the measured probe); large N reaches 0.51-0.52 of the probe (large_n.fp64_frac). "
-                                 "At N=3500 one launch holds only ~25 us of issue work for the whole chip and ~10 us of launch latency, CTA "
+                                 "port 2 cycles on sm_100, so the issue-bound ceiling is 34 flop x 32 lanes / (2*23+20.5 cycles) = 0.51 of "
+                                 "the nominal DFMA rate (0.56 of the measured probe); large N reaches 0.51-0.53 of the probe (large_n.fp64_frac). "
+                                 "At N=3500 one launch holds only ~24 us of issue work for the whole chip and ~9 us of launch latency, CTA "
                                  "prologue/epilogue and in-SM tail are exposed (per-CTA phase trace in profiles/)"},
             "roofline_substeps": {"bound": "hbm", "kernel": "k_substeps (25 fused step()+qstep())", "achieved": k2_gbs, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": k2_gbs / hbm_peak, "peak_source": peak_src, "launch_ms": k2_ms,
