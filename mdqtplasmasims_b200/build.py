@@ -51,7 +51,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     if out is None:
         # the C++ host driver (the reference's main loop on top of the C ABI); finds the library next to itself
         cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-o", DRIVER] + [os.path.join(CSRC, f) for f in DRIVER_SOURCES] + [
-            "-L" + HERE, "-lmdqt_b200", "-Wl,-rpath,$ORIGIN"]
+            "-L" + HERE, "-lmdqt_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("g++ (mdqt_run) failed:\n" + res.stdout + res.stderr)

@@ -13,9 +13,61 @@
 #include <string.h>
 #include <time.h>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+// output() formats ~9500 text lines per call (3 x 2001 velocity bins + one line per ion, SU:958-1024): about 3 ms of
+// fprintf, as long as the 40 MD steps between two calls take on the GPU. A single writer thread does the formatting in
+// call order while the time loop keeps the GPU busy; the files are byte-for-byte what a synchronous writer produces.
+struct OutputJob {
+  std::string dir;
+  unsigned counter; int N;
+  mdqt_diag d; double Epot0;
+  std::vector<double> pvel, pops, vx;  // vx = V[0][0..N): the only velocity row write_populations prints
+};
+class OutputWriter {
+ public:
+  OutputWriter() : th_([this] { run(); }) {}
+  ~OutputWriter() { finish(); }
+  void push(OutputJob&& j) {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_space_.wait(lk, [this] { return q_.size() < 4; });  // bounded: at most 4 outputs in flight
+    q_.push_back(std::move(j));
+    cv_work_.notify_one();
+  }
+  void finish() {
+    { std::lock_guard<std::mutex> lk(m_); done_ = true; }
+    cv_work_.notify_one();
+    if (th_.joinable()) th_.join();
+  }
+ private:
+  void run() {
+    for (;;) {
+      OutputJob j;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [this] { return done_ || !q_.empty(); });
+        if (q_.empty()) return;
+        j = std::move(q_.front());
+        q_.pop_front();
+        cv_space_.notify_one();
+      }
+      mdqt_io_append_energies(j.dir.c_str(), j.d.t, j.d.ekin_x, j.d.ekin_y, j.d.ekin_z, j.d.epot, j.Epot0, j.d.vx_avg);
+      mdqt_io_write_vel_dist(j.dir.c_str(), j.counter, j.pvel.data(), j.d.vx_avg);
+      mdqt_io_write_populations(j.dir.c_str(), j.counter, j.N, j.vx.data(), j.pops.data());
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_space_;
+  std::deque<OutputJob> q_;
+  bool done_ = false;
+  std::thread th_;
+};
 
 static void die(const char* what) {
   fprintf(stderr, "mdqt_run: %s: %s\n", what, mdqt_last_error());
@@ -86,6 +138,7 @@ int main(int argc, char** argv) {
   CK(mdqt_epot(h, &Epot0));  // Epotential(); Epot0 = Epot (SU:345-346). On resume the reference leaves Epot0 = 0 (Q8):
   if (newRun != 1) Epot0 = 0.0;
 
+  OutputWriter writer;
   int tsc = p.substeps_per_md;  // timeStepCounter (SU:1235)
   auto wall0 = std::chrono::steady_clock::now();
   long nsub_total = 0, nforce = 0, nout = 0;
@@ -99,9 +152,10 @@ int main(int argc, char** argv) {
       CK(mdqt_vel_dist(h, pvel.data()));
       CK(mdqt_populations(h, pops.data()));
       CK(mdqt_download_state(h, NULL, V.data(), NULL, NULL, ld));
-      mdqt_io_append_energies(dir, d.t, d.ekin_x, d.ekin_y, d.ekin_z, d.epot, Epot0, d.vx_avg);
-      mdqt_io_write_vel_dist(dir, counter, pvel.data(), d.vx_avg);
-      mdqt_io_write_populations(dir, counter, N, V.data(), pops.data());
+      OutputJob job;
+      job.dir = dir; job.counter = counter; job.N = N; job.d = d; job.Epot0 = Epot0;
+      job.pvel = pvel; job.pops.assign(pops.begin(), pops.begin() + (size_t)N * 3); job.vx.assign(V.begin(), V.begin() + N);
+      writer.push(std::move(job));
       counter++;
       nout++;
     }
@@ -109,6 +163,7 @@ int main(int argc, char** argv) {
     CK(mdqt_substeps(h, n));
     nsub_total += n;
   }
+  writer.finish();  // every output file is on disk before the restart files are written
   CK(mdqt_download_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
   double t_dev; uint64_t s_dev;
   CK(mdqt_get_time(h, &t_dev, &s_dev));
