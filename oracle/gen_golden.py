@@ -363,6 +363,43 @@ def recorder_series(seed, n, T, Gamma):
     return v
 
 
+def gen_fz_loop():
+    """The FZ408L time loop itself (FZ408L:1040-1072, through ref_fz_run_loop: the loop body re-typed around the reference's
+    own step()/qstep()/measureSpinUps()/Zfunc() and globals): a new run from init(4242), tmax = 0.0201, pump window
+    (0.0061, 0.0143), sampleFreq = 5. No jumps during the pump (injected rand = NOJUMP); the measurement draws follow."""
+    fz = po.RefFZ408L()
+    c = fz.consts
+    n = fz.init(4242)
+    s0 = fz.get_state()
+    tmax, tstart, tend, sf = 0.0201, 0.0061, 0.0143, 5
+    # count the pump sweeps with the loop's own time arithmetic
+    t, k = 0.0, 0
+    while t <= tmax + 0.0009:
+        if t < tend and t > tstart:
+            k += 1
+        t += c["dtq"]
+    rng = np.random.default_rng(41)
+    meas = rng.uniform(size=2 * n)
+    u = np.concatenate([np.full(k * n, NOJUMP), meas])
+    fz.set_c0(-1)
+    r = fz.run_loop(tmax, tstart, tend, sf, u)
+    s1 = fz.get_state()
+    nr = (s1["psi"] ** 2).sum(axis=2)  # psi is not touched after the pump window, so these are the measured norms
+    u_tab = np.zeros((n, 2))
+    cur = 0
+    for i in range(n):
+        u_tab[i, 0] = meas[cur]; cur += 1
+        c1 = nr[i, 0] + nr[i, 2]
+        if not (u_tab[i, 0] < c1) and (u_tab[i, 0] < c1 + nr[i, 3] + nr[i, 4]):
+            u_tab[i, 1] = meas[cur]; cur += 1
+    assert r["used"] == k * n + cur, (r["used"], k * n + cur)
+    np.savez_compressed(os.path.join(OUT, "fz408l_loop.npz"), R0=s0["R"], V0=s0["V"], psi0=s0["psi"], R1=s1["R"], V1=s1["V"],
+                        psi1=s1["psi"], t1=s1["t"], c0=r["c0"], iters=r["iters"], pump_sweeps=k, tag_u=u_tab, spin=r["spin"],
+                        nspin=r["nspin"], vaf=r["vaf"], tmax=tmax, tstart=tstart, tend=tend, sampleFreq=sf,
+                        **{kk: c[kk] for kk in c})
+    print("fz408l_loop: N=%d, %d iterations, %d pump sweeps, c0=%d, %d spin-up, VAF %s" % (n, r["iters"], k, r["c0"], r["nspin"], r["vaf"]))
+
+
 def seed_stream(ref, seed):
     """srand48(seed) inside the harness process (the reference's drand48 stream is then its own, un-injected)."""
     import ctypes
@@ -375,6 +412,9 @@ if __name__ == "__main__":
     po.build()
     if "--mainloop" in sys.argv:
         gen_su_mainloop()
+        sys.exit(0)
+    if "--fzloop" in sys.argv:
+        gen_fz_loop()
         sys.exit(0)
     if "--recorders" in sys.argv:
         gen_recorders()

@@ -619,3 +619,18 @@ class RefFZ408L:
 
     def zfunc(self, c1V):
         return self.lib.ref_fz_zfunc(c1V)
+
+    def run_loop(self, tmax, tstart, tend, sampleFreq, uniforms):
+        """The reference's main time loop (FZ408L:1040-1072; output()/printVAF() file writes left out) from the current
+        state, new-run flags; `uniforms` = ONE sequential stream for every drand48 the loop consumes."""
+        self.lib.ref_fz_run_loop.restype = ctypes.c_long
+        self.lib.ref_fz_run_loop.argtypes = [ctypes.c_double] * 3 + [ctypes.c_int, c_double_p, c_int_p, c_int_p]
+        vaf = np.zeros(2)
+        spin = np.zeros(self.N, dtype=np.int32)
+        nspin = ctypes.c_int(0)
+        (iters), used = self._with_u(uniforms, lambda: self.lib.ref_fz_run_loop(tmax, tstart, tend, sampleFreq, _dp(vaf),
+                                                                               spin.ctypes.data_as(c_int_p), ctypes.byref(nspin)))
+        return dict(iters=iters, used=used, vaf=vaf, spin=spin, nspin=nspin.value, c0=self.lib.ref_fz_get_c0())
+
+    def set_c0(self, c0):
+        self.lib.ref_fz_set_c0(c0)

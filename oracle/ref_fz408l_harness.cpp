@@ -102,4 +102,41 @@ int ref_fz_measure(int* out) {
   return NSpinUp;
 }
 double ref_fz_zfunc(int c1V) { Zfunc(c1V); return VAF; }
+int ref_fz_get_c0() { return c0; }
+void ref_fz_set_c0(int c) { c0 = c; }
+// The body of main()'s time loop (FZ408L:1040-1072) re-typed around the reference's OWN functions and globals, with the
+// compile-time tmax / tstartV0 and the derived tendV0 as parameters, and the file-writing output()/printVAF() calls left
+// out (recordedSpinUps starts at 0: a new run). Returns the number of loop iterations; vaf[0], vaf[1] = Zfunc values at the
+// measurement and at the last sampling point (NaN if none); spin = SpinUpList.
+long ref_fz_run_loop(double tmax_, double tstart_, double tend_, int sampleFreq_, double* vaf, int* spin, int* nspin) {
+  int timeStepCounter = plasmaToQuantumTimestepRatio;
+  int recorded = 0;
+  long iters = 0;
+  vaf[0] = vaf[1] = NAN;
+  *nspin = -1;
+  while (t <= tmax_ + 0.0009) {
+    if (recorded == 0 && t >= tend_) {
+      measureSpinUps();
+      recorded = 1;
+      for (unsigned i = 0; i < N; i++) spin[i] = SpinUpList[i];
+      *nspin = NSpinUp;
+      Zfunc(0);
+      vaf[0] = VAF;
+    }
+    if ((c0 + 1) % sampleFreq_ == 0 && timeStepCounter == 1 && recorded == 1) {
+      Zfunc(1);
+      vaf[1] = VAF;
+    }
+    if (timeStepCounter == plasmaToQuantumTimestepRatio) {
+      step();
+      c0++;
+      timeStepCounter = 0;
+    }
+    if (t < tend_ && t > tstart_) qstep();
+    else t += quantumTimestep;
+    timeStepCounter++;
+    iters++;
+  }
+  return iters;
+}
 }

@@ -234,3 +234,67 @@ def test_row_decomposed_diagnostics_sum_to_the_full_ones():
     assert abs(s1[4] - d["epot"]) <= 1e-12 * d["epot"]
     pvp = sum(e.vel_dist_partial(mean) for e in parts)
     assert np.abs(pvp - pv).max() <= 1e-11 * pv.max()
+
+
+def test_fz_main_loop_driver_golden(golden_dir):
+    """drivers.fz_main_loop = the reference's FZ408L time loop (new run from init(), pump window, measurement, sampling)."""
+    from mdqtplasmasims_b200 import drivers
+    g = np.load(os.path.join(golden_dir, "fz408l_loop.npz"))
+    n = g["R0"].shape[1]
+    p = su_params(n_ions=n, scheme=SCHEME_SR7, detuning=-2.5, Om=0.7)
+    p.substeps_per_md = int(g["ratio"])
+    assert p.dtq == float(g["dtq"]) and p.L == float(g["L"])
+    eng = Engine(p)
+    eng.upload(R=g["R0"], V=g["V0"], psi=g["psi0"], t=0.0)
+    sweeps = int(g["pump_sweeps"])
+    eng.set_forced_uniforms(np.full((sweeps, n, 5), NOJUMP))
+    eng.set_forced_tag_uniforms(g["tag_u"])
+    events = []
+    out = drivers.fz_main_loop(eng, float(g["tmax"]), float(g["tstart"]), float(g["tend"]), c0=-1, sampleFreq=int(g["sampleFreq"]),
+                               on_measure=lambda t, tg, nu, v: events.append(("m", t)), on_sample=lambda t, c, v: events.append(("s", t, c)))
+    s = eng.download(("R", "V", "psi"))
+    assert out["iters"] == int(g["iters"]) and out["c0"] == int(g["c0"])
+    assert s["t"] == float(g["t1"]) and out["t"] == float(g["t1"])           # the same repeated additions on host and device
+    assert np.abs(s["R"] - g["R1"]).max() <= RV_TOL * p.L
+    assert np.abs(s["V"] - g["V1"]).max() <= RV_TOL * np.abs(g["V1"]).max()
+    assert np.abs(s["psi"] - g["psi1"]).max() <= AMP_TOL
+    assert np.array_equal(out["tagged"], g["spin"]) and out["n_up"] == int(g["nspin"])
+    assert abs(out["vaf_measure"] - float(g["vaf"][0])) <= 1e-12 * abs(float(g["vaf"][0]))
+    assert abs(out["vaf_last"] - float(g["vaf"][1])) <= 1e-12 * abs(float(g["vaf"][1]))
+    assert [e[0] for e in events] == ["m", "s"] and events[1][2] == 9
+    # every forced pump sweep was consumed, none left over
+    with pytest.raises(Exception):
+        eng.qstep7(1)
+
+
+def test_mc_family_stage_drivers():
+    """drivers.mc_pump_and_tag / md_record_stage are the reference's Step 5-7 loops (MC408L:1222-1253): same calls, same order."""
+    from mdqtplasmasims_b200 import drivers, synthetic
+    n = 512
+
+    def fresh():
+        p = md_params(scheme=SCHEME_SR7, n_ions=n, density=2.0)
+        e = Engine(p)
+        e.upload(R=synthetic.random_positions(n, p.L, seed=2), V=synthetic.maxwellian(n, np.sqrt(1 / 3.), seed=2),
+                 psi=synthetic.random_s_state(n, 7, seed=2))
+        e.forces()
+        return e, p
+    a, p = fresh()
+    tagged, cnt = drivers.mc_pump_and_tag(a, 3)
+    b, _ = fresh()
+    for _ in range(3):
+        b.qstep7(p.substeps_per_md)
+        b.MDStep(dt=0.005)
+    tagged_b, cnt_b = b.tagParticles()
+    assert np.array_equal(tagged, tagged_b) and cnt == cnt_b and 0 < cnt < n
+    sa, sb = a.download(("R", "V", "psi")), b.download(("R", "V", "psi"))
+    assert all(np.array_equal(sa[k], sb[k]) for k in ("R", "V", "psi"))
+    grs = []
+    ac = drivers.md_record_stage(a, 8, Gamma=3.0, gr_every=4, on_gr=lambda k, r, g: grs.append((k, g.copy())))
+    b.vstore_begin(8)
+    for k in range(8):
+        b.MDStep(dt=0.005)
+        b.recordVelsForAutocorrelations(k)
+    ac_b = b.autocorrelations(3.0)
+    assert [k for k, _ in grs] == [0, 4] and all(np.array_equal(x, y) for x, y in zip(ac, ac_b))
+    assert ac[0][0] > 0  # VAF(0) = <v.v>
