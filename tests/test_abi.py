@@ -94,3 +94,62 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".h", ".cuh", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/mdqt_oracle.c (orc_", ""), f
+
+
+def _build_c_client(tmp_path):
+    """examples/abi_client.c: a plain C99 program against include/mdqt.h, linked to the in-tree library."""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "abi_client")
+    pkg_dir = os.path.join(ROOT, "mdqtplasmasims_b200")
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_client.c"),
+           "-L" + pkg_dir, "-lmdqt_b200", "-Wl,-rpath," + pkg_dir, "-lm", "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_c_client_compiles_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    """The ABI is usable from plain C (no C++ or torch types in the header); without a device the client gets
+    MDQT_ENODEVICE -- there is no CPU fallback to fall into."""
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    if lib.mdqt_device_count() > 0:
+        pytest.skip("a GPU is present: the run itself is covered by the gpu-marked test")
+    res = subprocess.run([exe, "64", "1"], capture_output=True, text=True)
+    assert res.returncode == 3 and "no CPU fallback" in res.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_matches_the_python_mirror(tmp_path):
+    """The same run through the C program and through the ctypes mirror: identical observables."""
+    import subprocess
+    import numpy as np
+    from mdqtplasmasims_b200 import Engine, su_params
+    exe = _build_c_client(tmp_path)
+    n, nsteps = 500, 3
+    res = subprocess.run([exe, str(n), str(nsteps)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    got = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in res.stdout.split()}
+    # replay the client's xorshift64 initial state in Python
+    state = 88172645463325252
+    M = (1 << 64) - 1
+
+    def urand():
+        nonlocal state
+        state ^= (state << 13) & M; state ^= state >> 7; state ^= (state << 17) & M
+        return (state >> 11) * (1.0 / 9007199254740992.0)
+    p = su_params(n_ions=n, N0=n, seed=2024, traj0=1)
+    R = np.zeros((3, n)); psi = np.zeros((n, 12, 2))
+    for i in range(n):
+        for c in range(3):
+            R[c, i] = p.L * urand()
+        r1, r2 = urand(), urand()
+        psi[i, 0, 0] = np.sqrt(r1); psi[i, 1, 0] = np.sqrt(1 - r1) * np.sqrt(r2); psi[i, 1, 1] = np.sqrt(1 - r1) * np.sqrt(1 - r2)
+    eng = Engine(p)
+    eng.upload(R=R, V=np.zeros((3, n)), psi=psi, tPart=np.zeros(n), t=0.0, substep=0)
+    eng.md_steps(nsteps)
+    d = eng.diagnostics()
+    s = eng.download(("psi",))
+    for k in ("t", "ekin_x", "ekin_y", "ekin_z", "epot", "vx_avg"):
+        assert got[k] == d[k], k
+    assert abs(got["norm"] - (s["psi"] ** 2).sum() / n) < 1e-14
