@@ -342,7 +342,7 @@ def run_ours(args):
                 traffic = None
         line = {
             "metric": "ion-steps/s (MDQT) & Yukawa pair-interactions/s", "value": value, "unit": "ion-steps/s",
-            "n_gpus": world, "steps": K, "warmup": w, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": W, "warmup_steps_run": w, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "mdqt_thesis_N0_3500 (BASELINE configs[1]): 12-level Sr+ MDQT, detuning=-1, detuningDP=+1, "
                                    "Om=OmDP=1, density=2, Ge=0.1; one trajectory per GPU",
