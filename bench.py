@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 MD_PER_STEP = 40          # sampleFreq (SU:78)
 FLOP_PER_PAIR = 34
 BYTES_PER_ION_STEP = 520
+FLOP_PER_ION_STEP = 1700  # ~1.7 kflop per no-jump 12-level ion-step (sparse H, 4 stages)
 N0 = 3500
 
 
@@ -232,9 +233,17 @@ def run_ours(args):
         a.record(es); ee.md_steps(2 * nmd); b_.record(es)
         ee.sync(); torch.cuda.synchronize(); barrier()
         ms = max_over_ranks(a.elapsed_time(b_))
+        ee.enable_timing(True)  # per-kernel split of the batched step (event pair per launch)
+        ee.md_steps(nmd)
+        e1_ms, _ = ee.kernel_time_ms(0)
+        e2_ms, _ = ee.kernel_time_ms(1)
+        ee.enable_timing(False)
         extras["ensemble"] = {"traj_per_gpu": Be, "ion_steps_per_s": sum_over_ranks(float(N0) * Be * 25 * 2 * nmd) / (ms * 1e-3),
                               "pair_interactions_per_s": sum_over_ranks(float(N0) * N0 * Be * 2 * nmd) / (ms * 1e-3),
-                              "ms_per_md_step": ms / (2 * nmd)}
+                              "ms_per_md_step": ms / (2 * nmd),
+                              "k_pairs_ms": e1_ms, "k_pairs_fp64_frac": FLOP_PER_PAIR * float(N0) * N0 * Be / (e1_ms * 1e-3) / 1e12 / fp64_peak,
+                              "k_substeps_ms": e2_ms,
+                              "k_substeps_fp64_frac": FLOP_PER_ION_STEP * float(N0) * Be * 25 / (e2_ms * 1e-3) / 1e12 / fp64_peak}
         ee.close()
 
     # ---- extra: large-N row decomposition with an NCCL all-gather of positions per MD step (config 5 shape) -----------------
@@ -367,7 +376,13 @@ def run_ours(args):
                                  "prologue/epilogue and in-SM tail are exposed (per-CTA phase trace in profiles/)"},
             "roofline_substeps": {"bound": "hbm", "kernel": "k_substeps (25 fused step()+qstep())", "achieved": k2_gbs, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": k2_gbs / hbm_peak, "peak_source": peak_src, "launch_ms": k2_ms,
-                                  "note": "effective bandwidth at 520 B per ion-substep; fused, so state crosses HBM once per 25 substeps"},
+                                  "flop_per_ion_step": FLOP_PER_ION_STEP,
+                                  "fp64_tflops": FLOP_PER_ION_STEP * (N0 * B * 25) / (k2_ms * 1e-3) / 1e12,
+                                  "fp64_frac": FLOP_PER_ION_STEP * (N0 * B * 25) / (k2_ms * 1e-3) / 1e12 / fp64_peak,
+                                  "note": "effective bandwidth at 520 B per ion-substep; fused, so state crosses HBM once per 25 substeps "
+                                          "(actual DRAM traffic: profiles/traffic.json). The kernel is not HBM-bound: one trajectory of 3500 ions is "
+                                          "220 warps, one per SM sub-partition, bound by its own in-order instruction stream (fp64_frac at ~1.7 kflop "
+                                          "per ion-step); batched trajectories fill the machine (ensemble.k_substeps_fp64_frac)"},
             "cpu_baseline": cpu,
         }
         line.update(extras)
