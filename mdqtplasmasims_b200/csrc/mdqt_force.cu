@@ -19,6 +19,7 @@
 // degree-5 polynomial with the exponent patched by integer adds (10), prefactor (4), accumulate (3).
 #include "mdqt_internal.h"
 #include "mdqt_fixed.cuh"
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -43,6 +44,14 @@ __device__ double c_exp2tab[kExpTable];  // global (L2-resident), not __constant
 
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER on B200 at N=3500 (114 vs 74 us per MD step)
+  return on;
+}
+
+bool cluster_enabled() {
+  // opt-in (MDQT_CLUSTER=1). Measured on B200: -2 us at N = 2048 (64 clusters of 4, one wave), but +8 us at N = 3000
+  // (94 clusters of 3) and N = 3500/4096 (more clusters than fit at once): cluster placement inside a GPC costs more balance
+  // than the cheaper reduction saves, and where it does so is hard to predict -- the default stays the global-memory path.
+  static const bool on = [] { const char* e = getenv("MDQT_CLUSTER"); return e && e[0] == '1'; }();
   return on;
 }
 
@@ -170,7 +179,10 @@ __device__ long long g_trace[8 * 8192];
 #ifndef MDQT_K1_MINB128
 #define MDQT_K1_MINB128 4
 #endif
-template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG>
+// CL = the j chunks of a row tile form one thread-block CLUSTER (gridDim.y = cluster size <= 8): the chunk sums are
+// combined through distributed shared memory in ascending chunk order -- the same order, hence the same bits, as the
+// global-memory path -- without partial-sum stores, fence, arrival counter and the last CTA's L2 round trips.
+template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG, bool CL = false>
 __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB32 : (RG == 128 && JS == 1) ? MDQT_K1_MINB128 : 1) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
   constexpr int kForceThreads = RG;  // shadows the namespace constant: rows per group in this instantiation
   __shared__ longlong2 sxy[kTJ];
@@ -305,6 +317,35 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
       }
     return;
   }
+  if (CL) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    double* spart = sjs;  // the in-CTA combine is over (sjs needs 3*(JS-1)*IPT*RG >= 3*IPT*RG doubles: JS >= 2 here)
+    __syncthreads();
+    if (owner) {
+#pragma unroll
+      for (int k = 0; k < IPT; k++) {
+        spart[(k * 3 + 0) * kForceThreads + ti] = ax[k]; spart[(k * 3 + 1) * kForceThreads + ti] = ay[k];
+        spart[(k * 3 + 2) * kForceThreads + ti] = az[k];
+      }
+    }
+    cluster.sync();
+    if (js == 0) {  // cluster rank 0 = chunk 0 (cluster dims (1, nsplit, 1)) adds the chunks in ascending order
+      for (int w = tid; w < kForceThreads * IPT * 3; w += NT) {
+        const int kc = w / kForceThreads, slot = w % kForceThreads;  // kc = k*3 + comp
+        const int row = a.row0 + tile * (kForceThreads * IPT) + (kc / 3) * kForceThreads + slot;
+        double v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = (r < a.nsplit) ? *cluster.map_shared_rank(&spart[w], r) : 0.0;
+        double sum = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) sum += v[r];
+        if (row < a.row0 + a.nrows) a.F[((size_t)b * 3 + (kc % 3)) * a.ld + row] = sum;
+      }
+    }
+    cluster.sync();  // nobody leaves while its shared memory may still be read
+    return;
+  }
   // j-split: store the partial, the last CTA of this (trajectory, i-tile) sums all partials in ascending split
   // order -> deterministic, independent of arrival order and of how many ranks share the rows.
 #pragma unroll
@@ -352,6 +393,16 @@ template <bool EPOT, bool HL>
 static void launch_pairs_hl(const ForceArgs& a, double* partials, cudaStream_t s, dim3 grid, int ipt, int jsub, bool pdl) {
   // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
   if (a.rg == 32) {
+    // clusters must be co-scheduled inside one GPC: a win (-2 us at N = 2048) only while every CTA of the grid is resident
+    // at once (two 256-thread or four 128-thread CTAs per SM at ~124 registers); beyond that the placement constraint costs
+    // more balance than the reduction saves (N = 3500: 41.5 us against 32.8 us), so larger grids keep the global-memory path
+    const long long ctas = (long long)grid.x * grid.y * grid.z;
+    const bool cl = !EPOT && a.nsplit >= 2 && a.nsplit <= 8 && ctas <= 148LL * (jsub == 8 ? 2 : 4) && cluster_enabled();
+    if (cl) {
+      if (jsub == 8) launch_kernel(k_pairs<1, 8, false, 8, HL, 32, true>, grid, dim3(256), s, pdl, a, partials, a.nsplit);
+      else launch_kernel(k_pairs<1, 4, false, 8, HL, 32, true>, grid, dim3(128), s, pdl, a, partials, a.nsplit);
+      return;
+    }
     if (jsub == 8) launch_kernel(k_pairs<1, 8, EPOT, 8, HL, 32>, grid, dim3(256), s, pdl, a, partials);
     else launch_kernel(k_pairs<1, 4, EPOT, 8, HL, 32>, grid, dim3(128), s, pdl, a, partials);
     return;

@@ -63,15 +63,21 @@ struct VVArgs {
 // their start and griddepcontrol.wait before touching data of their predecessor, so the next kernel's launch latency
 // and prologue overlap the current kernel's tail. `pdl` = launch with the programmatic-serialization attribute.
 bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool pdl, Args... args) {
+bool cluster_enabled();
+// cluster_y > 0: the grid's y dimension is launched as thread-block clusters of (1, cluster_y, 1)
+template <typename... KArgs, typename A0, typename A1>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, bool pdl, A0 a0, A1 a1, int cluster_y = 0) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; n++; }
+  if (cluster_y > 0) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = (unsigned)cluster_y; at[n].val.clusterDim.z = 1; n++;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, a0, a1);
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -1,6 +1,7 @@
 """GPU suite, part 3: the opt-in kernel mappings (environment knobs read once per process) stay parity-green:
-MDQT_QT_LANES=4 (four lanes per ion in the fused substep kernel), MDQT_PDL=1 (programmatic dependent launch) and the
-force-kernel plan overrides. Each runs __graft_entry__.smoke() -- one MD step with jumps against the oracle -- plus the
+MDQT_QT_LANES=4 (four lanes per ion in the fused substep kernel), MDQT_PDL=1 (programmatic dependent launch),
+MDQT_CLUSTER=1 (j chunks combined through distributed shared memory inside a thread-block cluster) and the force-kernel plan
+overrides. Each runs __graft_entry__.smoke() -- one MD step with jumps against the oracle -- plus the
 no-jump and jump-table goldens in a fresh interpreter."""
 import os
 import subprocess
@@ -12,7 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"MDQT_QT_LANES": "4"}, {"MDQT_PDL": "1"}, {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_JSUB": "4"},
+@pytest.mark.parametrize("env", [{"MDQT_QT_LANES": "4"}, {"MDQT_PDL": "1"}, {"MDQT_CLUSTER": "1"},
+                                 {"MDQT_CLUSTER": "1", "MDQT_FORCE_RG": "32", "MDQT_FORCE_JSUB": "4", "MDQT_FORCE_NSPLIT": "2"}, {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_JSUB": "4"},
                                  {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_NSPLIT": "3"}, {"MDQT_FORCE_JSUB": "1", "MDQT_FORCE_NSPLIT": "7"}])
 def test_variant_parity(env):
     e = dict(os.environ, **env)
