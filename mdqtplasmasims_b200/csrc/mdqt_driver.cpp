@@ -159,6 +159,20 @@ int main(int argc, char** argv) {
       counter++;
       nout++;
     }
+    if (do_forces && !do_output && n == p.substeps_per_md) {
+      // whole MD steps with no output() in between: hand the run of them to mdqt_md_steps (one replayed CUDA graph)
+      int k = 1;
+      for (;;) {
+        int c0b = c0, tscb = tsc, o2, f2;
+        double tb = t;
+        int n2 = mdqt_schedule_next(&c0b, &tscb, &tb, p.substeps_per_md, sampleFreq, p.dtq, tmax, &o2, &f2);
+        if (n2 != p.substeps_per_md || !f2 || o2) break;
+        c0 = c0b; tsc = tscb; t = tb; k++;
+      }
+      CK(mdqt_md_steps(h, k));
+      nforce += k; nsub_total += (long)k * n;
+      continue;
+    }
     if (do_forces) { CK(mdqt_forces(h)); nforce++; }
     CK(mdqt_substeps(h, n));
     nsub_total += n;

@@ -194,6 +194,14 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
   constexpr int NT = kForceThreads * JS;
 
   TRACE(0)
+  if (!EPOT && a.clock_advance > 0 && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // graph replay: this launch sits between the substep kernels of two MD steps, so nobody reads the clock now
+    double t = a.clock[0];
+    for (int k = 0; k < a.clock_advance; k++) t = __dadd_rn(t, a.clock_dtq);  // SU:716, one addition per substep
+    a.clock[0] = t;
+    unsigned long long* sub = reinterpret_cast<unsigned long long*>(a.clock + 1);
+    *sub += (unsigned long long)a.clock_advance;
+  }
   const int tid = threadIdx.x;
   const int ti = tid % kForceThreads, jh = tid / kForceThreads;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;

@@ -24,6 +24,10 @@ struct ForceArgs {
   int ipt;           // ion rows per thread (1 or 2)
   int jsub;          // intra-CTA split of each j tile over thread groups (1, 2, 4; 4 or 8 with 32-row groups)
   int rg;            // ion rows per thread group: 128 (default) or 32 (small systems)
+  // device clock {t, substep index}: inside a replayed CUDA graph kernel arguments are frozen, so the simulation time lives
+  // in device memory; the force kernel of MD step k >= 1 advances it by the substeps of step k-1 (clock_advance of them,
+  // t by the reference's repeated addition, SU:716) before the substep kernel of step k reads it. Null outside graphs.
+  double* clock; int clock_advance; double clock_dtq;
   int half_l;        // rcut == L/2 exactly (every reference program): the cut-off is a power of two in fixed-point units
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
 };
@@ -43,6 +47,7 @@ struct QTArgs {
   int do_tpart;                           // 1: tPart tracked (+= dtq, reset on a jump; SU:482, TS:155)
   int renorm, quad;
   double t0; uint64_t substep0; uint64_t seed;
+  const double* clock;                    // {t, substep index (as uint64 bits)} in device memory: overrides t0/substep0 when non-null
   double L, dtq;
   double detuning, detuningDP, Om, OmDP, dR, kRat, vKick, vKickDP, g2E, pv2qv;
   double fracOfSig, Te, sig0, density;

@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
   }
   if (do_tpart) tp = a.tPart[(size_t)b * a.ld + i];
-  double t = a.t0;
+  double t = a.clock ? a.clock[0] : a.t0;  // device clock inside a replayed CUDA graph
+  const uint64_t substep0 = a.clock ? *reinterpret_cast<const unsigned long long*>(a.clock + 1) : a.substep0;
   const double DT = 0.5 * a.dtq;
   const double dEDP = -a.detuning + a.detuningDP;
 
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
 
     // the uniforms of this (ion, substep): both lanes of an ion draw the same numbers
     double u0, u1;
-    const uint64_t sidx = a.substep0 + (uint64_t)s;
+    const uint64_t sidx = substep0 + (uint64_t)s;
     if (FORCED) {
       const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
       u0 = up[0]; u1 = up[1];
@@ -520,7 +521,8 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   double rx = Rb[i], r2 = Rb[(size_t)c2 * a.ld + i], vx = Vb[i], v2 = Vb[(size_t)c2 * a.ld + i];
   const double fx = Fb[i], f2 = Fb[(size_t)c2 * a.ld + i];
   double tp = a.tPart[(size_t)b * a.ld + i];
-  double t = a.t0;
+  double t = a.clock ? a.clock[0] : a.t0;  // device clock inside a replayed CUDA graph
+  const uint64_t substep0 = a.clock ? *reinterpret_cast<const unsigned long long*>(a.clock + 1) : a.substep0;
   const double DT = 0.5 * a.dtq;
 
   for (int s = 0; s < a.nsub; s++) {
@@ -553,7 +555,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
     tp = __dadd_rn(tp, a.dtq);
 
     double u0, u1;
-    const uint64_t sidx = a.substep0 + (uint64_t)s;
+    const uint64_t sidx = substep0 + (uint64_t)s;
     if (FORCED) {
       const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
       u0 = up[0]; u1 = up[1];
