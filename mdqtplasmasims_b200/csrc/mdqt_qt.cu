@@ -674,11 +674,15 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   int block = threads >= 148LL * 4 * 128 ? 128 : 64;
   int grid = (int)((threads + block - 1) / block);
   bool forced = a.forced_u != nullptr;
-  // Four lanes per ion is opt-in (MDQT_QT_LANES=4): measured on B200 at N = 3500 it is SLOWER than two lanes (35.2 vs
-  // 31.2 us per 25 substeps) -- the extra shuffle round trips per Runge-Kutta stage cost more latency than the shorter
-  // instruction stream saves. Kept as the verified alternative mapping (tests/test_gpu_parity.py runs it).
+  // Lanes per ion. One trajectory of a few thousand ions is a few hundred warps, at most one per SM sub-partition, each bound
+  // by its own in-order instruction stream: there four lanes per ion (35 % fewer instructions per warp, twice the warps) win
+  // -- 26.9 vs 28.5 us per 25 substeps at N = 3500 inside the replayed graph (profiles/r01c_k1_trace.txt). Once the warps
+  // outnumber the sub-partitions the kernel is throughput-bound and two lanes (fewer instructions per ion) win. The switch
+  // depends on N and the batch size only, so every rank of a row-decomposed run takes the same mapping.
+  // MDQT_QT_LANES=2|4 forces one mapping (both stay parity-tested, tests/test_gpu_variants.py).
   static const int lanes_override = [] { const char* e = getenv("MDQT_QT_LANES"); return e ? atoi(e) : 0; }();
-  const bool four = scheme == 12 && a.do_step && lanes_override == 4;
+  const bool small = 4LL * a.N * a.B <= 148LL * 4 * 32;  // four-lane warps fit one per sub-partition
+  const bool four = scheme == 12 && a.do_step && (lanes_override == 4 || (lanes_override != 2 && small));
   if (four) {
     long long th = 4LL * a.nrows * a.B;
     int g4 = (int)((th + 31) / 32);

@@ -1,5 +1,6 @@
 """GPU suite, part 3: the opt-in kernel mappings (environment knobs read once per process) stay parity-green:
-MDQT_QT_LANES=4 (four lanes per ion in the fused substep kernel), MDQT_PDL=1 (programmatic dependent launch),
+MDQT_QT_LANES=4|2 (four / two lanes per ion in the fused substep kernel; the default picks by system size), MDQT_GRAPH=0
+(stream launches instead of the replayed CUDA graph), MDQT_PDL=1 (programmatic dependent launch),
 MDQT_CLUSTER=1 (j chunks combined through distributed shared memory inside a thread-block cluster) and the force-kernel plan
 overrides. Each runs __graft_entry__.smoke() -- one MD step with jumps against the oracle -- plus the
 no-jump and jump-table goldens in a fresh interpreter."""
@@ -13,7 +14,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{"MDQT_QT_LANES": "4"}, {"MDQT_PDL": "1"}, {"MDQT_CLUSTER": "1"},
+@pytest.mark.parametrize("env", [{"MDQT_QT_LANES": "4"}, {"MDQT_QT_LANES": "2"}, {"MDQT_GRAPH": "0"}, {"MDQT_PDL": "1"}, {"MDQT_CLUSTER": "1"},
                                  {"MDQT_CLUSTER": "1", "MDQT_FORCE_RG": "32", "MDQT_FORCE_JSUB": "4", "MDQT_FORCE_NSPLIT": "2"}, {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_JSUB": "4"},
                                  {"MDQT_FORCE_IPT": "2", "MDQT_FORCE_NSPLIT": "3"}, {"MDQT_FORCE_JSUB": "1", "MDQT_FORCE_NSPLIT": "7"}])
 def test_variant_parity(env):
