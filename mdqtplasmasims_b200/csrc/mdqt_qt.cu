@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
 // K2, four lanes per ion (12-level scheme, small systems). With N ~ 3500 the two-lane kernel fills 220 of the chip's 592
 // warp schedulers with ONE warp each and is bound by the latency of its own instruction stream. Here every Hamiltonian
 // block is split once more -- lane (blk, 0) holds {S, P1, D3}, lane (blk, 1) holds {P2, D4, D5} -- so a warp carries
-// 8 ions and ~35 % fewer instructions per substep. Both halves run ONE uniform instruction stream with per-lane
+// 8 ions and fewer instructions per substep (643 vs 724 executed, ncu). Both halves run ONE uniform instruction stream with per-lane
 // coefficients (no divergence):
 //   row0 = D0 w0 + A01 w1 + a02 w2 + b00 r0      half0: S  (D0 = 0, A01 = c10, b00 = c20, r0 = P2)
 //                                                half1: P2 (D0 = E2 - i g2, A01 = conj(rot), a02 = c25, b00 = c20, r0 = S)
@@ -675,7 +675,7 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   int grid = (int)((threads + block - 1) / block);
   bool forced = a.forced_u != nullptr;
   // Lanes per ion. One trajectory of a few thousand ions is a few hundred warps, at most one per SM sub-partition, each bound
-  // by its own in-order instruction stream: there four lanes per ion (35 % fewer instructions per warp, twice the warps) win
+  // by its own in-order instruction stream: there four lanes per ion (643 vs 724 executed instructions per warp-substep, twice the warps) win
   // -- 26.9 vs 28.5 us per 25 substeps at N = 3500 inside the replayed graph (profiles/r01c_k1_trace.txt). Once the warps
   // outnumber the sub-partitions the kernel is throughput-bound and two lanes (fewer instructions per ion) win. The switch
   // depends on N and the batch size only, so every rank of a row-decomposed run takes the same mapping.
