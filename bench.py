@@ -313,9 +313,9 @@ def run_ours(args):
         em.upload(R=synthetic.random_positions(nm, pm.L, seed=3), V=synthetic.maxwellian(nm, np.sqrt(1 / 3.), seed=3))
         em.forces()
         sm = torch.cuda.ExternalStream(em.lib.mdqt_stream(em.h), device=torch.device("cuda", local))
-        for _ in range(200):
-            em.MDStep(dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.))
-        ms = timed(lambda: em.MDStep(dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.)), em, sm, 400)
+        for _ in range(5):
+            em.MDSteps(40, dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.))
+        ms = timed(lambda: em.MDSteps(40, dt=0.005, collisionFreq=0.25, sigma_v=np.sqrt(1 / 3.)), em, sm, 10) / 40
         extras["md_only_N4096"] = {"workload": "MDStep(): velocity Verlet + Andersen collisions, kappa=0.5 (MD:66-88, 504-511)",
                                    "ms_per_md_step": ms, "pair_interactions_per_s": float(nm) * nm / (ms * 1e-3)}
         em.close()
@@ -326,13 +326,12 @@ def run_ours(args):
         e7.forces()
         s7 = torch.cuda.ExternalStream(e7.lib.mdqt_stream(e7.h), device=torch.device("cuda", local))
 
-        def pump_step():
-            e7.qstep7(p7.substeps_per_md)  # for l < plasmaToQuantumTimestepRatio: qstep()  (MC408L:1228-1230)
-            e7.MDStep(dt=0.005)            # MDStep(k)                                     (MC408L:1231)
+        def pump_steps():  # 20 x { for l < plasmaToQuantumTimestepRatio: qstep(); MDStep(k) }  (MC408L:1227-1232)
+            e7.MDSteps(20, dt=0.005, qsteps=p7.substeps_per_md)
 
-        for _ in range(50):
-            pump_step()
-        ms = timed(pump_step, e7, s7, 100)
+        for _ in range(3):
+            pump_steps()
+        ms = timed(pump_steps, e7, s7, 5) / 20
         extras["qt_tagging_408_N4096"] = {"workload": "pump stage: 62 x 7-level qstep() + MDStep() per MD step (MC408L:1227-1232)",
                                           "ms_per_md_step": ms, "ion_steps_per_s": float(nm) * p7.substeps_per_md / (ms * 1e-3)}
         e7.close()

@@ -129,6 +129,11 @@ int mdqt_vel_dist_partial(mdqt_handle* h, const double* vx_mean, double* pvel);
  * collisions (probability dt*collisionFreq, velocities ~ N(0, sigma_v^2)) and the optional laser friction term
  * (laser: 0 none, 1 three-axis MD:494-496, 2 x only MD:491; coefficient = 1.234e-6*beta/sqrt(n)). */
 int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff);
+/* nsteps x { qsteps x qstep(); MDStep(); } in one call: the MD-family loops (MD:1081-1083, 1107-1165 with qsteps = 0) and the
+ * pump stage (MC408L:1227-1232 with qsteps = plasmaToQuantumTimestepRatio). Two or more steps are replayed as one CUDA
+ * graph (bitwise the same results as the single calls). */
+int mdqt_vv_steps(mdqt_handle* h, int nsteps, int qsteps, double dt, double collisionFreq, double sigma_v, int laser,
+                  double laser_coeff);
 /* nsub x qstep() without step(): the 7-level (MC408L:555-756, FZ408L:396-598) and 5-level (MC422L:552-727) pump
  * sweeps at frozen velocities without kick, and the 3-level test system (TS:140-293; V_x += kick, tPart tracked). */
 int mdqt_qsteps(mdqt_handle* h, int nsub);

@@ -26,7 +26,7 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 // one instantiated CUDA graph of `nsteps` MD steps, valid while the kernel arguments it froze are still the handle's
-struct GraphEntry { int nsteps; cudaGraphExec_t exec; ForceArgs fa; QTArgs qa; };
+struct GraphEntry { int nsteps; cudaGraphExec_t exec; ForceArgs fa; QTArgs qa; VVArgs va; };
 
 struct mdqt_handle {
   mdqt_params p;
@@ -52,9 +52,10 @@ struct mdqt_handle {
   std::vector<GraphEntry> graphs;   // small cache keyed by nsteps
 };
 
-__global__ void k_set_clock(double* clock, double t, unsigned long long substep) {
+__global__ void k_set_clock(double* clock, double t, unsigned long long substep, unsigned long long vv_step) {
   clock[0] = t;
-  *reinterpret_cast<unsigned long long*>(clock + 1) = substep;
+  reinterpret_cast<unsigned long long*>(clock)[1] = substep;
+  reinterpret_cast<unsigned long long*>(clock)[2] = vv_step;
 }
 
 static size_t state_elems(const mdqt_handle* h) { return (size_t)h->B * 3 * h->ld; }
@@ -261,7 +262,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   alloc(&h->scalars, (size_t)h->B * 16);
   alloc(&h->pvel, (size_t)h->B * 3 * kVelBins);
   alloc(&h->pops, (size_t)h->B * h->N * 3);
-  alloc(&h->clock, 2);
+  alloc(&h->clock, 4);
   if (e == cudaSuccess) {
     e = cudaMalloc((void**)&h->Rfix, sizeof(long long) * std::max<size_t>(ne, 1));
     if (e == cudaSuccess) e = cudaMemset(h->Rfix, 0, sizeof(long long) * std::max<size_t>(ne, 1));
@@ -510,9 +511,11 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
     if (h->graphs.size() >= 4) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
-    h->graphs.push_back(GraphEntry{nsteps, exec, fa, qa});
+    VVArgs v0;
+    memset(&v0, 0, sizeof(v0));
+    h->graphs.push_back(GraphEntry{nsteps, exec, fa, qa, v0});
   }
-  k_set_clock<<<1, 1, 0, h->stream>>>(h->clock, h->t, (unsigned long long)h->substep);
+  k_set_clock<<<1, 1, 0, h->stream>>>(h->clock, h->t, (unsigned long long)h->substep, (unsigned long long)h->vv_step);
   CU(cudaGraphLaunch(exec, h->stream));
   for (long long s = 0; s < (long long)nsteps * ratio; s++) h->t += h->p.dtq;  // host mirror: the same repeated addition
   h->substep += (uint64_t)nsteps * ratio;
@@ -646,12 +649,77 @@ int mdqt_populations(mdqt_handle* h, double* pops) {
   return MDQT_OK;
 }
 
+// nsteps x { qsteps x qstep(); MDStep() } as ONE replayed CUDA graph (see md_steps_graph): the MD-family loops
+// MD:1081-1083 / 1107-1165 (qsteps = 0) and the pump stage MC408L:1227-1232 (qsteps = plasmaToQuantumTimestepRatio).
+int mdqt_vv_steps(mdqt_handle* h, int nsteps, int qsteps, double dt, double collisionFreq, double sigma_v, int laser,
+                  double laser_coeff) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!(dt > 0) || nsteps < 0 || qsteps < 0) return fail(MDQT_EINVAL, "dt must be > 0, nsteps and qsteps >= 0");
+  if (qsteps > 0 && h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5) return fail(MDQT_ESTATE, "pump sweeps need the 7- or 5-level scheme");
+  CU(cudaSetDevice(h->p.device));
+  const bool graph = nsteps >= 2 && !h->timing && !h->forced_u && !h->forced_cu && graphs_enabled();
+  if (!graph) {
+    for (int k = 0; k < nsteps; k++) {
+      if (qsteps > 0) { int rc = mdqt_qsteps(h, qsteps); if (rc) return rc; }
+      int rc = mdqt_vv_step(h, dt, collisionFreq, sigma_v, laser, laser_coeff);
+      if (rc) return rc;
+    }
+    return MDQT_OK;
+  }
+  refresh_fixed(h);
+  ForceArgs fa = force_args(h);  // F / oldF alternate inside the graph: the entry is keyed on the pointers of step 0
+  QTArgs qa = qt_args(h, qsteps, 0, 0);
+  qa.clock = h->clock; qa.t0 = 0.0; qa.substep0 = 0;
+  VVArgs va;
+  memset(&va, 0, sizeof(va));
+  va.R = h->R; va.V = h->V; va.A = h->F; va.oldA = h->oldF;
+  va.N = h->N; va.ld = h->ld; va.B = h->B; va.row0 = h->row0; va.nrows = h->nrows; va.traj0 = h->p.traj0;
+  va.L = h->p.L; va.dt = dt; va.collisionFreq = collisionFreq; va.sigma_v = sigma_v; va.laser_coeff = laser_coeff; va.laser = laser;
+  va.seed = h->p.seed; va.Rfix = h->Rfix; va.invL = 1.0 / h->p.L; va.invL_lo = fma(-va.invL, h->p.L, 1.0) * va.invL;
+  va.clock = h->clock; va.adv_sub = qsteps;
+  cudaGraphExec_t exec = nullptr;
+  for (GraphEntry& g : h->graphs)
+    if (g.nsteps == -nsteps && !memcmp(&g.fa, &fa, sizeof(fa)) && !memcmp(&g.qa, &qa, sizeof(qa)) && !memcmp(&g.va, &va, sizeof(va))) { exec = g.exec; break; }
+  if (!exec) {
+    cudaGraph_t gr;
+    CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    double *F = h->F, *oldF = h->oldF;
+    for (int k = 0; k < nsteps; k++) {
+      if (qsteps > 0) launch_substeps(qa, h->qc, h->S, h->stream);     // qstep() sweeps (MC408L:1228-1230)
+      std::swap(F, oldF);                                              // oldA = A (MD:505-506)
+      VVArgs vk = va;
+      vk.A = oldF; vk.oldA = oldF; vk.adv_vv = k ? 1 : 0;
+      launch_vv_positions(vk, h->stream);                              // stepPositions (MD:507); advances the counters
+      ForceArgs fk = fa;
+      fk.F = F;
+      launch_forces(fk, h->stream);                                    // calculateAccelerations (MD:508)
+      vk.A = F;
+      launch_vv_velocities(vk, h->stream);                             // stepVelocities (MD:509)
+    }
+    cudaError_t e = cudaStreamEndCapture(h->stream, &gr);
+    if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, gr, 0);
+    cudaGraphDestroy(gr);
+    if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+    if (h->graphs.size() >= 4) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+    h->graphs.push_back(GraphEntry{-nsteps, exec, fa, qa, va});  // negative key: MD-family graphs
+  }
+  k_set_clock<<<1, 1, 0, h->stream>>>(h->clock, h->t, (unsigned long long)h->substep, (unsigned long long)h->vv_step);
+  CU(cudaGraphLaunch(exec, h->stream));
+  if (nsteps & 1) std::swap(h->F, h->oldF);
+  h->substep += (uint64_t)nsteps * qsteps;
+  h->vv_step += (uint64_t)nsteps;
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
 int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (!(dt > 0)) return fail(MDQT_EINVAL, "dt must be > 0");
   CU(cudaSetDevice(h->p.device));
   std::swap(h->F, h->oldF);  // oldA = A (MD:505-506)
   VVArgs a;
+  memset(&a, 0, sizeof(a));
   a.R = h->R; a.V = h->V; a.A = h->oldF; a.oldA = h->oldF;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = h->p.traj0;
   a.L = h->p.L; a.dt = dt; a.collisionFreq = collisionFreq; a.sigma_v = sigma_v; a.laser_coeff = laser_coeff; a.laser = laser;

@@ -62,6 +62,10 @@ struct VVArgs {
   uint64_t step; uint64_t seed;
   const double* forced_u;   // [N] collision uniforms or null
   const double* forced_n;   // [N][3] velocities assigned on collision or null
+  // device clock {t, substep index, MDStep index} for replayed CUDA graphs (null outside): the position kernel -- which runs
+  // after the pump sweeps and the velocity kernel of the previous step and before any reader of the new values -- adds
+  // adv_sub to the substep index and adv_vv to the MDStep index; the velocity kernel reads the MDStep index from it
+  double* clock; int adv_sub, adv_vv;
 };
 
 // Programmatic dependent launch (sm_90+): the hot kernels of an MD step call griddepcontrol.launch_dependents at

@@ -704,6 +704,11 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_vv_positions(VVArgs a) {
   long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a.clock && g == 0) {  // graph replay: advance the counters while nobody reads them
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(a.clock);
+    c[1] += (unsigned long long)a.adv_sub;
+    c[2] += (unsigned long long)a.adv_vv;
+  }
   if (g >= (long long)a.nrows * a.B * 3) return;
   int b = (int)(g / (3LL * a.nrows));
   int rem = (int)(g % (3LL * a.nrows));
@@ -723,6 +728,7 @@ __global__ void k_vv_velocities(VVArgs a) {
   int b = (int)(g / a.nrows);
   int i = a.row0 + (int)(g % a.nrows);
   size_t base = (size_t)b * 3 * a.ld + i;
+  const uint64_t vstep = a.clock ? reinterpret_cast<const unsigned long long*>(a.clock)[2] : a.step;
   double v[3];
   bool collide = false;
   if (a.collisionFreq > 0.0) {
@@ -732,14 +738,14 @@ __global__ void k_vv_velocities(VVArgs a) {
       nrm[0] = a.forced_n[3 * i]; nrm[1] = a.forced_n[3 * i + 1]; nrm[2] = a.forced_n[3 * i + 2];
       collide = u < a.dt * a.collisionFreq;
     } else {
-      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 3);
+      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, vstep, 3);
       u = u52(o.x, o.y);
       collide = u < a.dt * a.collisionFreq;  // MD:476-477
       if (collide) {                         // Box-Muller on stream calls 3..5 (orc_collision_draws)
         double ua = u52(o.z, o.w);
-        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 4);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, vstep, 4);
         double ub = u52(o.x, o.y), uc = u52(o.z, o.w);
-        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, a.step, 5);
+        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, vstep, 5);
         double ud = u52(o.x, o.y);
         double r = sqrt(-2.0 * log(ua)), sn, cs;
         sincos(6.283185307179586476925286766559 * ub, &sn, &cs);

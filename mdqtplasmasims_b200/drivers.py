@@ -82,9 +82,7 @@ def mc_pump_and_tag(eng, pumpMDTimeSteps, timeStep=0.005):
 
     at collisionFreq = 0. Returns (tagged, n_tagged)."""
     ratio = int(eng.params.substeps_per_md)
-    for _ in range(int(pumpMDTimeSteps)):
-        eng.qstep7(ratio)
-        eng.MDStep(dt=timeStep)
+    eng.MDSteps(int(pumpMDTimeSteps), dt=timeStep, qsteps=ratio)  # one replayed CUDA graph; same bits as the single calls
     return eng.tagParticles()
 
 

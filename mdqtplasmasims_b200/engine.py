@@ -47,6 +47,7 @@ ABI_SYMBOLS = [
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
+    "mdqt_vv_steps",
 ]
 
 _lib = None
@@ -108,6 +109,8 @@ def load_library():
     L.mdqt_vstore_record.argtypes = [vp, ctypes.c_int]
     L.mdqt_vstore_upload.argtypes = [vp, vp]
     L.mdqt_autocorrelations.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp]
+    L.mdqt_vv_steps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                ctypes.c_double]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
     L.mdqt_vel_dist_partial.argtypes = [vp, vp, vp]
     _lib = L
@@ -311,6 +314,10 @@ class Engine:
     def MDStep(self, dt=0.005, collisionFreq=0.0, sigma_v=1.0, laser=0, laser_coeff=0.0):
         """MDStep() MD:504-511."""
         self._ck(self.lib.mdqt_vv_step(self.h, dt, collisionFreq, sigma_v, laser, laser_coeff))
+
+    def MDSteps(self, nsteps, dt=0.005, collisionFreq=0.0, sigma_v=1.0, laser=0, laser_coeff=0.0, qsteps=0):
+        """nsteps x { qsteps x qstep(); MDStep(); } (MD:1081-1083; MC408L:1227-1232), replayed as one CUDA graph."""
+        self._ck(self.lib.mdqt_vv_steps(self.h, nsteps, qsteps, dt, collisionFreq, sigma_v, laser, laser_coeff))
 
     def qstep7(self, nsub=1):
         """nsub x qstep() of the 7-level pump (MC408L:555-756), velocities frozen, no kick."""

@@ -298,3 +298,31 @@ def test_mc_family_stage_drivers():
     ac_b = b.autocorrelations(3.0)
     assert [k for k, _ in grs] == [0, 4] and all(np.array_equal(x, y) for x, y in zip(ac, ac_b))
     assert ac[0][0] > 0  # VAF(0) = <v.v>
+
+
+def test_md_family_graph_replay_equals_single_steps():
+    """mdqt_vv_steps(n >= 2) replays { pump sweeps; stepPositions; calculateAccelerations; stepVelocities } x n as one CUDA graph
+    with the RNG counters in device memory; the single calls go through stream launches. Same kernels and uniforms -> same bits,
+    with collisions and with an odd number of steps (the A / oldA buffers swap roles every step)."""
+    from mdqtplasmasims_b200 import synthetic
+    n = 900
+    p = md_params(scheme=SCHEME_SR7, n_ions=n, density=2.0, seed=5, traj0=2)
+    R = synthetic.random_positions(n, p.L, seed=3)
+    V = synthetic.maxwellian(n, np.sqrt(1 / 3.), seed=3)
+    psi = synthetic.random_s_state(n, 7, seed=3)
+    a, b = Engine(p), Engine(p)
+    for e in (a, b):
+        e.upload(R=R, V=V, psi=psi)
+        e.forces()
+    kw = dict(dt=0.005, collisionFreq=40.0, sigma_v=np.sqrt(1 / 3.))   # ~20 % of the ions collide per step
+    a.MDSteps(5, qsteps=7, **kw); a.MDSteps(1, qsteps=7, **kw); a.MDSteps(5, qsteps=7, **kw); a.MDSteps(4, **kw)
+    for _ in range(11):
+        b.qstep7(7); b.MDStep(**kw)
+    for _ in range(4):
+        b.MDStep(**kw)
+    sa, sb = a.download(("R", "V", "psi")), b.download(("R", "V", "psi"))
+    assert sa["substep"] == sb["substep"] == 77
+    for k in ("R", "V", "psi"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.download_forces(), b.download_forces())
+    assert not np.array_equal(sa["V"], V)
