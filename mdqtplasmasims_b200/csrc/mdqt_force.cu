@@ -185,6 +185,12 @@ __device__ long long g_trace[8 * 8192];
 template <int IPT, int JS, bool EPOT, int UNR, bool HL, int RG, bool CL = false>
 __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB32 : (RG == 128 && JS == 1) ? MDQT_K1_MINB128 : 1) k_pairs(ForceArgs a, double* __restrict__ block_partials) {
   constexpr int kForceThreads = RG;  // shadows the namespace constant: rows per group in this instantiation
+#ifndef MDQT_K1_TJ32
+#define MDQT_K1_TJ32 1024
+#endif
+  // small systems: a CTA's whole j chunk (<= 1024 at the plans chosen there) is staged in ONE pass -- the L2 round trip of a
+  // second pass would be fully exposed (no other work to hide it behind): -0.7 us at N = 3500
+  constexpr int kTJ = (RG == 32) ? MDQT_K1_TJ32 : mdqt::kTJ;
   __shared__ longlong2 sxy[kTJ];
   __shared__ long long sz[kTJ];
   __shared__ double stab[kExpTable];
