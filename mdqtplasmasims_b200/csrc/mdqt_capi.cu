@@ -394,6 +394,12 @@ static ForceArgs force_args(mdqt_handle* h) {
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   a.half_l = (h->p.rcut == h->p.L / 2.) ? 1 : 0;
+  {
+    const double u = a.L / 18446744073709551616.0;  // L / 2^64
+    const double rc_u = sqrt(a.rc2) / u;
+    a.inv_u = 1.0 / u;
+    a.rc2_u = a.half_l ? 85070591730234615865843651857942052864.0 /* 2^126 = (L/2)^2 */ : rc_u * rc_u;
+  }
   return a;
 }
 

@@ -92,9 +92,8 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
 #else
   c.c1 = 1.0; c.c2 = 0.5; c.c3 = 1.6666666666666666e-01; c.c4 = 4.1666666666666664e-02; c.c5 = 8.3333333333333332e-03;
 #endif
-  const double rc_u = sqrt(a.rc2) / u;
-  c.rc2_u = a.half_l ? 85070591730234615865843651857942052864.0 /* 2^126 = (L/2)^2 */ : rc_u * rc_u;
-  c.out_scale = epot ? 1.0 / u : (1.0 / u) * (1.0 / u);
+  c.rc2_u = a.rc2_u;                                 // (rcut/u)^2, or 2^126 = (L/2)^2 exactly: formed on the host (no sqrt /
+  c.out_scale = epot ? a.inv_u : a.inv_u * a.inv_u;  // division in every thread's prologue)
   return c;
 }
 

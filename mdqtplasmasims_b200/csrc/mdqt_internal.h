@@ -30,6 +30,7 @@ struct ForceArgs {
   double* clock; int clock_advance; double clock_dtq;
   int half_l;        // rcut == L/2 exactly (every reference program): the cut-off is a power of two in fixed-point units
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
+  double inv_u, rc2_u;  // fixed-point unit u = L/2^64: 1/u, and the squared cut-off in units u^2
 };
 
 struct QTArgs {
