@@ -539,3 +539,31 @@ def test_md_steps_graph_replay_equals_stream_launches():
     for k in ("R", "V", "psi", "tPart"):
         assert np.array_equal(sa[k], sb[k]), k
     assert (sa["tPart"] < sa["t"] * 0.999).any()  # jumps happened on the way (tPart was reset)
+
+
+@pytest.mark.parametrize("n", [200, 6000])   # four lanes per ion (small systems) and two lanes per ion
+def test_renormalised_wavefunctions_vs_oracle(oracle, n):
+    """reNormalizewvFns = true (SU:74, 706-712): psi /= |psi| after every qstep, jumps included, in both lane mappings."""
+    from oracle import pyoracle as po
+    seed, traj, nsub = 4321, 2, 6
+    p = su_params(n_ions=n, N0=n, seed=seed, traj0=traj, renormalize=1)
+    qp, _ = po.su_params(renorm=1)
+    R = synthetic.random_positions(n, p.L, seed=8)
+    V = synthetic.maxwellian(n, 0.05, seed=8)
+    psi = synthetic.random_full_state(n, 12, seed=8)
+    eng = Engine(p)
+    eng.upload(R=R, V=V, psi=psi, tPart=np.zeros(n), t=0.0, substep=0)
+    eng.upload_forces(np.zeros((3, n)))
+    eng.step_qstep(nsub)
+    s = eng.download()
+    Ro, Vo, psio, tpo, t = R.copy(), V.copy(), psi.copy(), np.zeros(n), 0.0
+    Fo = np.zeros((3, n))
+    for k in range(nsub):
+        oracle.step_su(Ro, Vo, Fo, p.L, qp.dtq, t)
+        vx = Vo[0].copy()
+        t, _ = oracle.qstep12(psio, vx, tpo, t, qp, philox_uniforms(seed, traj, n, k))
+        Vo[0] = vx
+    assert np.abs(s["psi"] - psio).max() <= AMP_TOL
+    assert np.abs((s["psi"] ** 2).sum(axis=(1, 2)) - 1.0).max() <= 1e-14
+    assert np.array_equal(s["tPart"] == 0.0, tpo == 0.0) and (tpo == 0.0).any()   # same jumps, and there were some
+    assert np.abs(s["V"] - Vo).max() <= 1e-12
