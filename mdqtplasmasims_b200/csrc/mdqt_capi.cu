@@ -188,7 +188,10 @@ static void plan_force(mdqt_handle* h) {
     double best_t = model(tiles128 * h->nsplit, 4 * h->jsub, (double)h->jlen / h->jsub, h->nsplit);
     for (int js = 8; js >= 4; js /= 2)
       for (int ns = 1; ns <= 16; ns++) {
-        const int jlen = ((N + ns - 1) / ns + 7) & ~7;
+        // chunk length = a multiple of (in-CTA groups x loop unroll = js x 8): every warp's share is whole unrolled
+        // iterations (the scalar remainder loop has no ILP and all warps reach it together)
+        const int q = js * 8;
+        const int jlen = ((N + ns - 1) / ns + q - 1) / q * q;
         const int real_ns = (N + jlen - 1) / jlen;
         if (real_ns != ns) continue;
         const double t = model(tiles32 * ns, js, (double)jlen / js, ns);
