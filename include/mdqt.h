@@ -57,7 +57,10 @@ typedef struct mdqt_params {
   int32_t substeps_per_md; /* plasmaToQuantumTimestepRatio (SU:83) */
   int32_t renormalize;  /* reNormalizewvFns (SU:74) */
   int32_t quad;         /* 7-level only: circular-pump coupling mask of MC408Q:596 */
-  int32_t reserved;
+  int32_t plan_n;       /* 0, or the NOMINAL ion number (the reference's N0) that fixes the summation order of the force
+                           kernel and the lane mapping of the substep kernel: handles created with the same plan_n give
+                           the same bits for a trajectory whether it runs alone or batched with others (n_traj > 1),
+                           whatever each trajectory's actual ion count. 0: planned from n_ions and n_traj for speed. */
   double L;             /* box length (SU:297, MD:73) */
   double kappa;         /* 1/lDeb = sqrt(3 Ge) (SU:295) or kappa (MD:67) */
   double rcut;          /* L/2 (SU:195, MD:74) */
@@ -101,6 +104,17 @@ int mdqt_upload_forces(mdqt_handle* h, const double* F, int ld);
 int mdqt_download_forces(mdqt_handle* h, double* F, int ld);
 int mdqt_set_time(mdqt_handle* h, double t, uint64_t substep_index); /* global t (SU:114) and RNG substep counter */
 int mdqt_get_time(mdqt_handle* h, double* t, uint64_t* substep_index);
+
+/* Ensembles whose jobs drew different ion numbers (every reference job draws N ~ Binomial around N0, SU:299-337): trajectory
+ * b of the batch holds n_ions[b] <= mdqt_params.n_ions ions (the handle's capacity; host arrays keep the capacity as their
+ * stride, entries beyond n_ions[b] are ignored). Honoured by mdqt_forces, mdqt_substeps, mdqt_md_steps(_host), mdqt_epot,
+ * mdqt_diagnostics, mdqt_vel_dist and mdqt_populations; the MD-/FZ-family entry points return MDQT_ESTATE while counts are
+ * set. NULL restores "all trajectories hold n_ions". */
+int mdqt_set_ion_counts(mdqt_handle* h, const int32_t* n_ions /*[n_traj]*/);
+/* One Philox key per trajectory instead of mdqt_params.seed (the reference seeds every job of a SLURM array from
+ * time + job, SU:1219): trajectory b then draws exactly what a single-trajectory handle with seed = seeds[b] and
+ * traj0 = traj0 + b draws. NULL restores the common seed. */
+int mdqt_set_traj_seeds(mdqt_handle* h, const uint64_t* seeds /*[n_traj]*/);
 
 /* forces() (SU:192-236) / calculateAccelerations() (MD:387-448): all-pairs minimum-image Yukawa, r < L/2. */
 int mdqt_forces(mdqt_handle* h);
@@ -178,14 +192,18 @@ void* mdqt_device_ptr(mdqt_handle* h, int which);
 int mdqt_device_ld(mdqt_handle* h);
 void* mdqt_stream(mdqt_handle* h);
 
-/* After an external write into the device R buffer (NCCL all-gather): tell the handle whether all coordinates
- * lie in [0,L] (1: exact single-shift minimum image; 0: general rint path). */
+/* After an external write into the device R buffer (e.g. the caller's own NCCL all-gather): tells the handle that R
+ * changed, so the periodic fixed-point copy read by the pair kernels is refreshed before the next force evaluation. The
+ * `wrapped` argument is ignored (the fixed-point minimum image is exact for wrapped and unwrapped coordinates alike). */
 int mdqt_mark_wrapped(mdqt_handle* h, int wrapped);
 /* The j-range decomposition of the force kernel (a function of n_ions and n_traj only). */
 int mdqt_force_plan(mdqt_handle* h, int* nsplit, int* jlen);
 
-/* Per-kernel device timing of the most recent mdqt_md_steps call (ms, averaged per launch), measured with CUDA
- * events on the handle's stream when profiling is enabled. which: 0 = force kernel, 1 = substep kernel. */
+/* Per-kernel device timing of the most recent mdqt_md_steps call (ms, averaged per launch).
+ *   on = 1: a CUDA-event pair around every launch on the handle's stream (MD steps are then issued as stream launches);
+ *   on = 2: %globaltimer stamps written by the kernels themselves INSIDE the replayed CUDA graph (earliest CTA start to
+ *           latest CTA end of every launch) -- the durations as they are in production, plus the gaps between the kernels.
+ * which: 0 = force kernel, 1 = substep kernel, 2 = gap force -> substep, 3 = gap substep -> next force (2, 3: on = 2 only). */
 int mdqt_enable_timing(mdqt_handle* h, int on);
 int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* launches);
 /* FP64 FMA-chain microbenchmark on the handle's device: returns achieved TFLOP/s (2 flop per DFMA). */

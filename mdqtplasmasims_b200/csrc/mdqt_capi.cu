@@ -43,14 +43,23 @@ struct mdqt_handle {
   double *forced_cu, *forced_cn;
   QTConsts qc;
   double t; uint64_t substep, vv_step;
-  int nsplit, jlen, itiles, ipt, jsub, rg;
-  bool timing;
+  int nsplit, jlen, itiles, ipt, jsub, rg, items;
+  int* nb;              // [B] per-trajectory ion counts on the device (ensembles with unequal N) or null
+  std::vector<int> nb_host;
+  uint64_t* seeds;      // [B] per-trajectory Philox keys or null
+  int timing;  // 0 off; 1 = CUDA-event pair around every stream launch; 2 = %globaltimer stamps inside the replayed graph
+  unsigned long long* stamps; size_t stamps_cap;  // [launch]{min start, max end} ns
   std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
   size_t ev_used;
-  double time_ms[2]; int time_n[2];
+  double time_ms[4]; int time_n[4];  // force kernel, substep kernel, gap force->substep, gap substep->force
   double* clock;                    // device {t, substep index}: the simulation clock inside replayed graphs
   std::vector<GraphEntry> graphs;   // small cache keyed by nsteps
 };
+
+__global__ void k_init_stamps(unsigned long long* s, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) { s[2 * k] = ~0ULL; s[2 * k + 1] = 0ULL; }
+}
 
 __global__ void k_set_clock(double* clock, double t, unsigned long long substep, unsigned long long vv_step) {
   clock[0] = t;
@@ -142,7 +151,43 @@ int mdqt_params_ts(mdqt_params* p, int n_ions, double detuning, double Om) {
 
 // j-range decomposition: a function of (N, B) only, so that every rank of a row-decomposed run sums the same
 // j-chunks in the same order (bitwise identical forces for any GPU count).
+// Item-walking kernel (k_pairs_items): chunk length for `np` ions, chosen for ONE trajectory on the chip's 148 x 2 x 8
+// resident warps -- the latency-critical case; a batch walks B times as many equal items whatever the choice. A function of
+// np alone (mdqt_params.plan_n, else n_ions): not of the batch size, the row range or the environment.
+static int plan_items_jlen(int np) {
+  const long long W = 148LL * 2 * 8;
+  const long long G = (np + 31) / 32;
+  double best = 1e300;
+  int best_jl = 8;
+  for (int jl = 8; jl <= 256; jl += 8) {
+    const long long nch = (np + jl - 1) / jl;
+    const long long rounds = (G * nch + W - 1) / W;
+    // per item: jl pair iterations + ~14 iterations' worth of tile wait, partial store, fence and arrival; the last warp of
+    // a group fetches the partials in batches of 12 (one L2 round trip ~ 6 iterations each)
+    const double cost = (double)rounds * (jl + 14) + (nch > 1 ? 6.0 * ((nch + 11) / 12) : 0.0);
+    if (cost < best) { best = cost; best_jl = jl; }
+  }
+  return best_jl;
+}
+constexpr int kItemsMaxN = 8192;  // beyond this the partial-sum buffer (chunks x 3 x N) grows and CTA tiles win anyway
+
 static void plan_force(mdqt_handle* h) {
+  h->items = 0;
+  {
+    const int np = h->p.plan_n > 0 ? h->p.plan_n : h->N;
+    const char* e = getenv("MDQT_K1_ITEMS");  // developer knob (A/B runs): 0 = CTA-tile kernel everywhere
+    const bool off = e && e[0] == '0' && h->p.plan_n == 0;
+    // the chunk length must cover every trajectory's ions in <= 64 chunks even when n_ions exceeds the nominal plan_n
+    const long long total_items = (long long)h->B * ((h->nrows + 31) / 32) * ((h->N + 7) / 8);  // bound for any chunk length
+    if (np <= kItemsMaxN && h->N <= 2 * np && total_items < (1LL << 24) && !off) {
+      h->items = 1;
+      h->jlen = plan_items_jlen(np);
+      h->nsplit = (h->N + h->jlen - 1) / h->jlen;
+      h->ipt = 1; h->jsub = 1; h->rg = 32;
+      h->itiles = (h->nrows + 31) / 32;
+      return;
+    }
+  }
   // Cost model (fitted to B200 timings, profiles/): the kernel is issue-bound, so an SM's time is the work of the
   // CTAs assigned to it -- ceil(ctas/148) x (jlen + fixed CTA overhead) x rows per thread -- as long as >= 4 CTAs
   // are co-resident; two rows per thread amortise the shared-memory reads (~3 % fewer issue slots per pair).
@@ -245,8 +290,9 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
   h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
   h->gr_counts = nullptr; h->vstore = h->ac_partials = h->ac_out = nullptr; h->vstore_T = 0;
-  h->clock = nullptr;
-  h->timing = false; h->ev_used = 0; h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
+  h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr;
+  h->timing = 0; h->ev_used = 0; h->stamps = nullptr; h->stamps_cap = 0;
+  for (int k = 0; k < 4; k++) { h->time_ms[k] = 0; h->time_n[k] = 0; }
   plan_force(h);
   if (h->S) fill_qt_consts(h->qc, h->S, p->Om, p->OmDP, p->dR, p->vKick, p->vKickDP, p->dtq, p->g2E, p->quad);
   upload_exp_table();
@@ -292,6 +338,9 @@ int mdqt_destroy(mdqt_handle* h) {
   for (double* b : bufs) if (b) cudaFree(b);
   if (h->tagged) cudaFree(h->tagged);
   if (h->clock) cudaFree(h->clock);
+  if (h->nb) cudaFree(h->nb);
+  if (h->stamps) cudaFree(h->stamps);
+  if (h->seeds) cudaFree(h->seeds);
   for (GraphEntry& g : h->graphs) cudaGraphExecDestroy(g.exec);
   if (h->gr_counts) cudaFree(h->gr_counts);
   if (h->vstore) cudaFree(h->vstore);
@@ -388,12 +437,57 @@ int mdqt_get_time(mdqt_handle* h, double* t, uint64_t* substep_index) {
   return MDQT_OK;
 }
 
+int mdqt_set_ion_counts(mdqt_handle* h, const int32_t* n_ions) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!n_ions) {
+    if (h->nb) { cudaFree(h->nb); h->nb = nullptr; }
+    h->nb_host.clear();
+  } else {
+    if (h->S != MDQT_SCHEME_SR12 && h->S != MDQT_SCHEME_NONE) return fail(MDQT_ESTATE, "per-trajectory ion counts need the 12-level scheme (or none)");
+    if (h->nrows != h->N) return fail(MDQT_ESTATE, "per-trajectory ion counts on a row-decomposed handle");
+    if (!h->items) return fail(MDQT_ESTATE, "per-trajectory ion counts need the item-walking force plan (n_ions <= 8192)");
+    for (int b = 0; b < h->B; b++)
+      if (n_ions[b] < 1 || n_ions[b] > h->N) return fail(MDQT_EINVAL, "ion count outside [1, n_ions]");
+    if (!h->nb) CU(cudaMalloc((void**)&h->nb, sizeof(int) * (size_t)h->B));
+    CU(cudaMemcpy(h->nb, n_ions, sizeof(int) * (size_t)h->B, cudaMemcpyHostToDevice));
+    h->nb_host.assign(n_ions, n_ions + h->B);
+  }
+  for (GraphEntry& g : h->graphs) cudaGraphExecDestroy(g.exec);  // captured arguments carried the old pointer
+  h->graphs.clear();
+  return MDQT_OK;
+}
+
+int mdqt_set_traj_seeds(mdqt_handle* h, const uint64_t* seeds) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!seeds) {
+    if (h->seeds) { cudaFree(h->seeds); h->seeds = nullptr; }
+  } else {
+    if (!h->seeds) CU(cudaMalloc((void**)&h->seeds, sizeof(uint64_t) * (size_t)h->B));
+    CU(cudaMemcpy(h->seeds, seeds, sizeof(uint64_t) * (size_t)h->B, cudaMemcpyHostToDevice));
+  }
+  for (GraphEntry& g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+  return MDQT_OK;
+}
+
+// entry points whose kernels assume one ion count for the whole batch
+#define NEED_UNIFORM_N(h) do { if ((h)->nb) return fail(MDQT_ESTATE, "not available with per-trajectory ion counts (mdqt_set_ion_counts)"); } while (0)
+// entry points that advance positions more than once per call: on a row-decomposed handle the remote rows of R would be
+// stale from the second force evaluation on (one force call per position exchange)
+#define NEED_ALL_ROWS(h, what) do { if ((h)->nrows != (h)->N) return fail(MDQT_ESTATE, what ": a row-decomposed handle allows one force evaluation per position exchange (use mdqt_comm_init, or call mdqt_forces / mdqt_substeps and exchange R yourself)"); } while (0)
+
 static ForceArgs force_args(mdqt_handle* h) {
   ForceArgs a;
   memset(&a, 0, sizeof(a));  // padding included: graph entries are compared bytewise
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
+  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb;
+  a.mg_chunk = ((1ULL << 40) + h->nsplit - 1) / h->nsplit; a.mg_gcap = ((1ULL << 40) + a.gcap - 1) / a.gcap;
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   a.half_l = (h->p.rcut == h->p.L / 2.) ? 1 : 0;
@@ -424,6 +518,8 @@ static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step, int do_kick) {
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows; a.traj0 = p.traj0;
   a.nsub = nsub; a.do_step = do_step; a.do_kick = do_kick; a.do_tpart = do_kick;  // tPart lives where the kick does (SU, TS)
   a.scheme = h->S; a.S = h->S; a.renorm = p.renormalize; a.quad = p.quad;
+  a.nb = h->nb; a.seeds = h->seeds;
+  a.lanes = p.plan_n > 0 ? 2 : 0;  // batch-reproducible mode: one lane mapping whatever the batch size
   a.t0 = h->t; a.substep0 = h->substep; a.seed = p.seed;
   a.L = p.L; a.dtq = p.dtq;
   a.detuning = p.detuning; a.detuningDP = p.detuningDP; a.Om = p.Om; a.OmDP = p.OmDP; a.dR = p.dR; a.kRat = p.kRat;
@@ -477,6 +573,7 @@ int mdqt_qsteps(mdqt_handle* h, int nsub) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5 && h->S != MDQT_SCHEME_V3)
     return fail(MDQT_ESTATE, "mdqt_qsteps needs the 7-, 5- or 3-level scheme");
+  NEED_UNIFORM_N(h);
   if (nsub < 0) return fail(MDQT_EINVAL, "nsub < 0");
   if (nsub == 0) return MDQT_OK;
   CU(cudaSetDevice(h->p.device));
@@ -502,6 +599,17 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
   fa.clock = h->clock; fa.clock_dtq = h->p.dtq; fa.clock_advance = 0;
   QTArgs qa = qt_args(h, ratio, 1, 1);
   qa.clock = h->clock; qa.t0 = 0.0; qa.substep0 = 0;
+  const bool stamp = h->timing == 2;
+  if (stamp) {
+    const size_t need = (size_t)nsteps * 2;
+    if (h->stamps_cap < need) {
+      if (h->stamps) cudaFree(h->stamps);
+      h->stamps = nullptr; h->stamps_cap = 0;
+      CU(cudaMalloc((void**)&h->stamps, need * 2 * sizeof(unsigned long long)));
+      h->stamps_cap = need;
+    }
+    fa.stamp = h->stamps; qa.stamp = h->stamps + 2;  // per-launch slots are set at capture; these key the cached graph
+  }
   cudaGraphExec_t exec = nullptr;
   for (GraphEntry& g : h->graphs)
     if (g.nsteps == nsteps && !memcmp(&g.fa, &fa, sizeof(fa)) && !memcmp(&g.qa, &qa, sizeof(qa))) { exec = g.exec; break; }
@@ -511,8 +619,10 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
     for (int k = 0; k < nsteps; k++) {
       ForceArgs fk = fa;
       fk.clock_advance = k ? ratio : 0;  // the clock is set for step 0 before the replay; step k-1's substeps are added here
+      QTArgs qk = qa;
+      if (stamp) { fk.stamp = h->stamps + (size_t)4 * k; qk.stamp = h->stamps + (size_t)4 * k + 2; }
       launch_forces(fk, h->stream);
-      launch_substeps(qa, h->qc, h->S, h->stream);
+      launch_substeps(qk, h->qc, h->S, h->stream);
     }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
@@ -525,10 +635,24 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
     h->graphs.push_back(GraphEntry{nsteps, exec, fa, qa, v0});
   }
   k_set_clock<<<1, 1, 0, h->stream>>>(h->clock, h->t, (unsigned long long)h->substep, (unsigned long long)h->vv_step);
+  if (stamp) k_init_stamps<<<(2 * nsteps + 127) / 128, 128, 0, h->stream>>>(h->stamps, 2 * nsteps);
   CU(cudaGraphLaunch(exec, h->stream));
   for (long long s = 0; s < (long long)nsteps * ratio; s++) h->t += h->p.dtq;  // host mirror: the same repeated addition
   h->substep += (uint64_t)nsteps * ratio;
   CU(cudaGetLastError());
+  if (stamp) {  // per-kernel durations and the gaps between them INSIDE the replayed graph
+    std::vector<unsigned long long> st((size_t)nsteps * 4);
+    CU(cudaMemcpyAsync(st.data(), h->stamps, st.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; k++) { h->time_ms[k] = 0; h->time_n[k] = 0; }
+    for (int k = 0; k < nsteps; k++) {
+      const unsigned long long f0 = st[4 * k], f1 = st[4 * k + 1], q0 = st[4 * k + 2], q1 = st[4 * k + 3];
+      h->time_ms[0] += (double)(f1 - f0) * 1e-6; h->time_n[0]++;
+      h->time_ms[1] += (double)(q1 - q0) * 1e-6; h->time_n[1]++;
+      h->time_ms[2] += ((double)q0 - (double)f1) * 1e-6; h->time_n[2]++;
+      if (k + 1 < nsteps) { h->time_ms[3] += ((double)st[4 * k + 4] - (double)q1) * 1e-6; h->time_n[3]++; }
+    }
+  }
   return MDQT_OK;
 }
 
@@ -536,20 +660,22 @@ int mdqt_md_steps(mdqt_handle* h, int nsteps) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (h->S != MDQT_SCHEME_SR12) return fail(MDQT_ESTATE, "mdqt_md_steps needs the 12-level scheme");
   if (h->p.substeps_per_md < 1) return fail(MDQT_EINVAL, "substeps_per_md < 1");
+  if (nsteps > 1) NEED_ALL_ROWS(h, "mdqt_md_steps(n > 1)");
   CU(cudaSetDevice(h->p.device));
-  if (nsteps >= 2 && !h->timing && !h->forced_u && graphs_enabled()) return md_steps_graph(h, nsteps);
-  if (h->timing) h->ev_used = 0;
+  if (nsteps >= 2 && h->timing != 1 && !h->forced_u && graphs_enabled()) return md_steps_graph(h, nsteps);
+  const bool timing = h->timing == 1;
+  if (timing) h->ev_used = 0;
   for (int k = 0; k < nsteps; k++) {
     refresh_fixed(h);
-    if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
+    if (timing) CU(cudaEventRecord(next_event(h), h->stream));
     launch_forces(force_args(h), h->stream);
-    if (h->timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
+    if (timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
     int rc = enqueue_substeps(h, h->p.substeps_per_md, 1, 1);
     if (rc) return rc;
-    if (h->timing) CU(cudaEventRecord(next_event(h), h->stream));
+    if (timing) CU(cudaEventRecord(next_event(h), h->stream));
   }
   CU(cudaGetLastError());
-  if (h->timing) {
+  if (timing) {
     CU(cudaStreamSynchronize(h->stream));
     h->time_ms[0] = h->time_ms[1] = 0; h->time_n[0] = h->time_n[1] = 0;
     for (size_t k = 0; k + 3 < h->ev_used; k += 4) {
@@ -564,6 +690,7 @@ int mdqt_md_steps(mdqt_handle* h, int nsteps) {
 
 int mdqt_md_steps_host(mdqt_handle* h, int nsteps, double* R, double* V, double* psi, double* tPart, int ld) {
   if (!h || !R || !V || !psi || !tPart) return fail(MDQT_EINVAL, "null argument");
+  NEED_ALL_ROWS(h, "mdqt_md_steps_host");
   int rc = mdqt_upload_state(h, R, V, psi, tPart, ld);
   if (rc) return rc;
   rc = mdqt_md_steps(h, nsteps);
@@ -587,7 +714,7 @@ int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_diag_partial and all-reduce the sums");
   CU(cudaSetDevice(h->p.device));
   refresh_fixed(h);
-  launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
+  launch_diag(h->V, h->N, h->ld, h->B, h->nb, h->scalars, h->stream);
   launch_epot(force_args(h), h->epot_partials, h->scalars + (size_t)h->B * 8, h->stream);
   std::vector<double> s((size_t)h->B * 16);
   CU(cudaMemcpyAsync(s.data(), h->scalars, s.size() * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -602,6 +729,7 @@ int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
 
 int mdqt_diag_partial(mdqt_handle* h, const double* vx_mean, double* sums) {
   if (!h || !sums) return fail(MDQT_EINVAL, "null argument");
+  NEED_UNIFORM_N(h);
   CU(cudaSetDevice(h->p.device));
   refresh_fixed(h);
   double* mean_dev = nullptr;
@@ -624,6 +752,7 @@ int mdqt_diag_partial(mdqt_handle* h, const double* vx_mean, double* sums) {
 
 int mdqt_vel_dist_partial(mdqt_handle* h, const double* vx_mean, double* pvel) {
   if (!h || !pvel || !vx_mean) return fail(MDQT_EINVAL, "null argument");
+  NEED_UNIFORM_N(h);
   CU(cudaSetDevice(h->p.device));
   std::vector<double> m((size_t)h->B * 8, 0.0);
   for (int b = 0; b < h->B; b++) m[(size_t)b * 8] = vx_mean[b];
@@ -639,8 +768,8 @@ int mdqt_vel_dist(mdqt_handle* h, double* pvel) {
   if (!h || !pvel) return fail(MDQT_EINVAL, "null argument");
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_vel_dist_partial and all-reduce the bins");
   CU(cudaSetDevice(h->p.device));
-  launch_diag(h->V, h->N, h->ld, h->B, nullptr, h->scalars, h->stream);
-  launch_vel_dist(h->V, h->scalars, h->N, h->ld, h->B, h->pvel, h->stream);
+  launch_diag(h->V, h->N, h->ld, h->B, h->nb, h->scalars, h->stream);
+  launch_vel_dist(h->V, h->scalars, h->N, h->ld, h->B, h->nb, h->pvel, h->stream);
   CU(cudaMemcpyAsync(pvel, h->pvel, (size_t)h->B * 3 * kVelBins * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
@@ -649,6 +778,7 @@ int mdqt_vel_dist(mdqt_handle* h, double* pvel) {
 
 int mdqt_populations(mdqt_handle* h, double* pops) {
   if (!h || !pops) return fail(MDQT_EINVAL, "null argument");
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_populations: a row-decomposed handle holds the wavefunctions of its own rows only (use mdqt_populations_rows)");
   if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
   CU(cudaSetDevice(h->p.device));
   launch_populations(h->psi, h->S, h->N, h->ld, h->B, h->pops, h->stream);
@@ -665,8 +795,10 @@ int mdqt_vv_steps(mdqt_handle* h, int nsteps, int qsteps, double dt, double coll
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (!(dt > 0) || nsteps < 0 || qsteps < 0) return fail(MDQT_EINVAL, "dt must be > 0, nsteps and qsteps >= 0");
   if (qsteps > 0 && h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5) return fail(MDQT_ESTATE, "pump sweeps need the 7- or 5-level scheme");
+  NEED_UNIFORM_N(h);
+  NEED_ALL_ROWS(h, "mdqt_vv_steps");
   CU(cudaSetDevice(h->p.device));
-  const bool graph = nsteps >= 2 && !h->timing && !h->forced_u && !h->forced_cu && graphs_enabled();
+  const bool graph = nsteps >= 2 && h->timing != 1 && !h->forced_u && !h->forced_cu && graphs_enabled();
   if (!graph) {
     for (int k = 0; k < nsteps; k++) {
       if (qsteps > 0) { int rc = mdqt_qsteps(h, qsteps); if (rc) return rc; }
@@ -725,6 +857,8 @@ int mdqt_vv_steps(mdqt_handle* h, int nsteps, int qsteps, double dt, double coll
 int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v, int laser, double laser_coeff) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (!(dt > 0)) return fail(MDQT_EINVAL, "dt must be > 0");
+  NEED_UNIFORM_N(h);
+  NEED_ALL_ROWS(h, "mdqt_vv_step");
   CU(cudaSetDevice(h->p.device));
   std::swap(h->F, h->oldF);  // oldA = A (MD:505-506)
   VVArgs a;
@@ -747,6 +881,8 @@ int mdqt_vv_step(mdqt_handle* h, double dt, double collisionFreq, double sigma_v
 int mdqt_leapfrog_step(mdqt_handle* h, double dt) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (!(dt > 0)) return fail(MDQT_EINVAL, "dt must be > 0");
+  NEED_UNIFORM_N(h);
+  NEED_ALL_ROWS(h, "mdqt_leapfrog_step");
   CU(cudaSetDevice(h->p.device));
   LFArgs a;
   a.R = h->R; a.V = h->V; a.F = h->F; a.Rfix = h->Rfix;
@@ -780,6 +916,8 @@ int mdqt_advance_time(mdqt_handle* h, int nsub) {
 int mdqt_tag_particles(mdqt_handle* h, int32_t* tagged, int32_t* n_tagged) {
   if (!h || !n_tagged) return fail(MDQT_EINVAL, "null argument");
   if (h->S != MDQT_SCHEME_SR7 && h->S != MDQT_SCHEME_CA5) return fail(MDQT_ESTATE, "tagging needs the 7- or 5-level scheme");
+  NEED_UNIFORM_N(h);
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_tag_particles: a row-decomposed handle holds the wavefunctions of its own rows only");
   CU(cudaSetDevice(h->p.device));
   const size_t n = (size_t)h->B * h->N;
   if (!h->tagged) CU(cudaMalloc((void**)&h->tagged, sizeof(int) * (n + h->B)));
@@ -805,6 +943,8 @@ int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u) {
 
 int mdqt_vaf(mdqt_handle* h, int start, double* vaf) {
   if (!h || !vaf) return fail(MDQT_EINVAL, "null argument");
+  NEED_UNIFORM_N(h);
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_vaf: a row-decomposed handle holds the velocities of its own rows only");
   CU(cudaSetDevice(h->p.device));
   if (!h->vhold) {
     if (!start) return fail(MDQT_ESTATE, "mdqt_vaf: no interval started");
@@ -824,6 +964,7 @@ int mdqt_pair_correlation(mdqt_handle* h, double step, double rmax, int nbins, d
   if (!(step > 0) || nbins != (int)(rmax / step) || nbins < 1 || nbins > gr_max_bins())
     return fail(MDQT_EINVAL, "nbins must equal (int)(rmax/step) and lie in [1, 2048]");
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "pair correlation needs a handle that owns all rows");
+  NEED_UNIFORM_N(h);
   CU(cudaSetDevice(h->p.device));
   if (!h->gr_counts) CU(cudaMalloc((void**)&h->gr_counts, sizeof(unsigned long long) * (size_t)h->B * gr_max_bins()));
   launch_gr(h->R, h->N, h->ld, h->B, h->p.L, step, nbins, h->gr_counts, h->stream);
@@ -846,6 +987,7 @@ int mdqt_pair_correlation(mdqt_handle* h, double step, double rmax, int nbins, d
 int mdqt_vstore_begin(mdqt_handle* h, int T) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (T < 1 || T > 5000) return fail(MDQT_EINVAL, "T must lie in [1, 5000]");
+  NEED_UNIFORM_N(h);
   CU(cudaSetDevice(h->p.device));
   CU(cudaStreamSynchronize(h->stream));
   for (double** ptr : {&h->vstore, &h->ac_partials, &h->ac_out}) if (*ptr) { cudaFree(*ptr); *ptr = nullptr; }
@@ -961,7 +1103,7 @@ void* mdqt_stream(mdqt_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int mdqt_mark_wrapped(mdqt_handle* h, int wrapped) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
-  (void)wrapped;       // the fixed-point pair kernel handles any coordinates; what matters is that R changed
+  (void)wrapped;  // kept for ABI stability: the fixed-point pair kernel is exact for wrapped and unwrapped coordinates alike
   h->rfix_dirty = 1;
   return MDQT_OK;
 }
@@ -975,11 +1117,11 @@ int mdqt_force_plan(mdqt_handle* h, int* nsplit, int* jlen) {
 
 int mdqt_enable_timing(mdqt_handle* h, int on) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
-  h->timing = on != 0;
+  h->timing = (on == 2) ? 2 : (on != 0);
   return MDQT_OK;
 }
 int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* launches) {
-  if (!h || which < 0 || which > 1) return fail(MDQT_EINVAL, "bad argument");
+  if (!h || which < 0 || which > 3) return fail(MDQT_EINVAL, "bad argument");
   if (ms_per_launch) *ms_per_launch = h->time_n[which] ? h->time_ms[which] / h->time_n[which] : 0.0;
   if (launches) *launches = h->time_n[which];
   return MDQT_OK;

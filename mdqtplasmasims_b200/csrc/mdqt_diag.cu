@@ -29,9 +29,11 @@ __device__ __forceinline__ double block_sum_1024(double v, double* sred) {
 }
 
 // one CTA per trajectory; out[b][0..3] = vx_avg, ekin_x, ekin_y, ekin_z
-__global__ void __launch_bounds__(1024) k_diag(const double* __restrict__ V, int N, int ld, double* __restrict__ out) {
+__global__ void __launch_bounds__(1024) k_diag(const double* __restrict__ V, int Ncap, int ld, const int* __restrict__ nb,
+                                               double* __restrict__ out) {
   __shared__ double sred[32];
   const int b = blockIdx.x;
+  const int N = nb ? nb[b] : Ncap;
   const double* vx = V + (size_t)b * 3 * ld;
   const double* vy = vx + ld;
   const double* vz = vy + ld;
@@ -51,8 +53,8 @@ __global__ void __launch_bounds__(1024) k_diag(const double* __restrict__ V, int
   }
 }
 
-void launch_diag(const double* V, int N, int ld, int B, double*, double* diag_out, cudaStream_t s) {
-  k_diag<<<B, 1024, 0, s>>>(V, N, ld, diag_out);
+void launch_diag(const double* V, int N, int ld, int B, const int* nb, double* diag_out, cudaStream_t s) {
+  k_diag<<<B, 1024, 0, s>>>(V, N, ld, nb, diag_out);
 }
 
 // Row-decomposed runs: every rank owns the velocities of its rows only, so output() needs partial sums that
@@ -79,9 +81,10 @@ void launch_diag_partial(const double* V, int row0, int nrows, int ld, int B, co
 }
 
 // grid: (ceil(2001/8), 3, B); 256 threads = 8 bins x 32 lanes; lanes stride over ions [row0, row0 + nrows)
-__global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, const double* __restrict__ diag, int N, int ld,
-                                                  double* __restrict__ pvel, int row0 = 0) {
+__global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, const double* __restrict__ diag, int Ncap, int ld,
+                                                  double* __restrict__ pvel, int row0, const int* __restrict__ nb) {
   const int b = blockIdx.z, c = blockIdx.y;
+  const int N = nb ? nb[b] : Ncap;
   const int bin = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const double* v = V + ((size_t)b * 3 + c) * ld + row0;
@@ -100,14 +103,14 @@ __global__ void __launch_bounds__(256) k_vel_dist(const double* __restrict__ V, 
   if (lane == 0 && bin < kVelBins) pvel[((size_t)b * 3 + c) * kVelBins + bin] = s / (6.0 * sqrt(2 * M_PI * 0.002 * 0.002));
 }
 
-void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s) {
+void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, const int* nb, double* pvel, cudaStream_t s) {
   dim3 grid((kVelBins + 7) / 8, 3, B);
-  k_vel_dist<<<grid, 256, 0, s>>>(V, diag_out, N, ld, pvel);
+  k_vel_dist<<<grid, 256, 0, s>>>(V, diag_out, N, ld, pvel, 0, nb);
 }
 // the same KDE restricted to rows [row0,row0+nrows) about an externally supplied <v_x> (diag[b*8]): additive over ranks
 void launch_vel_dist_rows(const double* V, const double* diag, int row0, int nrows, int ld, int B, double* pvel, cudaStream_t s) {
   dim3 grid((kVelBins + 7) / 8, 3, B);
-  k_vel_dist<<<grid, 256, 0, s>>>(V, diag, nrows, ld, pvel, row0);
+  k_vel_dist<<<grid, 256, 0, s>>>(V, diag, nrows, ld, pvel, row0, nullptr);
 }
 
 // Zfunc() (FZ408L:938-961): out[b] = sum_j (1/N) Vhold_x[j] V_x[j], fixed-order block reduction; one CTA per trajectory

@@ -2,9 +2,20 @@
 // on top of the C ABI: same user inputs (by name, as options instead of edit-and-recompile), same directory tree,
 // same output and restart files, hot path on the GPU.
 //
-//   mdqt_run <job> [--Ge 0.1] [--density 2] [--sig0 4] [--Te 19] [--fracOfSig 0] [--N0 3500] [--detuning -1]
-//            [--detuningDP 1] [--Om 1] [--OmDP 1] [--saveDirectory dataLaserCool/] [--newRun 1] [--c0 0] [--tmax 30]
-//            [--reNormalizewvFns 0] [--sampleFreq 40] [--seed <time+job>] [--device 0] [--quiet]
+//   mdqt_run <job>  [options]                     one trajectory, exactly `./runFile <job>` of the reference (SU:1145)
+//   mdqt_run --jobs a-b [--batch 64] [--gpus 8]   the SLURM array of the reference (exampleSlurmFile.slurm:3,16:
+//                                                 `--array=a-b`, `srun exe $SLURM_ARRAY_TASK_ID`) on one box: jobs a..b are
+//                                                 dealt to the GPUs in contiguous blocks and advanced `batch` at a time in
+//                                                 one handle; every job draws its own N in init() (SU:299-337), keeps its own
+//                                                 seed (time + job, SU:1219, or --seed S -> S + job) and writes its own
+//                                                 job directory, byte-compatible with a single run of that job.
+//   options: [--Ge 0.1] [--density 2] [--sig0 4] [--Te 19] [--fracOfSig 0] [--N0 3500] [--detuning -1] [--detuningDP 1]
+//            [--Om 1] [--OmDP 1] [--saveDirectory dataLaserCool/] [--newRun 1] [--c0 0] [--tmax 30]
+//            [--reNormalizewvFns 0] [--sampleFreq 40] [--seed n] [--device 0] [--writers n] [--fast-single] [--quiet]
+//
+// A job gives the same bits whether it runs alone or inside any batch: the force summation plan and the substep kernel's
+// lane mapping are fixed by N0 (mdqt_params.plan_n), not by the batch. --fast-single lifts that for a lone job (the plan is
+// then chosen for speed from N and n_traj = 1; ~3 % faster, results differ in the last bits).
 #include "../../include/mdqt.h"
 #include "../../include/mdqt_io.h"
 #include <math.h>
@@ -12,18 +23,21 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
-// output() formats ~9500 text lines per call (3 x 2001 velocity bins + one line per ion, SU:958-1024): about 3 ms of
-// fprintf, as long as the 40 MD steps between two calls take on the GPU. A single writer thread does the formatting in
-// call order while the time loop keeps the GPU busy; the files are byte-for-byte what a synchronous writer produces.
+// output() formats ~9500 text lines per call and job (3 x 2001 velocity bins + one line per ion, SU:958-1024): about 3 ms
+// of fprintf, as long as the 40 MD steps between two calls take on the GPU for ONE trajectory -- and 64 times that for a
+// batch of 64. Writer threads do the formatting while the time loop keeps the GPU busy; a job's outputs always go to the
+// same writer, in call order, so its files are byte-for-byte what a synchronous writer produces.
 struct OutputJob {
   std::string dir;
   unsigned counter; int N;
@@ -36,7 +50,7 @@ class OutputWriter {
   ~OutputWriter() { finish(); }
   void push(OutputJob&& j) {
     std::unique_lock<std::mutex> lk(m_);
-    cv_space_.wait(lk, [this] { return q_.size() < 4; });  // bounded: at most 4 outputs in flight
+    cv_space_.wait(lk, [this] { return q_.size() < 16; });  // bounded: at most 16 outputs in flight per writer
     q_.push_back(std::move(j));
     cv_work_.notify_one();
   }
@@ -69,95 +83,121 @@ class OutputWriter {
   std::thread th_;
 };
 
-static void die(const char* what) {
-  fprintf(stderr, "mdqt_run: %s: %s\n", what, mdqt_last_error());
-  exit(1);
-}
-#define CK(call) do { if ((call) != 0) die(#call); } while (0)
-
-int main(int argc, char** argv) {
-  if (argc < 2) {
-    fprintf(stderr, "usage: mdqt_run <job> [--Ge x] [--density x] [--sig0 x] [--Te x] [--fracOfSig x] [--N0 n] [--detuning x]\n"
-                    "       [--detuningDP x] [--Om x] [--OmDP x] [--saveDirectory dir/] [--newRun 0|1] [--c0 n] [--tmax x]\n"
-                    "       [--reNormalizewvFns 0|1] [--sampleFreq n] [--seed n] [--device n] [--quiet]\n");
-    return 2;
-  }
-  // defaults = the reference's globals (SU:56-78)
-  std::map<std::string, std::string> opt = {
-      {"Ge", "0.1"}, {"density", "2"}, {"sig0", "4.0"}, {"Te", "19.0"}, {"fracOfSig", "0"}, {"N0", "3500"}, {"detuning", "-1"},
-      {"detuningDP", "1"}, {"Om", "1"}, {"OmDP", "1"}, {"saveDirectory", "dataLaserCool/"}, {"newRun", "1"}, {"c0", "0"},
-      {"tmax", "30"}, {"reNormalizewvFns", "0"}, {"sampleFreq", "40"}, {"seed", ""}, {"device", "0"}};
+struct Options {
+  double Ge = 0.1, density = 2, sig0 = 4.0, Te = 19.0, fracOfSig = 0, detuning = -1, detuningDP = 1, Om = 1, OmDP = 1, tmax = 30;
+  int N0 = 3500, newRun = 1, c0 = 0, renorm = 0, sampleFreq = 40, device = 0, writers = 0, fast_single = 0;
   bool quiet = false;
-  unsigned job = (unsigned)atof(argv[1]);  // SU:1145
-  for (int i = 2; i < argc; i++) {
-    std::string a = argv[i];
-    if (a == "--quiet") { quiet = true; continue; }
-    if (a.rfind("--", 0) != 0 || !opt.count(a.substr(2)) || i + 1 >= argc) { fprintf(stderr, "mdqt_run: bad option %s\n", a.c_str()); return 2; }
-    opt[a.substr(2)] = argv[++i];
-  }
-  const double Ge = atof(opt["Ge"].c_str()), density = atof(opt["density"].c_str()), sig0 = atof(opt["sig0"].c_str());
-  const double Te = atof(opt["Te"].c_str()), fracOfSig = atof(opt["fracOfSig"].c_str()), detuning = atof(opt["detuning"].c_str());
-  const double detuningDP = atof(opt["detuningDP"].c_str()), Om = atof(opt["Om"].c_str()), OmDP = atof(opt["OmDP"].c_str());
-  const double tmax = atof(opt["tmax"].c_str());
-  const int N0 = atoi(opt["N0"].c_str()), newRun = atoi(opt["newRun"].c_str()), sampleFreq = atoi(opt["sampleFreq"].c_str());
-  int c0 = atoi(opt["c0"].c_str());
-  const long seed = opt["seed"].empty() ? (long)((unsigned)time(NULL) + job) : atol(opt["seed"].c_str());  // SU:1219
-  const int ld = N0 + 1000;  // SU:126
+  long seed = 0;          // base seed
+  bool seed_add_job = true;  // job j is seeded with seed + j (the reference's time(NULL) + job, SU:1219)
+  std::string saveDirectory = "dataLaserCool/";
+};
 
-  char dir[1024];
-  if (mdqt_io_dirname(dir, sizeof(dir), opt["saveDirectory"].c_str(), Ge, density, sig0, Te, fracOfSig, detuning, detuningDP, Om,
-                      OmDP, N0, job, 1)) { fprintf(stderr, "mdqt_run: directory name too long\n"); return 1; }
+struct BatchResult { int ok = 0; long nsub = 0, nforce = 0, nout = 0; double wall = 0, ions = 0; };
 
-  std::vector<double> R(3 * (size_t)ld), V(3 * (size_t)ld), psi((size_t)ld * 24), tPart(ld, 0.0), vholder((size_t)3 * MDQT_NUM_VINTERVALS * ld, 0.0);
-  std::vector<double> pvel(3 * 2001), pops((size_t)ld * 3);
-  unsigned counter = 0;
+static std::mutex g_print;
+#define CKB(call)                                                                                        \
+  do {                                                                                                   \
+    if ((call) != 0) {                                                                                   \
+      std::lock_guard<std::mutex> lk_(g_print);                                                          \
+      fprintf(stderr, "mdqt_run: %s: %s\n", #call, mdqt_last_error());                                   \
+      if (h) mdqt_destroy(h);                                                                            \
+      return res;                                                                                        \
+    }                                                                                                    \
+  } while (0)
+
+// jobs job0 .. job0+B-1 in ONE handle on `device`: init()/readConditions() per job, the main loop, output() per job,
+// writeConditions() per job (SU:1139-1383)
+static BatchResult run_batch(const Options& o, unsigned job0, int B, int device, std::vector<std::unique_ptr<OutputWriter>>& writers) {
+  BatchResult res;
+  mdqt_handle* h = NULL;
+  const int ld = o.N0 + 1000;  // SU:126
+  std::vector<std::string> dirs(B);
+  std::vector<long> seeds(B);
+  std::vector<int32_t> Nb(B);
+  std::vector<unsigned> counter(B, 0);
+  std::vector<double> R((size_t)B * 3 * ld), V((size_t)B * 3 * ld), psi_ld((size_t)ld * 24), tp_ld(ld);
+  std::vector<std::vector<double>> psi_b(B), tp_b(B), vholder(B);
   double t = 0.0, L = 0, lDeb = 0;
-  int N;
-  if (newRun == 1) {
-    N = mdqt_io_init_su(seed, N0, Ge, ld, R.data(), V.data(), psi.data(), tPart.data(), &L, &lDeb);  // init(), SU:289-348
-    if (N < 0) { fprintf(stderr, "mdqt_run: more than N0+1000 ions drawn\n"); return 1; }
-    printf("%i\n", N);  // SU:338
-    c0 = -1;            // SU:347
-  } else {
-    N = mdqt_io_read_conditions(dir, c0, ld, R.data(), V.data(), psi.data(), &counter, &t, vholder.data());  // SU:785-916
-    if (N < 0) { fprintf(stderr, "mdqt_run: cannot read restart files for c0=%d in %s (%d)\n", c0, dir, N); return 1; }
+  int c0 = o.c0;
+  for (int b = 0; b < B; b++) {
+    const unsigned job = job0 + b;
+    char dir[1024];
+    if (mdqt_io_dirname(dir, sizeof(dir), o.saveDirectory.c_str(), o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning,
+                        o.detuningDP, o.Om, o.OmDP, o.N0, job, 1)) { fprintf(stderr, "mdqt_run: directory name too long\n"); return res; }
+    dirs[b] = dir;
+    seeds[b] = o.seed_add_job ? o.seed + (long)job : o.seed;
+    vholder[b].assign((size_t)3 * MDQT_NUM_VINTERVALS * ld, 0.0);
+    double* Rb = R.data() + (size_t)b * 3 * ld;
+    double* Vb = V.data() + (size_t)b * 3 * ld;
+    int N;
+    if (o.newRun == 1) {
+      N = mdqt_io_init_su(seeds[b], o.N0, o.Ge, ld, Rb, Vb, psi_ld.data(), tp_ld.data(), &L, &lDeb);  // init(), SU:289-348
+      if (N < 0) { fprintf(stderr, "mdqt_run: job %u drew more than N0+1000 ions\n", job); return res; }
+      { std::lock_guard<std::mutex> lk(g_print); printf("%i\n", N); }  // SU:338
+    } else {
+      double tb = 0;
+      N = mdqt_io_read_conditions(dir, o.c0, ld, Rb, Vb, psi_ld.data(), &counter[b], &tb, vholder[b].data());  // SU:785-916
+      if (N < 0) { fprintf(stderr, "mdqt_run: cannot read restart files for c0=%d in %s (%d)\n", o.c0, dir, N); return res; }
+      std::fill(tp_ld.begin(), tp_ld.end(), 0.0);  // tPart is not checkpointed by the reference (Q7)
+      t = tb;
+    }
+    Nb[b] = N;
+    psi_b[b].assign(psi_ld.begin(), psi_ld.begin() + (size_t)N * 24);
+    tp_b[b].assign(tp_ld.begin(), tp_ld.begin() + N);
+  }
+  if (o.newRun == 1) c0 = -1;  // SU:347
+  const int Ncap = *std::max_element(Nb.begin(), Nb.end());
+  // wavefunctions and tPart cross the ABI with the handle's capacity as their stride
+  std::vector<double> psi((size_t)B * Ncap * 24, 0.0), tPart((size_t)B * Ncap, 0.0);
+  for (int b = 0; b < B; b++) {
+    std::copy(psi_b[b].begin(), psi_b[b].end(), psi.begin() + (size_t)b * Ncap * 24);
+    std::copy(tp_b[b].begin(), tp_b[b].end(), tPart.begin() + (size_t)b * Ncap);
+    for (int i = Nb[b]; i < Ncap; i++) psi[((size_t)b * Ncap + i) * 24] = 1.0;  // padding ions: a harmless normalised state
   }
 
   mdqt_params p;
-  CK(mdqt_params_su(&p, Ge, density, sig0, Te, fracOfSig, detuning, detuningDP, Om, OmDP, N0, N));
-  p.traj0 = (int)job; p.seed = (uint64_t)seed; p.device = atoi(opt["device"].c_str());
-  p.renormalize = atoi(opt["reNormalizewvFns"].c_str());
-  mdqt_handle* h = NULL;
-  CK(mdqt_create(&p, &h));
-  CK(mdqt_upload_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
+  CKB(mdqt_params_su(&p, o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning, o.detuningDP, o.Om, o.OmDP, o.N0, Ncap));
+  p.n_traj = B; p.traj0 = (int)job0; p.seed = (uint64_t)seeds[0]; p.device = device;
+  p.renormalize = o.renorm;
+  p.plan_n = (B == 1 && o.fast_single) ? 0 : o.N0;
+  CKB(mdqt_create(&p, &h));
+  if (B > 1) {
+    std::vector<uint64_t> s64(seeds.begin(), seeds.end());
+    CKB(mdqt_set_ion_counts(h, Nb.data()));
+    CKB(mdqt_set_traj_seeds(h, s64.data()));
+  }
+  CKB(mdqt_upload_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
   // RNG substep counter: continue the stream where a previous run of this job stopped
-  uint64_t sub0 = newRun == 1 ? 0 : (uint64_t)llround(t / p.dtq);
-  CK(mdqt_set_time(h, t, sub0));
+  const uint64_t sub0 = o.newRun == 1 ? 0 : (uint64_t)llround(t / p.dtq);
+  CKB(mdqt_set_time(h, t, sub0));
 
-  double Epot0 = 0.0;
-  CK(mdqt_epot(h, &Epot0));  // Epotential(); Epot0 = Epot (SU:345-346). On resume the reference leaves Epot0 = 0 (Q8):
-  if (newRun != 1) Epot0 = 0.0;
+  std::vector<double> Epot0(B, 0.0);
+  CKB(mdqt_epot(h, Epot0.data()));  // Epotential(); Epot0 = Epot (SU:345-346). On resume the reference leaves Epot0 = 0 (Q8):
+  if (o.newRun != 1) std::fill(Epot0.begin(), Epot0.end(), 0.0);
 
-  OutputWriter writer;
+  std::vector<mdqt_diag> diag(B);
+  std::vector<double> pvel((size_t)B * 3 * 2001), pops((size_t)B * Ncap * 3);
   int tsc = p.substeps_per_md;  // timeStepCounter (SU:1235)
   auto wall0 = std::chrono::steady_clock::now();
-  long nsub_total = 0, nforce = 0, nout = 0;
   for (;;) {
     int do_output, do_forces;
-    int n = mdqt_schedule_next(&c0, &tsc, &t, p.substeps_per_md, sampleFreq, p.dtq, tmax, &do_output, &do_forces);
+    int n = mdqt_schedule_next(&c0, &tsc, &t, p.substeps_per_md, o.sampleFreq, p.dtq, o.tmax, &do_output, &do_forces);
     if (n == 0) break;
     if (do_output) {  // output(), SU:917-1032
-      mdqt_diag d;
-      CK(mdqt_diagnostics(h, &d));
-      CK(mdqt_vel_dist(h, pvel.data()));
-      CK(mdqt_populations(h, pops.data()));
-      CK(mdqt_download_state(h, NULL, V.data(), NULL, NULL, ld));
-      OutputJob job;
-      job.dir = dir; job.counter = counter; job.N = N; job.d = d; job.Epot0 = Epot0;
-      job.pvel = pvel; job.pops.assign(pops.begin(), pops.begin() + (size_t)N * 3); job.vx.assign(V.begin(), V.begin() + N);
-      writer.push(std::move(job));
-      counter++;
-      nout++;
+      CKB(mdqt_diagnostics(h, diag.data()));
+      CKB(mdqt_vel_dist(h, pvel.data()));
+      CKB(mdqt_populations(h, pops.data()));
+      CKB(mdqt_download_state(h, NULL, V.data(), NULL, NULL, ld));
+      for (int b = 0; b < B; b++) {
+        OutputJob job;
+        job.dir = dirs[b]; job.counter = counter[b]; job.N = Nb[b]; job.d = diag[b]; job.Epot0 = Epot0[b];
+        job.pvel.assign(pvel.begin() + (size_t)b * 3 * 2001, pvel.begin() + (size_t)(b + 1) * 3 * 2001);
+        job.pops.assign(pops.begin() + (size_t)b * Ncap * 3, pops.begin() + ((size_t)b * Ncap + Nb[b]) * 3);
+        job.vx.assign(V.begin() + (size_t)b * 3 * ld, V.begin() + (size_t)b * 3 * ld + Nb[b]);
+        writers[(job0 + b) % writers.size()]->push(std::move(job));
+        counter[b]++;
+      }
+      res.nout++;
     }
     if (do_forces && !do_output && n == p.substeps_per_md) {
       // whole MD steps with no output() in between: hand the run of them to mdqt_md_steps (one replayed CUDA graph)
@@ -165,31 +205,135 @@ int main(int argc, char** argv) {
       for (;;) {
         int c0b = c0, tscb = tsc, o2, f2;
         double tb = t;
-        int n2 = mdqt_schedule_next(&c0b, &tscb, &tb, p.substeps_per_md, sampleFreq, p.dtq, tmax, &o2, &f2);
+        int n2 = mdqt_schedule_next(&c0b, &tscb, &tb, p.substeps_per_md, o.sampleFreq, p.dtq, o.tmax, &o2, &f2);
         if (n2 != p.substeps_per_md || !f2 || o2) break;
         c0 = c0b; tsc = tscb; t = tb; k++;
       }
-      CK(mdqt_md_steps(h, k));
-      nforce += k; nsub_total += (long)k * n;
+      CKB(mdqt_md_steps(h, k));
+      res.nforce += k; res.nsub += (long)k * n;
       continue;
     }
-    if (do_forces) { CK(mdqt_forces(h)); nforce++; }
-    CK(mdqt_substeps(h, n));
-    nsub_total += n;
+    if (do_forces) { CKB(mdqt_forces(h)); res.nforce++; }
+    CKB(mdqt_substeps(h, n));
+    res.nsub += n;
   }
-  writer.finish();  // every output file is on disk before the restart files are written
-  CK(mdqt_download_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
+  CKB(mdqt_download_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
   double t_dev; uint64_t s_dev;
-  CK(mdqt_get_time(h, &t_dev, &s_dev));
+  CKB(mdqt_get_time(h, &t_dev, &s_dev));
   if (t_dev != t) fprintf(stderr, "mdqt_run: warning: host/device clocks differ (%.17g vs %.17g)\n", t, t_dev);
-  if (mdqt_io_write_conditions(dir, c0, N, counter, R.data(), V.data(), psi.data(), ld, vholder.data())) {  // SU:1381
-    fprintf(stderr, "mdqt_run: cannot write restart files into %s\n", dir);
-    return 1;
+  res.wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  // every output file of these jobs must be on disk before their restart files are written: the caller drains the writers;
+  // the restart files themselves do not depend on them
+  for (int b = 0; b < B; b++) {
+    if (mdqt_io_write_conditions(dirs[b].c_str(), c0, Nb[b], counter[b], R.data() + (size_t)b * 3 * ld, V.data() + (size_t)b * 3 * ld,
+                                 psi.data() + (size_t)b * Ncap * 24, ld, vholder[b].data())) {  // SU:1381
+      fprintf(stderr, "mdqt_run: cannot write restart files into %s\n", dirs[b].c_str());
+      mdqt_destroy(h);
+      return res;
+    }
+    res.ions += Nb[b];
   }
-  double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
-  if (!quiet)
-    fprintf(stderr, "mdqt_run: job %u, N=%d, t=%.6f, c0=%d: %ld substeps, %ld force calls, %ld outputs in %.3f s (%.3e ion-steps/s); files in %s\n",
-            job, N, t, c0, nsub_total, nforce, nout, wall, (double)N * nsub_total / wall, dir);
+  if (!o.quiet) {
+    std::lock_guard<std::mutex> lk(g_print);
+    if (B == 1)
+      fprintf(stderr, "mdqt_run: job %u, N=%d, t=%.6f, c0=%d: %ld substeps, %ld force calls, %ld outputs in %.3f s (%.3e ion-steps/s); files in %s\n",
+              job0, Nb[0], t, c0, res.nsub, res.nforce, res.nout, res.wall, res.ions * res.nsub / res.wall, dirs[0].c_str());
+    else
+      fprintf(stderr, "mdqt_run: jobs %u-%u on GPU %d, N=%d..%d, t=%.6f, c0=%d: %ld substeps, %ld force calls, %ld outputs in %.3f s (%.3e ion-steps/s)\n",
+              job0, job0 + B - 1, device, *std::min_element(Nb.begin(), Nb.end()), Ncap, t, c0, res.nsub, res.nforce, res.nout, res.wall,
+              res.ions * res.nsub / res.wall);
+  }
   mdqt_destroy(h);
-  return 0;
+  res.ok = 1;
+  return res;
+}
+
+static void usage() {
+  fprintf(stderr, "usage: mdqt_run <job> | --jobs a-b [--batch n] [--gpus n]\n"
+                  "       [--Ge x] [--density x] [--sig0 x] [--Te x] [--fracOfSig x] [--N0 n] [--detuning x] [--detuningDP x] [--Om x]\n"
+                  "       [--OmDP x] [--saveDirectory dir/] [--newRun 0|1] [--c0 n] [--tmax x] [--reNormalizewvFns 0|1] [--sampleFreq n]\n"
+                  "       [--seed n] [--device n] [--writers n] [--fast-single] [--quiet]\n");
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { usage(); return 2; }
+  // defaults = the reference's globals (SU:56-78)
+  std::map<std::string, std::string> opt = {
+      {"Ge", "0.1"}, {"density", "2"}, {"sig0", "4.0"}, {"Te", "19.0"}, {"fracOfSig", "0"}, {"N0", "3500"}, {"detuning", "-1"},
+      {"detuningDP", "1"}, {"Om", "1"}, {"OmDP", "1"}, {"saveDirectory", "dataLaserCool/"}, {"newRun", "1"}, {"c0", "0"},
+      {"tmax", "30"}, {"reNormalizewvFns", "0"}, {"sampleFreq", "40"}, {"seed", ""}, {"device", "0"}, {"jobs", ""},
+      {"batch", "64"}, {"gpus", "1"}, {"writers", "0"}};
+  Options o;
+  long job_a = -1, job_b = -1;
+  int i = 1;
+  if (argv[1][0] != '-') { job_a = job_b = (long)(unsigned)atof(argv[1]); i = 2; }  // SU:1145
+  for (; i < argc; i++) {
+    std::string a = argv[i];
+    if (a == "--quiet") { o.quiet = true; continue; }
+    if (a == "--fast-single") { o.fast_single = 1; continue; }
+    if (a.rfind("--", 0) != 0 || !opt.count(a.substr(2)) || i + 1 >= argc) { fprintf(stderr, "mdqt_run: bad option %s\n", a.c_str()); usage(); return 2; }
+    opt[a.substr(2)] = argv[++i];
+  }
+  if (!opt["jobs"].empty()) {
+    if (sscanf(opt["jobs"].c_str(), "%ld-%ld", &job_a, &job_b) != 2 || job_a < 0 || job_b < job_a) { fprintf(stderr, "mdqt_run: --jobs wants a-b\n"); return 2; }
+  }
+  if (job_a < 0) { usage(); return 2; }
+  o.Ge = atof(opt["Ge"].c_str()); o.density = atof(opt["density"].c_str()); o.sig0 = atof(opt["sig0"].c_str());
+  o.Te = atof(opt["Te"].c_str()); o.fracOfSig = atof(opt["fracOfSig"].c_str()); o.detuning = atof(opt["detuning"].c_str());
+  o.detuningDP = atof(opt["detuningDP"].c_str()); o.Om = atof(opt["Om"].c_str()); o.OmDP = atof(opt["OmDP"].c_str());
+  o.tmax = atof(opt["tmax"].c_str());
+  o.N0 = atoi(opt["N0"].c_str()); o.newRun = atoi(opt["newRun"].c_str()); o.sampleFreq = atoi(opt["sampleFreq"].c_str());
+  o.c0 = atoi(opt["c0"].c_str()); o.renorm = atoi(opt["reNormalizewvFns"].c_str()); o.device = atoi(opt["device"].c_str());
+  o.saveDirectory = opt["saveDirectory"];
+  const bool array = !opt["jobs"].empty();
+  // seed of job j: the reference's srand48(time(NULL) + job) (SU:1219). With --seed S a single run uses S itself, an array
+  // uses S + job -- so `mdqt_run j --seed S+j` reproduces job j of `mdqt_run --jobs a-b --seed S` bit for bit
+  const bool have_seed = !opt["seed"].empty();
+  o.seed = have_seed ? atol(opt["seed"].c_str()) : (long)(unsigned)time(NULL);
+  o.seed_add_job = array || !have_seed;
+  const int batch = std::max(1, atoi(opt["batch"].c_str()));
+  int gpus = std::max(1, atoi(opt["gpus"].c_str()));
+  const int ndev = mdqt_device_count();
+  if (ndev <= 0) { fprintf(stderr, "mdqt_run: no CUDA device (the engine has no CPU fallback)\n"); return 1; }
+  if (array && gpus > ndev) gpus = ndev;
+  const long njobs = job_b - job_a + 1;
+  int nwriters = atoi(opt["writers"].c_str());
+  if (nwriters <= 0) nwriters = array ? (int)std::min<long>(std::max(1u, std::thread::hardware_concurrency()), std::min<long>(njobs, 32)) : 1;
+  std::vector<std::unique_ptr<OutputWriter>> writers;
+  for (int w = 0; w < nwriters; w++) writers.emplace_back(new OutputWriter());
+
+  auto wall0 = std::chrono::steady_clock::now();
+  std::vector<BatchResult> results;
+  std::mutex rm;
+  int failed = 0;
+  if (!array) {
+    BatchResult r = run_batch(o, (unsigned)job_a, 1, o.device, writers);
+    failed = !r.ok;
+  } else {
+    // contiguous blocks of jobs per GPU, one host thread per GPU, `batch` jobs per handle
+    std::vector<std::thread> th;
+    for (int g = 0; g < gpus; g++) {
+      const long lo = job_a + njobs * g / gpus, hi = job_a + njobs * (g + 1) / gpus;  // [lo, hi)
+      if (lo >= hi) continue;
+      th.emplace_back([&, g, lo, hi] {
+        for (long j = lo; j < hi; j += batch) {
+          const int B = (int)std::min<long>(batch, hi - j);
+          BatchResult r = run_batch(o, (unsigned)j, B, (o.device + g) % ndev, writers);
+          std::lock_guard<std::mutex> lk(rm);
+          results.push_back(r);
+          if (!r.ok) failed++;
+        }
+      });
+    }
+    for (auto& t : th) t.join();
+  }
+  for (auto& w : writers) w->finish();  // every output file is on disk before the process reports success
+  if (array && !o.quiet) {
+    double ion_sub = 0;
+    for (const BatchResult& r : results) ion_sub += r.ions * r.nsub;
+    const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    fprintf(stderr, "mdqt_run: %ld jobs on %d GPU(s), batch %d, %d writer thread(s): %.3f s wall, %.3e ion-steps/s aggregate\n", njobs, gpus,
+            batch, nwriters, wall, ion_sub / wall);
+  }
+  return failed ? 1 : 0;
 }

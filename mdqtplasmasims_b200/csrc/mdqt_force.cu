@@ -6,23 +6,28 @@
 // N(N-1)/2 unordered pairs with a racy OpenMP scatter; here every ion row i gathers over ALL j (N^2 ordered
 // pair-interactions per call), which needs no scatter and sums in a fixed order.
 //
-// Bound: the FP64 pipe (64 lanes/clk/SM). Memory traffic is negligible (24 B per j per CTA, staged in shared memory
-// and broadcast). Pair geometry:
-//   PERIODIC FIXED POINT: coordinates are kept as 64-bit integers in units of
-//     L/2^64, so that the two's-complement difference x_i - x_j IS the minimum image (the reference's
-//     d -= L*round(d/L), SU:218-220) -- for free, for any (wrapped or unwrapped) input, and exactly: differences are
-//     formed without rounding and converted to double with 53-bit relative precision. Delta + minimum image cost
-//     2 integer adds + 1 int->fp64 conversion per component and NO FP64-pipe instruction.
-//   2 fp64 magic-number rint: t = fma(d,1/L,1.5*2^52); n = t-1.5*2^52; d = fma(-L,n,d): 3+9 FP64 instructions.
-// The rest is common: r^2 (3), 1/r = MUFU.RSQ64H seed + one 3rd-order Newton step (5), r (1), cut-off DSETP (1),
-// exp(-kappa r) by magic-number reduction to |rr| <= ln2/256 + a 128-entry 2^(j/128) table in shared memory + a
-// degree-5 polynomial with the exponent patched by integer adds (10), prefactor (4), accumulate (3).
+// Bound: the FP64 pipe / the sub-partition issue port (an FP64 warp instruction holds the port for 2 cycles). Memory
+// traffic is negligible (24 B per j per pass, staged in shared memory and broadcast). Pair arithmetic (23 FP64-pipe
+// instructions per ordered pair):
+//   PERIODIC FIXED POINT: coordinates are kept as 64-bit integers in units of L/2^64, so that the two's-complement
+//     difference x_i - x_j IS the minimum image (the reference's d -= L*round(d/L), SU:218-220) -- for free, for any
+//     (wrapped or unwrapped) input, and exactly: differences are formed without rounding and converted to double with
+//     53-bit relative precision. Delta + minimum image cost 2 integer adds + 1 int->fp64 conversion per component and
+//     NO FP64-pipe instruction.
+//   r^2 (3), 1/r = MUFU.RSQ64H seed + one 3rd-order Newton step (5), r (1); the cut-off r < L/2 is ONE unsigned integer
+//   compare of the high word of r^2 (r^2 < 2^126 fixed-point units; other cut-offs take one DSETP) and the self pair needs
+//   no predicate (r^2 carries +1 unit^2, its f is multiplied by Delta = 0); exp(-kappa r) by a magic-number reduction in
+//   units of ln2/1024 + a 1024-entry 2^(j/1024) table in shared memory (high words pre-biased: the exponent patch is one
+//   integer add) + a cubic (6); prefactor (5); accumulate (3).
+// Two kernels share that loop: k_pairs (CTA tiles of 128 or 32 rows, large N) and k_pairs_items (a persistent grid whose
+// warps walk a static list of (trajectory, 32-row group, j chunk) items; small/medium N at any batch size).
 #include "mdqt_internal.h"
 #include "mdqt_fixed.cuh"
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 namespace mdqt {
 
@@ -72,7 +77,6 @@ void upload_exp_table() {
 // Everything the pair loop needs, in the length unit `u` of the chosen formulation (u = 1 for variant 2,
 // u = L/2^64 for the fixed-point variant): kappa*u, (rcut/u)^2, and the exp reduction constants.
 struct PairConsts {
-  double L, invL, invL_lo;
   double kappa_u, negkappa_u, nk_scale, negc, rc2_u;
   double c1, c2, c3, c4, c5;  // exp polynomial coefficients in the reduced variable
   double out_scale;  // 1/u^2 for forces, 1/u for the potential energy
@@ -80,7 +84,6 @@ struct PairConsts {
 
 __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot) {
   PairConsts c;
-  c.L = a.L; c.invL = a.invL; c.invL_lo = a.invL_lo;
   const double u = a.L / MDQT_2P64;
   c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
   const double T = (double)kExpTable;
@@ -138,6 +141,18 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
 }
 
 constexpr int kTJ = 512;  // j positions staged per pass
+
+// Graph replay: a force launch sits between the substep kernels of two MD steps, so nobody reads the device clock while
+// it runs; one thread adds the substeps of the previous MD step (t by the reference's repeated addition, SU:716). Called
+// AFTER griddepcontrol.wait, so that with programmatic dependent launch the previous substep kernel has finished reading.
+__device__ __forceinline__ void advance_clock(const ForceArgs& a) {
+  if (a.clock_advance <= 0) return;
+  double t = a.clock[0];
+  for (int k = 0; k < a.clock_advance; k++) t = __dadd_rn(t, a.clock_dtq);
+  a.clock[0] = t;
+  unsigned long long* sub = reinterpret_cast<unsigned long long*>(a.clock + 1);
+  *sub += (unsigned long long)a.clock_advance;
+}
 
 // 8-byte asynchronous global -> shared copies (LDGSTS): the exp table, the first j tile and the thread's own rows are all
 // in flight together in the CTA prologue (one L2 round trip instead of three), and tiles never pass through registers
@@ -199,14 +214,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
   constexpr int NT = kForceThreads * JS;
 
   TRACE(0)
-  if (!EPOT && a.clock_advance > 0 && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    // graph replay: this launch sits between the substep kernels of two MD steps, so nobody reads the clock now
-    double t = a.clock[0];
-    for (int k = 0; k < a.clock_advance; k++) t = __dadd_rn(t, a.clock_dtq);  // SU:716, one addition per substep
-    a.clock[0] = t;
-    unsigned long long* sub = reinterpret_cast<unsigned long long*>(a.clock + 1);
-    *sub += (unsigned long long)a.clock_advance;
-  }
+  if (threadIdx.x == 0) stamp_time(a.stamp, 0);
   const int tid = threadIdx.x;
   const int ti = tid % kForceThreads, jh = tid / kForceThreads;
   const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
   const long long* __restrict__ Z = Y + a.ld;
   for (int k = tid; k < kExpTable; k += NT) cp_async8(&stab[k], &c_exp2tab[k]);
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
+  if (!EPOT && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) advance_clock(a);
 
   int irow[IPT];
   long long xi[IPT], yi[IPT], zi[IPT];
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
       for (int w = 0; w < kForceThreads / 32; w++) tot += sred[w];  // the warps of group 0
       block_partials[((size_t)b * gridDim.y + js) * gridDim.x + tile] = tot;
     }
+    if (tid == 0) stamp_time(a.stamp, 1);
     return;
   }
 
@@ -328,6 +338,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
         double* Fb = a.F + (size_t)b * 3 * a.ld;
         Fb[irow[k]] = ax[k]; Fb[a.ld + irow[k]] = ay[k]; Fb[2 * a.ld + irow[k]] = az[k];
       }
+    if (tid == 0) stamp_time(a.stamp, 1);
     return;
   }
   if (CL) {
@@ -357,6 +368,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
       }
     }
     cluster.sync();  // nobody leaves while its shared memory may still be read
+    if (tid == 0) stamp_time(a.stamp, 1);
     return;
   }
   // j-split: store the partial, the last CTA of this (trajectory, i-tile) sums all partials in ascending split
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
   }
   __syncthreads();
   TRACE(3)
-  if (!s_last) return;
+  if (!s_last) { if (tid == 0) stamp_time(a.stamp, 1); return; }
   __threadfence();
   // the last CTA: all NT threads share the final reduction (thread -> (row slot, component) round robin)
   for (int w = tid; w < kForceThreads * IPT * 3; w += NT) {
@@ -400,6 +412,204 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
     }
   }
   TRACE(4)
+  if (tid == 0) stamp_time(a.stamp, 1);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// K1, item-walking form (small and medium systems, any number of batched trajectories).
+//
+// A few thousand ions are only ~24 us of issue work for the whole chip, and a grid of CTA tiles loses a third of that to
+// wave quantisation (1.49 waves at N = 3500), CTA prologues and the last CTA's partial-sum reduction. Here the grid is
+// PERSISTENT -- two 8-warp CTAs per SM -- and the unit of work is an ITEM = (trajectory b, group g of 32 rows, chunk c
+// of jlen positions), handled by ONE warp: lane <-> row, the chunk staged by the warp itself into its private shared-
+// memory buffer (cp.async, double buffered: the next item's tile and rows are in flight while this one computes), no
+// CTA-wide barrier after the prologue. Items are dealt round-robin to the grid's warps; jlen is chosen so that the item
+// count fills all warps evenly when one trajectory runs alone (N = 3500: 110 groups x 21 chunks of 168 = 2310 items on
+// 2368 warps, one each), and a batch simply walks B times as many items.
+// Every item writes one partial sum; the last warp to arrive for a (trajectory, group) adds the partials in ascending
+// chunk order. The summation order of a row is therefore a function of jlen alone -- i.e. of mdqt_params.plan_n, not of
+// the batch size, of the trajectory's position in the batch, or of the number of row-owning ranks: a job gives the same
+// bits alone or batched. Trajectories of an ensemble may hold different ion counts nb[b] (SU:299-337).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kItemWarps = 8;
+constexpr int kItemCtasPerSM = 2;
+constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps + the exp table = 116 KB per CTA
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+struct Item { int b, g, ch, Nb; };
+
+template <bool EPOT, bool HL>
+__global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double stab[kExpTable];  // static: the table index folds into the LDS immediate offset
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tj = a.jlen;  // tile capacity (a multiple of 8, <= kItemMaxJ)
+  // per warp and buffer: xy[tj] (16 B), z[tj] (8 B), then the item's 32 rows x, y, z (3 x 32 x 8 B)
+  const unsigned bufbytes = 24u * (unsigned)tj + 768u;
+  unsigned char* wbase = smem_raw + (size_t)warp * (2 * (size_t)bufbytes);
+  const PairConsts c = make_consts(a, EPOT);
+  if (tid == 0) stamp_time(a.stamp, 0);
+  for (int k = tid; k < kExpTable; k += kItemWarps * 32) cp_async8(&stab[k], &c_exp2tab[k]);
+  pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
+  if (!EPOT && tid == 0 && blockIdx.x == 0) advance_clock(a);
+
+  const int W = gridDim.x * kItemWarps;
+  const int total = a.B * a.gcap * a.nsplit;
+  const int rowend_cap = a.row0 + a.nrows;
+  // item k -> (b, g, ch) by multiplication with host-made reciprocals (k < 2^24, divisors < 2^16: exact)
+  auto decode = [&](int k, Item& it) {
+    const unsigned t = (unsigned)(((unsigned long long)(unsigned)k * a.mg_chunk) >> 40);
+    it.ch = k - (int)t * a.nsplit;
+    it.b = (int)(((unsigned long long)t * a.mg_gcap) >> 40);
+    it.g = (int)t - it.b * a.gcap;
+    it.Nb = a.nb ? a.nb[it.b] : a.N;
+    // empty when the group or the chunk lies beyond the trajectory's ions
+    return (a.row0 + it.g * 32 < min(rowend_cap, it.Nb)) && (it.ch * a.jlen < it.Nb);
+  };
+  auto next_valid = [&](int k, Item& it) {
+    while (k < total && !decode(k, it)) {
+      if (EPOT && lane == 0) item_partials[k] = 0.0;  // the per-trajectory sum runs over all item slots
+      k += W;
+    }
+    return k;
+  };
+  auto issue = [&](const Item& it, int buf) {
+    const long long* __restrict__ X = a.Rfix + (size_t)it.b * 3 * a.ld;
+    const long long* __restrict__ Y = X + a.ld;
+    const long long* __restrict__ Z = Y + a.ld;
+    unsigned char* base = wbase + (size_t)buf * bufbytes;
+    longlong2* sxy = reinterpret_cast<longlong2*>(base);
+    long long* sz = reinterpret_cast<long long*>(base + 16u * (unsigned)tj);
+    long long* srow = reinterpret_cast<long long*>(base + 24u * (unsigned)tj);
+    const int jbeg = it.ch * a.jlen, cnt = min(a.jlen, it.Nb - jbeg);
+    for (int q = lane; q < cnt; q += 32) {
+      cp_async8(&sxy[q].x, X + jbeg + q); cp_async8(&sxy[q].y, Y + jbeg + q); cp_async8(&sz[q], Z + jbeg + q);
+    }
+    const int ir = min(a.row0 + it.g * 32 + lane, min(rowend_cap, it.Nb) - 1);  // idle lanes shadow the last row (never stored)
+    cp_async8(&srow[lane], X + ir); cp_async8(&srow[32 + lane], Y + ir); cp_async8(&srow[64 + lane], Z + ir);
+  };
+
+  Item cur, nxt;
+  int k = next_valid(warp * gridDim.x + blockIdx.x, cur);  // consecutive items go to different SMs
+  if (k < total) issue(cur, 0);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();  // the exp table is complete for every warp; the only CTA-wide barrier of the kernel
+  int buf = 0;
+  while (k < total) {
+    const int kn = next_valid(k + W, nxt);
+    __syncwarp();  // every lane is done reading the buffer that the next tile overwrites
+    if (kn < total) issue(nxt, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait_1();  // all but the newest group: this item's tile has landed
+    __syncwarp();
+    const unsigned char* base = wbase + (size_t)buf * bufbytes;
+    const longlong2* __restrict__ sxy = reinterpret_cast<const longlong2*>(base);
+    const long long* __restrict__ sz = reinterpret_cast<const long long*>(base + 16u * (unsigned)tj);
+    const long long* __restrict__ srow = reinterpret_cast<const long long*>(base + 24u * (unsigned)tj);
+    const long long xi = srow[lane], yi = srow[32 + lane], zi = srow[64 + lane];
+    const int cnt = min(a.jlen, cur.Nb - cur.ch * a.jlen);
+    double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll 8
+    for (int jj = 0; jj < cnt; jj++) {
+      const longlong2 pxy = sxy[jj];
+      const long long pz = sz[jj];
+      const double dx = __ll2double_rn((long long)((unsigned long long)xi - (unsigned long long)pxy.x));
+      const double dy = __ll2double_rn((long long)((unsigned long long)yi - (unsigned long long)pxy.y));
+      const double dz = __ll2double_rn((long long)((unsigned long long)zi - (unsigned long long)pz));
+      const double r2 = EPOT ? fma(dx, dx, fma(dy, dy, dz * dz)) : fma(dx, dx, fma(dy, dy, fma(dz, dz, 1.0)));  // see k_pairs
+      double rinv, ef;
+      bool valid;
+      pair_core<HL>(r2, c, stab, rinv, ef, valid);
+      if (EPOT) {
+        const double u = ef * rinv;
+        ax += valid ? u : 0.0;
+      } else {
+        double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);
+        if (HL)
+          asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+              : "+d"(f) : "r"(__double2hiint(r2)));
+        else
+          asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
+              : "+d"(f) : "d"(r2), "d"(c.rc2_u));
+        ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
+      }
+    }
+    ax *= c.out_scale; ay *= c.out_scale; az *= c.out_scale;
+    const int row = a.row0 + cur.g * 32 + lane;
+    const bool live = row < min(rowend_cap, cur.Nb);
+    if (EPOT) {
+      double sum = live ? ax : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+      if (lane == 0) item_partials[k] = sum;
+    } else {
+      const int nch_b = (cur.Nb + a.jlen - 1) / a.jlen;  // chunks this trajectory really has
+      double* Fb = a.F + (size_t)cur.b * 3 * a.ld;
+      if (nch_b == 1) {
+        if (live) { Fb[row] = ax; Fb[a.ld + row] = ay; Fb[2 * a.ld + row] = az; }
+      } else {
+        const size_t stride = (size_t)a.B * 3 * a.ld;
+        if (live) {
+          double* Fp = a.Fpart + (size_t)cur.ch * stride + (size_t)cur.b * 3 * a.ld;
+          __stcg(&Fp[row], ax); __stcg(&Fp[a.ld + row], ay); __stcg(&Fp[2 * a.ld + row], az);
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned old = 0;
+        unsigned* ctr = a.counters + (size_t)cur.b * a.gcap + cur.g;
+        if (lane == 0) old = atomicAdd(ctr, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old == (unsigned)nch_b - 1) {  // the last warp of this (trajectory, group): add the chunks in ascending order
+          if (lane == 0) *ctr = 0;         // self-reset for the next call
+          __threadfence();
+          if (live) {
+            const double* src = a.Fpart + (size_t)cur.b * 3 * a.ld + row;
+            double sx = 0.0, sy = 0.0, szz = 0.0;
+            for (int s0 = 0; s0 < nch_b; s0 += 12) {  // 36 independent loads per batch: one L2 round trip
+              double vx[12], vy[12], vz[12];
+#pragma unroll
+              for (int q = 0; q < 12; q++) {
+                const bool in = s0 + q < nch_b;
+                const double* pq = src + (size_t)(in ? s0 + q : 0) * stride;
+                vx[q] = in ? __ldcg(pq) : 0.0; vy[q] = in ? __ldcg(pq + a.ld) : 0.0; vz[q] = in ? __ldcg(pq + 2 * a.ld) : 0.0;
+              }
+#pragma unroll
+              for (int q = 0; q < 12; q++) { sx += vx[q]; sy += vy[q]; szz += vz[q]; }  // + 0.0 for absent chunks: exact
+            }
+            Fb[row] = sx; Fb[a.ld + row] = sy; Fb[2 * a.ld + row] = szz;
+          }
+        }
+      }
+    }
+    k = kn; buf ^= 1; cur = nxt;
+  }
+  pdl_launch_dependents();
+  if (lane == 0) stamp_time(a.stamp, 1);
+}
+
+template <bool EPOT>
+static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)kItemWarps * 2 * (24 * (size_t)a.jlen + 768);
+  const long long total = (long long)a.B * a.gcap * a.nsplit;
+  const int grid = (int)std::min<long long>(148LL * kItemCtasPerSM, (total + kItemWarps - 1) / kItemWarps);
+  const bool hl = a.half_l && MDQT_VALID_INT;
+  auto kern = hl ? k_pairs_items<EPOT, true> : k_pairs_items<EPOT, false>;
+  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  if (!attr_done[EPOT][hl]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kItemWarps * 2 * (24 * (size_t)kItemMaxJ + 768)));
+    attr_done[EPOT][hl] = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kItemWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  int n = 0;
+  if (!EPOT && pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; n++; }
+  cfg.attrs = at; cfg.numAttrs = n;
+  cudaLaunchKernelEx(&cfg, kern, a, partials);
 }
 
 template <bool EPOT, bool HL>
@@ -429,6 +639,7 @@ static void launch_pairs_hl(const ForceArgs& a, double* partials, cudaStream_t s
 
 template <bool EPOT>
 static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
+  if (a.items) { launch_items<EPOT>(a, partials, s); return; }
   // rows per group / per thread and the intra-CTA split: decided by the planner from (N, B) only
   const int rg = a.rg == 32 ? 32 : kForceThreads;
   const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
@@ -460,7 +671,8 @@ int epot_partials_needed(const ForceArgs& a) {
   return tiles * a.nsplit * a.B;
 }
 
-__global__ void k_epot_final(const double* __restrict__ partials, int per_traj, double scale, double* __restrict__ out) {
+__global__ void k_epot_final(const double* __restrict__ partials, int per_traj, double half, int N, const int* __restrict__ nb,
+                             double* __restrict__ out) {
   __shared__ double sred[256];
   const double* p = partials + (size_t)blockIdx.x * per_traj;
   double s = 0.0;
@@ -471,16 +683,20 @@ __global__ void k_epot_final(const double* __restrict__ partials, int per_traj, 
     if (threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[blockIdx.x] = sred[0] * scale;
+  if (threadIdx.x == 0) out[blockIdx.x] = sred[0] * (half / (double)(nb ? nb[blockIdx.x] : N));
 }
 
 void launch_epot(const ForceArgs& a, double* partials, double* result, cudaStream_t s) {
   launch_pairs<true>(a, partials, s);
-  const int rg = a.rg == 32 ? 32 : kForceThreads;
-  const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
-  int tiles = (a.nrows + rg * ipt - 1) / (rg * ipt);
+  int per_traj;
+  if (a.items) per_traj = a.gcap * a.nsplit;
+  else {
+    const int rg = a.rg == 32 ? 32 : kForceThreads;
+    const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
+    per_traj = (a.nrows + rg * ipt - 1) / (rg * ipt) * a.nsplit;
+  }
   // ordered pairs counted twice -> 1/2; per particle -> 1/N (SU:272)
-  k_epot_final<<<a.B, 256, 0, s>>>(partials, tiles * a.nsplit, 0.5 / (double)a.N, result);
+  k_epot_final<<<a.B, 256, 0, s>>>(partials, per_traj, 0.5, a.N, a.nb, result);
 }
 
 // ---- FP64 peak probe: 8 independent DFMA chains per thread, all-register operands ----

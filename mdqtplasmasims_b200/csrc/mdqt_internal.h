@@ -31,6 +31,12 @@ struct ForceArgs {
   int half_l;        // rcut == L/2 exactly (every reference program): the cut-off is a power of two in fixed-point units
   double L, halfL, invL, invL_lo, kappa, rc2;  // 1/L = invL + invL_lo (double-double)
   double inv_u, rc2_u;  // fixed-point unit u = L/2^64: 1/u, and the squared cut-off in units u^2
+  // item-walking kernel (small and medium systems, any batch size): every warp of a persistent grid walks a static list of
+  // (trajectory, 32-row group, j chunk) items. items = 1 selects it; gcap = row groups per trajectory (at capacity)
+  int items, gcap;
+  unsigned long long mg_chunk, mg_gcap;  // ceil(2^40 / nsplit), ceil(2^40 / gcap): item index -> (b, g, chunk) without division
+  const int* nb;     // [B] ions per trajectory (ensembles whose jobs drew different N, SU:299-337) or null: all N
+  unsigned long long* stamp;  // {min start, max end} of this launch in %globaltimer ns (in-graph kernel timing) or null
 };
 
 struct QTArgs {
@@ -47,7 +53,11 @@ struct QTArgs {
   int do_kick;                            // 1: V_x += optical-force / recoil kick (SU:705, TS:283); 0: frozen V (MC408L:754)
   int do_tpart;                           // 1: tPart tracked (+= dtq, reset on a jump; SU:482, TS:155)
   int renorm, quad;
+  int lanes;                              // lanes per ion of the 12-level kernel: 0 = by (N, B), 2 or 4 = pinned
   double t0; uint64_t substep0; uint64_t seed;
+  const int* nb;                          // [B] ions per trajectory or null (all N)
+  const uint64_t* seeds;                  // [B] Philox key per trajectory or null (all `seed`)
+  unsigned long long* stamp;              // {min start, max end} of this launch in %globaltimer ns, or null
   const double* clock;                    // {t, substep index (as uint64 bits)} in device memory: overrides t0/substep0 when non-null
   double L, dtq;
   double detuning, detuningDP, Om, OmDP, dR, kRat, vKick, vKickDP, g2E, pv2qv;
@@ -90,6 +100,13 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return cudaLaunchKernelEx(&cfg, kern, a0, a1);
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// in-graph kernel timing: every CTA (or warp) folds its start / end time into the launch's {min start, max end} slot
+__device__ __forceinline__ void stamp_time(unsigned long long* stamp, int end) {
+  if (!stamp) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (end) atomicMax(stamp + 1, t); else atomicMin(stamp, t);
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 void launch_forces(const ForceArgs& a, cudaStream_t s);
@@ -101,9 +118,9 @@ struct QTConsts;
 void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s);
 void launch_vv_positions(const VVArgs& a, cudaStream_t s);
 void launch_vv_velocities(const VVArgs& a, cudaStream_t s);
-// diag_out[B][8]: vx_avg, ekin_x, ekin_y, ekin_z; pvel[B][3][2001]; pops[B][N][3]
-void launch_diag(const double* V, int N, int ld, int B, double* scratch, double* diag_out, cudaStream_t s);
-void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, double* pvel, cudaStream_t s);
+// diag_out[B][8]: vx_avg, ekin_x, ekin_y, ekin_z; pvel[B][3][2001]; pops[B][N][3]; nb = per-trajectory ion counts or null
+void launch_diag(const double* V, int N, int ld, int B, const int* nb, double* diag_out, cudaStream_t s);
+void launch_vel_dist(const double* V, const double* diag_out, int N, int ld, int B, const int* nb, double* pvel, cudaStream_t s);
 void launch_diag_partial(const double* V, int row0, int nrows, int ld, int B, const double* mean, double* out, cudaStream_t s);
 void launch_vel_dist_rows(const double* V, const double* diag, int row0, int nrows, int ld, int B, double* pvel, cudaStream_t s);
 void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s);

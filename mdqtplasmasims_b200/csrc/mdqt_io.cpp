@@ -46,7 +46,10 @@ int mdqt_io_init_su(long seed, int N0, double Ge, int ld, double* R, double* V, 
   const double lDeb = 1. / sqrt(3. * Ge);                    // SU:295
   const double L = pow(N0 * 4. * M_PI / 3., 0.333333333);    // SU:297
   const double N9L = (unsigned)(9. * 9. * 9. * (L * L * L) * 3. / (4. * M_PI));  // SU:299
-  srand48(seed);
+  // srand48(seed) + drand48() on a LOCAL generator state (erand48: the same 48-bit LCG and the same numbers as the
+  // reference's global stream), so that the jobs of an ensemble can be initialised from several threads at once
+  unsigned short xs[3] = {0x330E, (unsigned short)(seed & 0xFFFF), (unsigned short)((seed >> 16) & 0xFFFF)};
+  auto drand48 = [&xs]() { return erand48(xs); };
   int N = 0;
   for (int i = 0; i < N9L; i++) {
     double x = 9. * L * drand48() - 4. * L;  // SU:305-307

@@ -174,10 +174,13 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = gid & 1;
   const long long slot = gid >> 1;
-  const bool active = slot < (long long)a.nrows * a.B;
+  const bool inrange = slot < (long long)a.nrows * a.B;
   // inactive lanes still run (the shuffles are warp-wide) on a harmless shadow of the first ion; they never store
-  const int b = active ? (int)(slot / a.nrows) : 0;
-  const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
+  const int b = inrange ? (int)(slot / a.nrows) : 0;
+  const int i0 = inrange ? a.row0 + (int)(slot % a.nrows) : a.row0;
+  const bool active = inrange && i0 < (a.nb ? a.nb[b] : a.N);  // ensembles: trajectory b holds nb[b] <= N ions
+  const int i = active ? i0 : a.row0;
+  const uint64_t seed = a.seeds ? a.seeds[b] : a.seed;
   const int S = (NL == 6) ? 12 : a.S;  // compile-time stride for the 12-level hot path
   // the 12-level scheme always kicks and tracks tPart together with step() (SU); the small schemes choose at run time
   const bool do_kick = (NL == 6) ? (a.do_step != 0) : (a.do_kick != 0);
@@ -208,6 +211,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
 
   pdl_wait();  // forces / state come from the previous kernels in the stream
+  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 0);
   cplx y[NL];
 #pragma unroll
   for (int k = 0; k < NL; k++) {
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
       const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
       u0 = up[0]; u1 = up[1];
     } else {
-      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
+      uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
       u0 = u52(o.x, o.y); u1 = u52(o.z, o.w);
     }
 
@@ -337,9 +341,9 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
         const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
         u2 = up[2]; u3 = up[3]; u4 = up[4];
       } else {
-        uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
+        uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
         u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
-        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
+        o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
         u4 = u52(o.x, o.y);
       }
       tp = 0.0;
@@ -391,6 +395,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   }
 
   pdl_launch_dependents();  // the force kernel's launch + prologue may overlap the stores below (it waits before reading)
+  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 1);
   if (!active) return;
 #pragma unroll
   for (int k = 0; k < NL; k++)
@@ -470,9 +475,12 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = gid & 3, blk = q >> 1, half = q & 1;
   const long long slot = gid >> 2;
-  const bool active = slot < (long long)a.nrows * a.B;
-  const int b = active ? (int)(slot / a.nrows) : 0;
-  const int i = active ? a.row0 + (int)(slot % a.nrows) : a.row0;
+  const bool inrange = slot < (long long)a.nrows * a.B;
+  const int b = inrange ? (int)(slot / a.nrows) : 0;
+  const int i0 = inrange ? a.row0 + (int)(slot % a.nrows) : a.row0;
+  const bool active = inrange && i0 < (a.nb ? a.nb[b] : a.N);  // ensembles: trajectory b holds nb[b] <= N ions
+  const int i = active ? i0 : a.row0;
+  const uint64_t seed = a.seeds ? a.seeds[b] : a.seed;
 
   double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
   double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
@@ -513,6 +521,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   const int base = threadIdx.x & 28;  // first lane of this ion's quad within the warp
 
   pdl_wait();
+  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 0);
   cplx y[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) { y[k].re = Pb[(size_t)(2 * map[k]) * a.ld + i]; y[k].im = Pb[(size_t)(2 * map[k] + 1) * a.ld + i]; }
@@ -560,7 +569,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
       const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
       u0 = up[0]; u1 = up[1];
     } else {
-      uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
+      uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
       u0 = u52(o.x, o.y); u1 = u52(o.z, o.w);
     }
     // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
@@ -618,9 +627,9 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
         const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
         u2 = up[2]; u3 = up[3]; u4 = up[4];
       } else {
-        uint4 o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
+        uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
         u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
-        o = philox_call(a.seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
+        o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
         u4 = u52(o.x, o.y);
       }
       tp = 0.0;
@@ -654,6 +663,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
     t = __dadd_rn(t, a.dtq);  // SU:716
   }
 
+  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 1);
   if (!active) return;
 #pragma unroll
   for (int k = 0; k < 3; k++) { Pb[(size_t)(2 * map[k]) * a.ld + i] = y[k].re; Pb[(size_t)(2 * map[k] + 1) * a.ld + i] = y[k].im; }
@@ -682,7 +692,9 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   // MDQT_QT_LANES=2|4 forces one mapping (both stay parity-tested, tests/test_gpu_variants.py).
   static const int lanes_override = [] { const char* e = getenv("MDQT_QT_LANES"); return e ? atoi(e) : 0; }();
   const bool small = 4LL * a.N * a.B <= 148LL * 4 * 32;  // four-lane warps fit one per sub-partition
-  const bool four = scheme == 12 && a.do_step && (lanes_override == 4 || (lanes_override != 2 && small));
+  // a.lanes (mdqt_params.plan_n != 0: batch-reproducible mode) pins the mapping so that a job gives the same bits alone or batched
+  const int want = lanes_override ? lanes_override : a.lanes;
+  const bool four = scheme == 12 && a.do_step && (want == 4 || (want != 2 && small));
   if (four) {
     long long th = 4LL * a.nrows * a.B;
     int g4 = (int)((th + 31) / 32);

@@ -27,7 +27,7 @@ class Params(ctypes.Structure):
     """``mdqt_params`` of include/mdqt.h (same field order)."""
     _fields_ = [(k, ctypes.c_int32) for k in (
         "struct_bytes", "scheme", "n_ions", "n_traj", "traj0", "row0", "n_rows", "device", "substeps_per_md",
-        "renormalize", "quad", "reserved")] + [(k, ctypes.c_double) for k in (
+        "renormalize", "quad", "plan_n")] + [(k, ctypes.c_double) for k in (
             "L", "kappa", "rcut", "dtq", "detuning", "detuningDP", "Om", "OmDP", "dR", "kRat", "vKick", "vKickDP", "g2E",
             "pv2qv", "fracOfSig", "Te", "sig0", "density")] + [("seed", ctypes.c_uint64)]
 
@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
-    "mdqt_vv_steps",
+    "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def load_library():
     L.mdqt_autocorrelations.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp]
     L.mdqt_vv_steps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                 ctypes.c_double]
+    L.mdqt_set_ion_counts.argtypes = [vp, vp]
+    L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
     L.mdqt_vel_dist_partial.argtypes = [vp, vp, vp]
     _lib = L
@@ -253,6 +255,24 @@ class Engine:
 
     def sync(self):
         self._ck(self.lib.mdqt_sync(self.h))
+
+    def set_ion_counts(self, counts):
+        """Ensemble whose jobs drew different N (SU:299-337): trajectory b holds counts[b] <= n_ions ions."""
+        if counts is None:
+            self._ck(self.lib.mdqt_set_ion_counts(self.h, None))
+            return
+        c = np.ascontiguousarray(counts, dtype=np.int32)
+        assert c.shape == (self.B,)
+        self._ck(self.lib.mdqt_set_ion_counts(self.h, ctypes.c_void_p(c.ctypes.data)))
+
+    def set_traj_seeds(self, seeds):
+        """One Philox key per trajectory (the reference seeds every SLURM-array job separately, SU:1219)."""
+        if seeds is None:
+            self._ck(self.lib.mdqt_set_traj_seeds(self.h, None))
+            return
+        c = np.ascontiguousarray(seeds, dtype=np.uint64)
+        assert c.shape == (self.B,)
+        self._ck(self.lib.mdqt_set_traj_seeds(self.h, ctypes.c_void_p(c.ctypes.data)))
 
     # ---- the reference's hot-path functions -----------------------------------------------------------------
     def forces(self):
@@ -416,7 +436,7 @@ class Engine:
         self._ck(self.lib.mdqt_mark_wrapped(self.h, 1 if wrapped else 0))
 
     def enable_timing(self, on=True):
-        self._ck(self.lib.mdqt_enable_timing(self.h, 1 if on else 0))
+        self._ck(self.lib.mdqt_enable_timing(self.h, int(on)))  # 1: event pairs on stream launches; 2: stamps inside the graph
 
     def kernel_time_ms(self, which):
         ms, n = ctypes.c_double(), ctypes.c_int()

@@ -407,6 +407,57 @@ def seed_stream(ref, seed):
     libc.srand48(ctypes.c_long(seed))
 
 
+# ---- coupled statistical fixture (north-star: "temperatures and state populations must agree statistically") ------------
+COUPLED = dict(N0=500, tmax=2.4, seeds=list(range(101, 117)))
+
+
+def coupled_worker(seed):
+    """One reference trajectory of the COUPLED main loop (SU:1248-1381: forces() every 25 substeps, step(), qstep() with the
+    lasers ON, output() every 40 MD steps), 1 thread, the reference's own drand48 stream (srand48(seed)). The reference
+    hard-codes N0 = 3500 (#define, SU:69); N0 enters only init() and the directory name, so the start state for N0 = 500 is
+    drawn by mdqt_io_init_su -- the replica of init() that tests/test_hostio.py pins bitwise to the reference -- and the
+    box is set through the harness. Returns the parsed energies.dat rows and the mean S/P/D populations per output()."""
+    import shutil
+    import tempfile
+    from mdqtplasmasims_b200 import hostio
+    N0, tmax = COUPLED["N0"], COUPLED["tmax"]
+    st = hostio.init_su(seed, N0=N0, Ge=0.1)
+    ref = po.RefSU()
+    ref.set_box(st["L"], st["lDeb"])
+    ref.set_state(R=st["R"], V=st["V"], psi=st["psi"], tPart=st["tPart"], t=0.0)
+    seed_stream(ref, seed + 100000)
+    d = tempfile.mkdtemp() + "/"
+    ref.set_savedir(d)
+    ref.set_counters(-1, 0)                      # c0 = -1 after init() (SU:347)
+    ref.lib.ref_su_set_Epot0(ref.epot())         # Epot0 = Epot (SU:345-346)
+    nsub = ref.run_until(tmax, do_output=1)
+    en = np.loadtxt(os.path.join(d, "energies.dat"), ndmin=2)
+    pops = []
+    for k in range(en.shape[0]):
+        a = np.loadtxt(os.path.join(d, "statePopulationsVsVTime%06d.dat" % k), ndmin=2)
+        pops.append([a[:, 1].mean(), a[:, 2].mean(), a[:, 3].mean(), a[:, 0].std()])
+    fin = ref.get_state()
+    recent = float((fin["tPart"] < 25 * ref.consts["dtq"] * 0.999).mean())  # ions that jumped within the last 25 substeps
+    shutil.rmtree(d, ignore_errors=True)
+    return dict(seed=seed, N=st["N"], nsub=nsub, energies=en, pops=np.array(pops), recent_jump_frac=recent,
+                norm_final=float((fin["psi"] ** 2).sum(axis=(1, 2)).mean()))
+
+
+def gen_su_coupled(procs=7):
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(coupled_worker, COUPLED["seeds"], chunksize=1)
+    nrow = min(r["energies"].shape[0] for r in res)
+    np.savez(os.path.join(OUT, "su_coupled.npz"), N0=COUPLED["N0"], tmax=COUPLED["tmax"], seeds=np.array([r["seed"] for r in res]),
+             N=np.array([r["N"] for r in res]), nsub=np.array([r["nsub"] for r in res]),
+             energies=np.stack([r["energies"][:nrow] for r in res]), pops=np.stack([r["pops"][:nrow] for r in res]),
+             recent_jump_frac=np.array([r["recent_jump_frac"] for r in res]), norm_final=np.array([r["norm_final"] for r in res]))
+    e = np.stack([r["energies"][:nrow] for r in res])
+    print("su_coupled: %d seeds, N=%s, %d outputs; <EkinX>(t_end)=%.5g <EkinY>=%.5g popP=%.4f" %
+          (len(res), [r["N"] for r in res], nrow, e[:, -1, 1].mean(), e[:, -1, 2].mean(),
+           np.mean([r["pops"][-1, 1] for r in res])))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     po.build()
@@ -424,6 +475,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--ensemble" in sys.argv:
         gen_su_ensemble_stats()
+        sys.exit(0)
+    if "--coupled" in sys.argv:
+        gen_su_coupled()
         sys.exit(0)
     gen_su_forces()
     gen_su_nojump()
