@@ -35,6 +35,7 @@ MD_PER_STEP = 40          # sampleFreq (SU:78)
 FLOP_PER_PAIR = 34
 BYTES_PER_ION_STEP = 520
 FLOP_PER_ION_STEP = 1700  # ~1.7 kflop per no-jump 12-level ion-step (sparse H, 4 stages)
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 lanes x 2 flop x 1.965 GHz = 37.2 (B200 nominal)
 N0 = 3500
 
 
@@ -199,6 +200,16 @@ def run_ours(args):
     k1_ms, k1_n = eng.kernel_time_ms(0)
     k2_ms, k2_n = eng.kernel_time_ms(1)
     eng.enable_timing(False)
+    k1_pair_ms, k2_pair_ms = k1_ms, k2_ms      # CUDA-event pair around every single stream launch (includes launch latency)
+    # the force kernel's average launch duration: CUDA events on the engine's stream around ONE replayed graph of back-to-back
+    # launches (no per-launch event / launch-latency overhead) -- this is what `roofline.achieved` uses
+    k1_ms = float(np.median([eng.time_forces(40) for _ in range(5)]))
+    # inside the production graph: %globaltimer stamps written by the kernels (earliest CTA start .. latest CTA end)
+    eng.enable_timing(2)
+    one_step()
+    g_k1, _ = eng.kernel_time_ms(0); g_k2, _ = eng.kernel_time_ms(1); g_gap12, _ = eng.kernel_time_ms(2); g_gap21, _ = eng.kernel_time_ms(3)
+    eng.enable_timing(False)
+    k2_ms = g_k2
     pairs_per_launch = float(N0) * N0 * B
     k1_tflops = FLOP_PER_PAIR * pairs_per_launch / (k1_ms * 1e-3) / 1e12
     k2_gbs = BYTES_PER_ION_STEP * (N0 * B * 25) / (k2_ms * 1e-3) / 1e9
@@ -221,10 +232,17 @@ def run_ours(args):
     # ---- extra: ensemble throughput mode (config 4 shape: 64 trajectories batched per GPU) -----------------------------------
     if args.ensemble > 1:
         Be = args.ensemble
-        pe = su_params(n_ions=N0, N0=N0, n_traj=Be, traj0=1000 + rank * Be, seed=12345, device=local)
+        # every reference job draws its own N ~ Binomial(729 N0, 1/729) (SU:299-337): unequal ion counts in one handle
+        counts = np.random.default_rng(4321 + rank).binomial(729 * N0, 1.0 / 729, size=Be).astype(np.int32)
+        cap = int(counts.max())
+        pe = su_params(n_ions=cap, N0=N0, n_traj=Be, traj0=1000 + rank * Be, seed=12345, device=local, plan_n=N0)
         ee = Engine(pe)
-        Re, Ve, Pe, Te_ = synthetic_state(N0, pe.L, 1000 + rank * Be, Be)
+        ee.set_ion_counts(counts)
+        ee.set_traj_seeds(np.arange(Be, dtype=np.uint64) + 777 + rank * Be)
+        Re, Ve, Pe, Te_ = synthetic_state(cap, pe.L, 1000 + rank * Be, Be)
         ee.upload(R=Re, V=Ve, psi=Pe, tPart=Te_, t=0.0, substep=0)
+        ions_e = float(counts.sum())
+        pairs_e = float((counts.astype(np.float64) ** 2).sum())
         es = torch.cuda.ExternalStream(ee.lib.mdqt_stream(ee.h), device=torch.device("cuda", local))
         nmd = 4
         ee.md_steps(nmd); ee.md_steps(nmd); ee.sync()
@@ -233,27 +251,30 @@ def run_ours(args):
         a.record(es); ee.md_steps(2 * nmd); b_.record(es)
         ee.sync(); torch.cuda.synchronize(); barrier()
         ms = max_over_ranks(a.elapsed_time(b_))
-        ee.enable_timing(True)  # per-kernel split of the batched step (event pair per launch)
+        ee.enable_timing(2)  # per-kernel split of the batched step (stamps inside the replayed graph)
         ee.md_steps(nmd)
         e1_ms, _ = ee.kernel_time_ms(0)
         e2_ms, _ = ee.kernel_time_ms(1)
         ee.enable_timing(False)
-        extras["ensemble"] = {"traj_per_gpu": Be, "ion_steps_per_s": sum_over_ranks(float(N0) * Be * 25 * 2 * nmd) / (ms * 1e-3),
-                              "pair_interactions_per_s": sum_over_ranks(float(N0) * N0 * Be * 2 * nmd) / (ms * 1e-3),
+        extras["ensemble"] = {"traj_per_gpu": Be, "ion_counts": "N_b ~ Binomial(729*3500, 1/729): min %d, max %d (mdqt_set_ion_counts)" % (counts.min(), cap),
+                              "ion_steps_per_s": sum_over_ranks(ions_e * 25 * 2 * nmd) / (ms * 1e-3),
+                              "pair_interactions_per_s": sum_over_ranks(pairs_e * 2 * nmd) / (ms * 1e-3),
                               "ms_per_md_step": ms / (2 * nmd),
-                              "k_pairs_ms": e1_ms, "k_pairs_fp64_frac": FLOP_PER_PAIR * float(N0) * N0 * Be / (e1_ms * 1e-3) / 1e12 / fp64_peak,
+                              "k_pairs_ms": e1_ms, "k_pairs_fp64_frac": FLOP_PER_PAIR * pairs_e / (e1_ms * 1e-3) / 1e12 / fp64_peak,
+                              "k_pairs_fp64_frac_nominal": FLOP_PER_PAIR * pairs_e / (e1_ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
                               "k_substeps_ms": e2_ms,
-                              "k_substeps_fp64_frac": FLOP_PER_ION_STEP * float(N0) * Be * 25 / (e2_ms * 1e-3) / 1e12 / fp64_peak}
+                              "k_substeps_fp64_frac": FLOP_PER_ION_STEP * ions_e * 25 / (e2_ms * 1e-3) / 1e12 / fp64_peak}
         ee.close()
 
     # ---- extra: large-N row decomposition with an NCCL all-gather of positions per MD step (config 5 shape) -----------------
-    if args.large_n > 0:
-        from mdqtplasmasims_b200 import sharding
-        NL = (args.large_n // world) * world
+    for key, n_large in (("large_n", args.large_n), ("large_n_1e6", args.large_n2)):
+        if n_large <= 0:
+            continue
+        from mdqtplasmasims_b200 import sharding, synthetic
+        NL = (n_large // world) * world
         row0, rows = sharding.row_block(NL, world, rank)
         pl = su_params(n_ions=NL, N0=NL, row0=row0, n_rows=rows, seed=777, device=local)
         el = Engine(pl)
-        from mdqtplasmasims_b200 import synthetic
         Rl = synthetic.random_positions(NL, pl.L, seed=777)
         el.upload(R=Rl, V=np.zeros((3, NL)), psi=synthetic.random_s_state(NL, 12, seed=777), tPart=np.zeros(NL), t=0.0, substep=0)
         ls = torch.cuda.ExternalStream(el.lib.mdqt_stream(el.h), device=torch.device("cuda", local))
@@ -280,18 +301,23 @@ def run_ours(args):
         b_.record(ls)
         el.sync(); torch.cuda.synchronize(); barrier()
         ms = max_over_ranks(a.elapsed_time(b_)) / nl
-        # output() observables of the row-decomposed run (outside the timed region): partial sums + two small all-reduces
-        obs = None
+        # output() observables of the run (outside the timed region): one rank computes them directly, several ranks
+        # all-reduce their partial sums -- the printed digits must not depend on the number of GPUs
         if world > 1:
             with torch.cuda.device(local):
                 dd = sharding.distributed_diagnostics(el, NL, dist)
-            obs = {"epot_per_ion": float(dd["epot"]), "ekin_x": float(dd["ekin_x"]), "collective": "2 x ncclAllReduce of 5 fp64"}
-        extras["large_n"] = {"n_ions": NL, "scaling": "strong", "rows_per_gpu": rows, "ms_per_md_step": ms, "observables": obs,
-                             "pair_interactions_per_s": float(NL) * NL / (ms * 1e-3),
-                             "ion_steps_per_s": float(NL) * 25 / (ms * 1e-3),
-                             "fp64_frac": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (fp64_peak * world),
-                             "collective": "ncclAllGather of 3 x N/G fp64 per rank per MD step" if world > 1 else "none (1 GPU)"}
+            obs = {"epot_per_ion": repr(float(dd["epot"])), "ekin_x": repr(float(dd["ekin_x"])), "collective": "2 x ncclAllReduce of 5 fp64"}
+        else:
+            dd = el.diagnostics()
+            obs = {"epot_per_ion": repr(float(dd["epot"])), "ekin_x": repr(float(dd["ekin_x"])), "collective": "none (1 GPU)"}
+        extras[key] = {"n_ions": NL, "scaling": "strong", "rows_per_gpu": rows, "ms_per_md_step": ms, "md_steps_timed": nl, "observables": obs,
+                       "pair_interactions_per_s": float(NL) * NL / (ms * 1e-3),
+                       "ion_steps_per_s": float(NL) * 25 / (ms * 1e-3),
+                       "fp64_frac": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (fp64_peak * world),
+                       "fp64_frac_nominal": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (FP64_NOMINAL_TFLOPS * world),
+                       "collective": "ncclAllGather of 3 x N/G fp64 per rank per MD step" if world > 1 else "none (1 GPU)"}
         el.close()
+        del Rdev
 
     # ---- extra: the MD-family shapes (BASELINE configs[0] and [2]): MDStep at N=4096 and the 7-level pump stage -------------
     if args.md_family and rank == 0:
@@ -338,7 +364,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_sample(threads=os.cpu_count() or 1, budget_s=20.0)
+        cpu = cpu_baseline_block()
 
     if rank == 0:
         traffic = None
@@ -362,11 +388,19 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "ion-steps/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes,
                     "api": "mdqt_md_steps_host (C ABI), pinned host buffers"},
             "gpu_launches": K * MD_PER_STEP * 2,
-            "roofline": {"bound": "fp64", "kernel": "k_pairs (all-pairs Yukawa force)", "achieved": k1_tflops, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak, "traffic": traffic,
+            "fp64_tflops_probe": fp64_peak, "fp64_tflops_nominal": FP64_NOMINAL_TFLOPS,
+            "in_graph_us": {"k_pairs": g_k1 * 1e3, "k_substeps": g_k2 * 1e3, "gap_pairs_to_substeps": g_gap12 * 1e3,
+                            "gap_substeps_to_pairs": g_gap21 * 1e3,
+                            "how": "%globaltimer stamps written by the kernels inside the replayed production graph "
+                                   "(earliest CTA start to latest CTA end per launch), mean over one bench step"},
+            "roofline": {"bound": "fp64", "kernel": "k_pairs_items (all-pairs Yukawa force)", "achieved": k1_tflops, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": k1_tflops / fp64_peak, "frac_nominal": k1_tflops / FP64_NOMINAL_TFLOPS,
+                         "frac_in_md_graph": FLOP_PER_PAIR * pairs_per_launch / (g_k1 * 1e-3) / 1e12 / fp64_peak,
+                         "launch_ms_event_pair_per_stream_launch": k1_pair_ms, "traffic": traffic,
                          "peak_source": "measured live: DFMA-chain probe kernel (mdqt_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": pairs_per_launch, "launch_ms": k1_ms, "launches_timed": k1_n,
-                         "timing": "second pass over the same steps with a CUDA-event pair around every launch",
+                         "timing": "CUDA-event pair on the engine's stream around one replayed graph of 40 back-to-back launches, median of 5 "
+                                   "(launch_ms_event_pair_per_stream_launch = the round-1 method, which adds launch latency to every launch)",
                          "note": "HBM/tensor do not bound this kernel. Per ordered pair the inner loop issues 23 FP64-pipe + ~20.5 other "
                                  "instructions (cuobjdump; exp and rsqrt expand). An FP64 warp instruction holds the sub-partition's issue "
                                  "port 2 cycles on sm_100, so the issue-bound ceiling is 34 flop x 32 lanes / (2*23+20.5 cycles) = 0.51 of "
@@ -375,6 +409,7 @@ def run_ours(args):
                                  "prologue/epilogue and in-SM tail are exposed (per-CTA phase trace in profiles/)"},
             "roofline_substeps": {"bound": "hbm", "kernel": "k_substeps (25 fused step()+qstep())", "achieved": k2_gbs, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": k2_gbs / hbm_peak, "peak_source": peak_src, "launch_ms": k2_ms,
+                                  "launch_ms_event_pair_per_stream_launch": k2_pair_ms, "timing": "in-graph %globaltimer stamps",
                                   "flop_per_ion_step": FLOP_PER_ION_STEP,
                                   "fp64_tflops": FLOP_PER_ION_STEP * (N0 * B * 25) / (k2_ms * 1e-3) / 1e12,
                                   "fp64_frac": FLOP_PER_ION_STEP * (N0 * B * 25) / (k2_ms * 1e-3) / 1e12 / fp64_peak,
@@ -400,58 +435,79 @@ import json, os, sys, time
 sys.path.insert(0, %(root)r)
 import numpy as np
 from oracle import pyoracle as po
-budget, steps = float(sys.argv[1]), int(sys.argv[2])
+budget, steps, md_max = float(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 kind = "reference" if po.ref_available("su") else "port"
-res = []
 if kind == "reference":
     ref = po.RefSU()
     N = ref.init(12345)          # the reference's own init(): random frozen start, N ~ Binomial around N0 = 3500
-    ref.forces(); ref.step(); ref.qstep()
-    for k in range(steps):
-        t0 = time.perf_counter(); ref.forces(); tf = time.perf_counter() - t0
-        m, ts = 0, 0.0
-        while m < 25 and (m < 2 or ts < budget / max(1, steps)):
-            t0 = time.perf_counter(); ref.step(); ref.qstep(); ts += time.perf_counter() - t0; m += 1
-        res.append((tf, ts / m, m))
+    def forces(): ref.forces()
+    def substep(): ref.step(); ref.qstep()
 else:
     orc = po.Oracle()
     p, ratio = po.su_params()
     N = 3500
     L = (3500 * 4 * np.pi / 3) ** 0.333333333
     rng = np.random.default_rng(12345)
-    R = rng.uniform(0, L, (3, N)); V = np.zeros((3, N)); psi = np.zeros((N, 12, 2)); psi[:, 0, 0] = 1; tp = np.zeros(N); t = 0.0
-    for k in range(steps):
-        t0 = time.perf_counter(); F = orc.forces_su(R, L, 1 / np.sqrt(0.3)); tf = time.perf_counter() - t0
-        m, ts = 0, 0.0
-        while m < 25 and (m < 2 or ts < budget / max(1, steps)):
-            t0 = time.perf_counter(); orc.step_su(R, V, F, L, p.dtq, t); Vx = V[0].copy()
-            t, _ = orc.qstep12(psi, Vx, tp, t, p, rng.uniform(size=(N, 5))); V[0] = Vx
-            ts += time.perf_counter() - t0; m += 1
-        res.append((tf, ts / m, m))
-print(json.dumps({"kind": kind, "N": int(N), "res": res}))
+    st = dict(R=rng.uniform(0, L, (3, N)), V=np.zeros((3, N)), psi=np.zeros((N, 12, 2)), tp=np.zeros(N), t=0.0, F=None)
+    st["psi"][:, 0, 0] = 1
+    def forces(): st["F"] = orc.forces_su(st["R"], L, 1 / np.sqrt(0.3))
+    def substep():
+        orc.step_su(st["R"], st["V"], st["F"], L, p.dtq, st["t"]); Vx = st["V"][0].copy()
+        st["t"], _ = orc.qstep12(st["psi"], Vx, st["tp"], st["t"], p, rng.uniform(size=(N, 5))); st["V"][0] = Vx
+# calibration: one forces() and two substeps -> how many whole MD steps of a 40-step sampling interval fit the budget
+t0 = time.perf_counter(); forces(); tf = time.perf_counter() - t0
+t0 = time.perf_counter(); substep(); substep(); ts = (time.perf_counter() - t0) / 2
+m = int(max(1, min(md_max, budget / max(1, steps) / (tf + 25 * ts))))
+res = []
+for k in range(steps):
+    t0 = time.perf_counter()
+    for _ in range(m):
+        forces()
+        for _ in range(25):
+            substep()
+    res.append(time.perf_counter() - t0)
+print(json.dumps({"kind": kind, "N": int(N), "md_steps_per_step": m, "step_s": res, "forces_s": tf, "substep_s": ts}))
 """
 
 
-def cpu_reference_sample(threads, budget_s, steps=1):
-    """Time the reference's CPU path on a bounded sample: `steps` x { 1 forces() + up to 25 x (step()+qstep()) }."""
+def cpu_reference_run(threads, budget_s, steps, md_max=MD_PER_STEP):
+    """Run the reference's CPU path for REAL: `steps` steps of m whole MD steps each (m <= 40 sized to the budget), every MD
+    step = forces() + 25 x { step(); qstep(); } (SU:1369-1378). Returns the child's record (wall seconds per step)."""
     env = dict(os.environ, OMP_NUM_THREADS=str(threads))
-    try:
-        out = subprocess.run([sys.executable, "-c", _CPU_CHILD % {"root": ROOT}, str(budget_s), str(steps)], env=env,
-                             capture_output=True, text=True, timeout=600)
-        d = json.loads(out.stdout.strip().splitlines()[-1])
-    except Exception as e:  # pragma: no cover
-        return {"value": None, "unit": "ion-steps/s", "cores": threads, "kind": "unavailable", "sample": "failed: %r" % (e,)}
-    per = [N_ * 25.0 / (tf + 25.0 * tsub) for (tf, tsub, m), N_ in ((r, d["N"]) for r in d["res"])]
-    tf = float(np.median([r[0] for r in d["res"]])); tsub = float(np.median([r[1] for r in d["res"]]))
-    used_threads = threads if d["kind"] == "reference" else 1
-    return {"value": float(np.median(per)), "unit": "ion-steps/s", "cores": used_threads, "kind": d["kind"],
-            "per_step_values": per,
-            "sample": "N=%d; per step: 1 forces() (%.3f s) + %d x {step(); qstep();} (%.4f s each), extrapolated to a full MD step "
-                      "of 25 substeps; %s" % (d["N"], tf, d["res"][0][2], tsub,
-                                              "unmodified reference sources (oracle/_ref, Armadillo shim for the 12x12 algebra), "
-                                              "OMP_NUM_THREADS=%d as shipped -- note its OpenMP force loop races (SURVEY App. C Q1)" % threads
-                                              if d["kind"] == "reference" else "oracle restatement (scalar C), 1 thread"),
-            "pair_interactions_per_s_ordered_equiv": d["N"] * (d["N"] - 1.0) / tf}
+    out = subprocess.run([sys.executable, "-c", _CPU_CHILD % {"root": ROOT}, str(budget_s), str(steps), str(md_max)], env=env,
+                         capture_output=True, text=True, timeout=900)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+REF_LABEL = ("unmodified reference sources (oracle/_ref: laserCoolingPlusExpansionMDQTSpeedUp.cpp compiled g++ -std=c++11 -fopenmp -O3) "
+             "with the from-scratch Armadillo shim for the 12x12 algebra (real Armadillo is not installable here)")
+
+
+def cpu_baseline_block(budget_s=18.0):
+    """cpu_baseline of our arm's line: the reference on the host cores at OMP_NUM_THREADS = 1 (the only race-free setting,
+    SURVEY App. C Q1), 4 (as shipped, slurm:7) and all cores; each a bounded sample of whole MD steps."""
+    ncpu = os.cpu_count() or 1
+    by = {}
+    kind, N = "unavailable", None
+    for thr, share in ((1, 0.45), (4, 0.25), (ncpu, 0.30)):
+        if str(thr) in by:
+            continue
+        try:
+            d = cpu_reference_run(thr, budget_s * share, steps=1)
+        except Exception as e:  # pragma: no cover
+            by[str(thr)] = {"value": None, "error": repr(e)}
+            continue
+        kind, N = d["kind"], d["N"]
+        t = d["step_s"][0]
+        by[str(thr)] = {"value": d["N"] * 25.0 * d["md_steps_per_step"] / t, "md_steps_run": d["md_steps_per_step"], "wall_s": t,
+                        "forces_s": d["forces_s"], "substep_s": d["substep_s"],
+                        "pair_interactions_per_s_ordered_equiv": d["N"] * (d["N"] - 1.0) / d["forces_s"]}
+    allv = by.get(str(ncpu), {})
+    return {"value": allv.get("value"), "unit": "ion-steps/s", "cores": ncpu if kind == "reference" else 1, "kind": kind,
+            "sample": "N=%s; whole MD steps (forces() + 25 x {step(); qstep();}) run for real, %s MD step(s) at all %d threads; %s; "
+                      "multi-thread values are 'as shipped': the OpenMP force loop races (SURVEY App. C Q1), 1 thread is the correct one"
+                      % (N, allv.get("md_steps_run"), ncpu, REF_LABEL if kind == "reference" else "oracle restatement (scalar C), 1 thread"),
+            "by_threads": by}
 
 
 def run_reference(args):
@@ -460,19 +516,31 @@ def run_reference(args):
         return  # rank 0 alone runs the CPU arm; the others exit 0 without work
     threads = os.cpu_count() or 1
     K, W = args.steps, max(1, min(args.warmup, 3))
-    # bounded: each step is one forces() + a sample of the 25 substeps; the whole run is capped at ~4 minutes
-    budget = min(240.0, 8.0 * (K + W))
+    # every step is m whole MD steps run for real (m <= 40, sized so that the K + W steps end within ~2.5 minutes); the line
+    # reports what was run: ms_per_step is the measured wall time of a step of m MD steps, value = N x 25 x m / that
     t0 = time.perf_counter()
-    cpu = cpu_reference_sample(threads, budget_s=budget, steps=K + W)
+    try:
+        d = cpu_reference_run(threads, budget_s=150.0, steps=K + W)
+    except Exception as e:  # pragma: no cover
+        print(json.dumps({"impl": "reference", "unavailable": "CPU reference run failed: %r" % (e,)}), flush=True)
+        return
     wall = time.perf_counter() - t0
-    vals = cpu.pop("per_step_values", [cpu["value"]])[W:] or [cpu["value"]]
-    value = float(np.median(vals)) if cpu["value"] is not None else None
-    cpu["value"] = value
+    m, N = d["md_steps_per_step"], d["N"]
+    timed = d["step_s"][W:]
+    step_s = float(np.mean(timed))
+    value = N * 25.0 * m * len(timed) / float(np.sum(timed))
+    cpu = {"value": value, "unit": "ion-steps/s", "cores": threads if d["kind"] == "reference" else 1, "kind": d["kind"],
+           "sample": "N=%d; %d timed steps of %d whole MD steps each (of the 40 of a sampling interval), every MD step = forces() + 25 x "
+                     "{step(); qstep();} run for real; %s; OMP_NUM_THREADS=%d as shipped -- its OpenMP force loop races (SURVEY App. C Q1)"
+                     % (N, len(timed), m, REF_LABEL if d["kind"] == "reference" else "oracle restatement (scalar C), 1 thread", threads)}
     line = {"impl": "reference", "metric": "ion-steps/s (MDQT) & Yukawa pair-interactions/s", "value": value, "unit": "ion-steps/s",
-            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": (N0 * 25.0 * MD_PER_STEP / value * 1e3) if value else None,
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": step_s * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "mdqt_thesis_N0_3500 (BASELINE configs[1]) on the host CPU: the reference's forces()/step()/qstep()",
-                       "n_ions": N0, "md_steps_per_step": MD_PER_STEP, "substeps_per_md_step": 25, "host_threads": threads},
+            "config": {"workload": "mdqt_thesis_N0_3500 (BASELINE configs[1]): 12-level Sr+ MDQT, detuning=-1, detuningDP=+1, "
+                                   "Om=OmDP=1, density=2, Ge=0.1; one trajectory per GPU",
+                       "n_ions": N, "md_steps_per_step": m, "substeps_per_md_step": 25, "host_threads": threads,
+                       "note": "the reference's forces()/step()/qstep() on the host CPU; a step is %d of the 40 MD steps of a sampling "
+                               "interval when the host is too slow for all 40 within the run budget" % m},
             "cpu_baseline": cpu, "wall_s": wall,
             "e2e": {"value": value, "unit": "ion-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -487,6 +555,7 @@ def main():
     ap.add_argument("--traj-per-gpu", type=int, default=1)
     ap.add_argument("--ensemble", type=int, default=64, help="extra pass: trajectories batched per GPU (0/1 = skip)")
     ap.add_argument("--large-n", type=int, default=200000, help="extra pass: row-decomposed large-N MD step (0 = skip)")
+    ap.add_argument("--large-n2", type=int, default=1000000, help="second large-N pass: BASELINE configs[4], N = 10^6 (0 = skip)")
     ap.add_argument("--no-md-family", dest="md_family", action="store_false", help="skip the MD-only / 7-level pump extras")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -206,6 +206,10 @@ int mdqt_force_plan(mdqt_handle* h, int* nsplit, int* jlen);
  * which: 0 = force kernel, 1 = substep kernel, 2 = gap force -> substep, 3 = gap substep -> next force (2, 3: on = 2 only). */
 int mdqt_enable_timing(mdqt_handle* h, int on);
 int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* launches);
+/* Average duration of one force-kernel launch (ms), timed with a CUDA-event pair on the handle's stream around ONE replayed
+ * graph of `reps` back-to-back launches (after a warm-up replay): no per-launch event or launch-latency overhead. F is
+ * overwritten with the same values every launch, so the state is unchanged. */
+int mdqt_time_forces(mdqt_handle* h, int reps, double* ms_per_launch);
 /* FP64 FMA-chain microbenchmark on the handle's device: returns achieved TFLOP/s (2 flop per DFMA). */
 int mdqt_fp64_peak(mdqt_handle* h, double* tflops);
 

@@ -1127,6 +1127,35 @@ int mdqt_kernel_time_ms(mdqt_handle* h, int which, double* ms_per_launch, int* l
   return MDQT_OK;
 }
 
+int mdqt_time_forces(mdqt_handle* h, int reps, double* ms_per_launch) {
+  if (!h || !ms_per_launch || reps < 1) return fail(MDQT_EINVAL, "bad argument");
+  CU(cudaSetDevice(h->p.device));
+  refresh_fixed(h);
+  cudaGraph_t graph;
+  cudaGraphExec_t exec = nullptr;
+  CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  for (int k = 0; k < reps; k++) launch_forces(force_args(h), h->stream);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaGraphLaunch(exec, h->stream);  // warm-up replay
+  cudaEventRecord(e0, h->stream);
+  cudaGraphLaunch(exec, h->stream);
+  cudaEventRecord(e1, h->stream);
+  e = cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaGraphExecDestroy(exec);
+  if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("mdqt_time_forces: ") + cudaGetErrorString(e));
+  *ms_per_launch = (double)ms / reps;
+  return MDQT_OK;
+}
+
 int mdqt_fp64_peak(mdqt_handle* h, double* tflops) {
   if (!h || !tflops) return fail(MDQT_EINVAL, "null argument");
   CU(cudaSetDevice(h->p.device));

@@ -47,7 +47,7 @@ ABI_SYMBOLS = [
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
-    "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds",
+    "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def load_library():
     L.mdqt_vv_steps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                 ctypes.c_double]
     L.mdqt_set_ion_counts.argtypes = [vp, vp]
+    L.mdqt_time_forces.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
     L.mdqt_vel_dist_partial.argtypes = [vp, vp, vp]
@@ -442,6 +443,12 @@ class Engine:
         ms, n = ctypes.c_double(), ctypes.c_int()
         self._ck(self.lib.mdqt_kernel_time_ms(self.h, which, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def time_forces(self, reps=20):
+        """ms per force-kernel launch: CUDA events around one replayed graph of ``reps`` back-to-back launches."""
+        v = ctypes.c_double()
+        self._ck(self.lib.mdqt_time_forces(self.h, reps, ctypes.byref(v)))
+        return v.value
 
     def fp64_peak_tflops(self):
         v = ctypes.c_double()

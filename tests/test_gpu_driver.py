@@ -113,3 +113,35 @@ def test_output_files_match_reference_output(tmp_path):
     for f in ("energies.dat", "vel_distX_time000007.dat", "vel_distY_time000007.dat", "vel_distZ_time000007.dat",
               "statePopulationsVsVTime000007.dat"):
         _compare_text(open(db + f).read(), open(da + f).read(), rtol=2e-6, atol=1e-300, min_identical=0.995)
+
+
+DROPIN = os.path.join(ROOT, "oracle", "_ref", "su_dropin")
+
+
+@pytest.mark.skipif(not os.path.exists(DROPIN), reason="oracle/_ref/su_dropin not built (needs /root/reference at build time)")
+def test_reference_main_runs_on_the_abi(tmp_path, golden_dir):
+    """The drop-in boundary executed: the UNMODIFIED reference program's own main() (directory setup, operator tables, init(),
+    the time loop, output(), writeConditions()) with forces()/step()/qstep()/Epotential() routed through the C ABI exactly as
+    INTEGRATION.md section 2 shows (examples/su_dropin.cpp). srand48(777), lasers off, tmax = 0.081: the files it writes are
+    the files the all-CPU reference wrote (tests/golden/su_mainloop)."""
+    gdir = os.path.join(golden_dir, "su_mainloop")
+    r = subprocess.run([DROPIN, "1", "--seed", "777", "--Om", "0", "--OmDP", "0", "--tmax", "0.081"], capture_output=True, text=True,
+                       timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    d = hostio.dirname(str(tmp_path) + "/dataLaserCool/", Om=0.0, OmDP=0.0, job=1)
+    assert os.path.isdir(d), os.listdir(str(tmp_path))
+    gold = {f[:-3]: gzip.open(os.path.join(gdir, f), "rt").read() for f in os.listdir(gdir) if f.endswith(".gz")}
+    for f, g in gold.items():
+        path = os.path.join(d, f)
+        assert os.path.exists(path), f
+        ours = open(path).read()
+        if f.startswith(("ions_", "wvFns_", "VZERO_")):
+            assert ours == g, f
+        elif f.startswith("conditions_"):
+            _compare_text(ours, g, rtol=2e-6, atol=1e-9, min_identical=0.999)
+        elif f == "energies.dat":
+            a, b = _numbers(ours), _numbers(g)
+            assert a.shape == b.shape == (1, 7)
+            assert np.allclose(a[0, :5], b[0, :5], rtol=2e-6) and abs(a[0, 5] - b[0, 5]) < 1e-9 and abs(a[0, 6] - b[0, 6]) < 1e-9
+        else:  # vel_dist* and statePopulations*: computed by the reference's own output() from the downloaded state
+            _compare_text(ours, g, rtol=2e-5, atol=1e-12, min_identical=0.99)
