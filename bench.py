@@ -278,19 +278,15 @@ def run_ours(args):
         Rl = synthetic.random_positions(NL, pl.L, seed=777)
         el.upload(R=Rl, V=np.zeros((3, NL)), psi=synthetic.random_s_state(NL, 12, seed=777), tPart=np.zeros(NL), t=0.0, substep=0)
         ls = torch.cuda.ExternalStream(el.lib.mdqt_stream(el.h), device=torch.device("cuda", local))
-        ld = el.ld
-
-        class _CAI:  # expose the engine's position buffer to torch for the in-place NCCL all-gather
-            __cuda_array_interface__ = {"shape": (3, ld), "typestr": "<f8", "data": (el.device_ptr(0), False), "version": 3}
-        Rdev = torch.as_tensor(_CAI(), device=torch.device("cuda", local))
+        if world > 1:  # the communicator lives in the library: rank 0's NCCL id travels through torch.distributed
+            box = [Engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            el.comm_init(box[0], rank, world)
 
         def md_step_large():
-            el.forces()
-            el.step_qstep(25)
-            if world > 1:
-                with torch.cuda.stream(ls):  # the collective is ordered after the substep kernel on the engine's stream
-                    sharding.allgather_positions(Rdev, NL, world, rank, dist)
-                el.mark_wrapped(True)  # R was written from outside: the fixed-point copy is refreshed before the next force call
+            # forces over the own rows x all j; 25 fused substeps of the own rows; with several ranks ONE in-place ncclAllGather of
+            # the fixed-point positions on a communication stream, overlapped with the own-row j chunks of the next force call
+            el.md_steps(1)
 
         md_step_large(); el.sync(); torch.cuda.synchronize(); barrier()
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -303,21 +299,18 @@ def run_ours(args):
         ms = max_over_ranks(a.elapsed_time(b_)) / nl
         # output() observables of the run (outside the timed region): one rank computes them directly, several ranks
         # all-reduce their partial sums -- the printed digits must not depend on the number of GPUs
-        if world > 1:
-            with torch.cuda.device(local):
-                dd = sharding.distributed_diagnostics(el, NL, dist)
-            obs = {"epot_per_ion": repr(float(dd["epot"])), "ekin_x": repr(float(dd["ekin_x"])), "collective": "2 x ncclAllReduce of 5 fp64"}
-        else:
-            dd = el.diagnostics()
-            obs = {"epot_per_ion": repr(float(dd["epot"])), "ekin_x": repr(float(dd["ekin_x"])), "collective": "none (1 GPU)"}
+        dd = el.diagnostics()  # several ranks: partial sums over the own rows + two small ncclAllReduce calls inside the library
+        obs = {"epot_per_ion": repr(float(dd["epot"])), "ekin_x": repr(float(dd["ekin_x"])),
+               "collective": "2 x ncclAllReduce (1 and 5 fp64)" if world > 1 else "none (1 GPU)"}
         extras[key] = {"n_ions": NL, "scaling": "strong", "rows_per_gpu": rows, "ms_per_md_step": ms, "md_steps_timed": nl, "observables": obs,
                        "pair_interactions_per_s": float(NL) * NL / (ms * 1e-3),
                        "ion_steps_per_s": float(NL) * 25 / (ms * 1e-3),
                        "fp64_frac": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (fp64_peak * world),
                        "fp64_frac_nominal": FLOP_PER_PAIR * float(NL) * NL / (ms * 1e-3) / 1e12 / (FP64_NOMINAL_TFLOPS * world),
-                       "collective": "ncclAllGather of 3 x N/G fp64 per rank per MD step" if world > 1 else "none (1 GPU)"}
+                       "collective": ("one in-place ncclAllGather of a [3][N/G] int64 fixed-point block per rank and MD step, inside the "
+                                      "library (mdqt_comm_init), overlapped with the own-row j chunks of the next force call")
+                       if world > 1 else "none (1 GPU)"}
         el.close()
-        del Rdev
 
     # ---- extra: the MD-family shapes (BASELINE configs[0] and [2]): MDStep at N=4096 and the 7-level pump stage -------------
     if args.md_family and rank == 0:

@@ -192,6 +192,26 @@ void* mdqt_device_ptr(mdqt_handle* h, int which);
 int mdqt_device_ld(mdqt_handle* h);
 void* mdqt_stream(mdqt_handle* h);
 
+/* Row-decomposed large-N runs inside the library (one process or thread per GPU, NCCL over NVLink). Rank `rank` of `world`
+ * creates its handle with row0 = rank * N/world, n_rows = N/world (N divisible by world) and uploads ALL N positions (the
+ * other arrays matter for its own rows only). Rank 0 makes the 128-byte id (ncclGetUniqueId) and hands it to the others by
+ * any means; all ranks then call mdqt_comm_init concurrently (it is a collective). From then on:
+ *   mdqt_md_steps(h, n)      n x { forces over the own rows x all j; substeps of the own rows; all-gather of positions } --
+ *                            ONE in-place ncclAllGather of a [3][rows] block of fixed-point positions per rank and MD step, on a
+ *                            communication stream, overlapped with the j chunks of the next force call that lie inside the own rows;
+ *   mdqt_diagnostics, mdqt_vel_dist   whole-system values on every rank (partial sums + ncclAllReduce);
+ *   mdqt_populations_rows, mdqt_download_state   the rank's own rows (remote rows of R are NOT kept current: only their
+ *                            fixed-point copy, which is what the pair kernels read);
+ *   mdqt_comm_exchange_positions   the bare all-gather, after the caller's own mdqt_substeps.
+ * Forces, hence trajectories, are bitwise independent of the number of ranks. */
+int mdqt_comm_unique_id(void* id_out /* 128 bytes */);
+int mdqt_comm_init(mdqt_handle* h, const void* unique_id /* 128 bytes */, int rank, int world);
+int mdqt_comm_destroy(mdqt_handle* h);
+int mdqt_comm_exchange_positions(mdqt_handle* h);
+int mdqt_comm_allreduce(mdqt_handle* h, double* values, int n); /* sum over the ranks, in place, n <= 6019 */
+/* S/P/D populations of the handle's own rows: pops = double [n_traj][n_rows][3] (row-decomposed handles). */
+int mdqt_populations_rows(mdqt_handle* h, double* pops);
+
 /* After an external write into the device R buffer (e.g. the caller's own NCCL all-gather): tells the handle that R
  * changed, so the periodic fixed-point copy read by the pair kernels is refreshed before the next force evaluation. The
  * `wrapped` argument is ignored (the fixed-point minimum image is exact for wrapped and unwrapped coordinates alike). */

@@ -9,8 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmdqt_b200.so")
 DRIVER = os.path.join(HERE, "mdqt_run")
-SOURCES = ["mdqt_force.cu", "mdqt_qt.cu", "mdqt_diag.cu", "mdqt_capi.cu", "mdqt_io.cpp"]
-HEADERS = ["mdqt_internal.h", "mdqt_qtconsts.h", os.path.join("..", "..", "include", "mdqt.h"),
+SOURCES = ["mdqt_force.cu", "mdqt_qt.cu", "mdqt_diag.cu", "mdqt_capi.cu", "mdqt_comm.cu", "mdqt_io.cpp"]
+HEADERS = ["mdqt_internal.h", "mdqt_handle.h", "mdqt_fixed.cuh", "mdqt_qtconsts.h", os.path.join("..", "..", "include", "mdqt.h"),
            os.path.join("..", "..", "include", "mdqt_io.h")]
 DRIVER_SOURCES = ["mdqt_driver.cpp"]
 
@@ -39,7 +39,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     target = out or LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"] + ["-D" + d for d in defines] + [
-           "-o", target] + [os.path.join(CSRC, f) for f in SOURCES]
+           "-o", target] + [os.path.join(CSRC, f) for f in SOURCES] + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

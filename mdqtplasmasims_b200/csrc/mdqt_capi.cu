@@ -2,9 +2,7 @@
 // reference's host layouts (double R[3][ld], cx_mat wvFns[], SU:126-152) and the device SoA layout, and the
 // stream-ordered sequencing of the hot-path kernels (the body of the reference's main loop, SU:1369-1378).
 // There is no CPU fallback anywhere in this file: without a CUDA device every entry point fails.
-#include "../../include/mdqt.h"
-#include "mdqt_internal.h"
-#include "mdqt_qtconsts.h"
+#include "mdqt_handle.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -15,46 +13,14 @@
 #include <vector>
 
 using namespace mdqt;
+#define force_args mdqt_force_args
+#define qt_args mdqt_qt_args
+#define refresh_fixed mdqt_refresh_fixed
+#define enqueue_substeps mdqt_enqueue_substeps
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
-#define CU(call)                                                                                             \
-  do {                                                                                                       \
-    cudaError_t e_ = (call);                                                                                 \
-    if (e_ != cudaSuccess)                                                                                   \
-      return fail(MDQT_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                           \
-  } while (0)
-
-// one instantiated CUDA graph of `nsteps` MD steps, valid while the kernel arguments it froze are still the handle's
-struct GraphEntry { int nsteps; cudaGraphExec_t exec; ForceArgs fa; QTArgs qa; VVArgs va; };
-
-struct mdqt_handle {
-  mdqt_params p;
-  int N, B, S, ld, row0, nrows;
-  cudaStream_t stream;
-  double *R, *V, *F, *oldF, *psi, *tPart, *Fpart, *psi_stage, *epot_partials, *scalars, *pvel, *pops, *vhold, *forced_tag;
-  int* tagged;      // [B][N] spin tags + [B] counts (allocated on first use)
-  unsigned long long* gr_counts;  // [B][gr_max_bins]
-  double *vstore, *ac_partials, *ac_out; int vstore_T;  // vStore[B][3][N][T] and autocorrelation scratch
-  unsigned* counters;
-  long long* Rfix;  // periodic fixed-point copy of R (what the pair kernels read)
-  int rfix_dirty;   // R was written by an upload / externally: refresh Rfix before the next pair kernel
-  double* forced_u; int forced_nsub, forced_cursor;
-  double *forced_cu, *forced_cn;
-  QTConsts qc;
-  double t; uint64_t substep, vv_step;
-  int nsplit, jlen, itiles, ipt, jsub, rg, items;
-  int* nb;              // [B] per-trajectory ion counts on the device (ensembles with unequal N) or null
-  std::vector<int> nb_host;
-  uint64_t* seeds;      // [B] per-trajectory Philox keys or null
-  int timing;  // 0 off; 1 = CUDA-event pair around every stream launch; 2 = %globaltimer stamps inside the replayed graph
-  unsigned long long* stamps; size_t stamps_cap;  // [launch]{min start, max end} ns
-  std::vector<cudaEvent_t> ev;  // [force_start, force_end, sub_start, sub_end] per MD step when timing
-  size_t ev_used;
-  double time_ms[4]; int time_n[4];  // force kernel, substep kernel, gap force->substep, gap substep->force
-  double* clock;                    // device {t, substep index}: the simulation clock inside replayed graphs
-  std::vector<GraphEntry> graphs;   // small cache keyed by nsteps
-};
+int mdqt_fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { return mdqt_fail(code, msg); }
 
 __global__ void k_init_stamps(unsigned long long* s, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,7 +256,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
   h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
   h->gr_counts = nullptr; h->vstore = h->ac_partials = h->ac_out = nullptr; h->vstore_T = 0;
-  h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr;
+  h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr; h->comm = nullptr;
   h->timing = 0; h->ev_used = 0; h->stamps = nullptr; h->stamps_cap = 0;
   for (int k = 0; k < 4; k++) { h->time_ms[k] = 0; h->time_n[k] = 0; }
   plan_force(h);
@@ -333,6 +299,7 @@ int mdqt_destroy(mdqt_handle* h) {
   if (!h) return MDQT_OK;
   cudaSetDevice(h->p.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  mdqt_comm_release(h);
   double* bufs[] = {h->R, h->V, h->F, h->oldF, h->psi, h->psi_stage, h->tPart, h->Fpart, h->epot_partials, h->scalars,
                     h->pvel, h->pops, h->forced_u, h->forced_cu, h->forced_cn, h->vhold, h->forced_tag};
   for (double* b : bufs) if (b) cudaFree(b);
@@ -356,6 +323,7 @@ int mdqt_destroy(mdqt_handle* h) {
 
 int mdqt_sync(mdqt_handle* h) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (h->comm) mdqt_comm_sync_pending(h);
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   return MDQT_OK;
@@ -480,7 +448,7 @@ int mdqt_set_traj_seeds(mdqt_handle* h, const uint64_t* seeds) {
 // stale from the second force evaluation on (one force call per position exchange)
 #define NEED_ALL_ROWS(h, what) do { if ((h)->nrows != (h)->N) return fail(MDQT_ESTATE, what ": a row-decomposed handle allows one force evaluation per position exchange (use mdqt_comm_init, or call mdqt_forces / mdqt_substeps and exchange R yourself)"); } while (0)
 
-static ForceArgs force_args(mdqt_handle* h) {
+extern "C++" ForceArgs mdqt_force_args(mdqt_handle* h) {
   ForceArgs a;
   memset(&a, 0, sizeof(a));  // padding included: graph entries are compared bytewise
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
@@ -488,6 +456,7 @@ static ForceArgs force_args(mdqt_handle* h) {
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
   a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb;
   a.mg_chunk = ((1ULL << 40) + h->nsplit - 1) / h->nsplit; a.mg_gcap = ((1ULL << 40) + a.gcap - 1) / a.gcap;
+  { const int g2 = (h->nrows + 63) / 64; a.mg_gcap2 = ((1ULL << 40) + g2 - 1) / g2; }
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
   a.invL_lo = fma(-a.invL, a.L, 1.0) * a.invL;  // 1/L - fl(1/L), to first order
   a.half_l = (h->p.rcut == h->p.L / 2.) ? 1 : 0;
@@ -501,14 +470,15 @@ static ForceArgs force_args(mdqt_handle* h) {
 }
 
 // the pair kernels read the fixed-point copy of R: refresh it if R was written from outside the engine's kernels
-static void refresh_fixed(mdqt_handle* h) {
+extern "C++" void mdqt_refresh_fixed(mdqt_handle* h, bool wait_comm) {
+  if (wait_comm && h->comm) mdqt_comm_sync_pending(h);  // remote rows of Rfix may still be arriving on the communication stream
   if (!h->rfix_dirty) return;
   const double invL = 1.0 / h->p.L;
   launch_to_fixed(h->R, h->Rfix, state_elems(h), invL, fma(-invL, h->p.L, 1.0) * invL, h->stream);
   h->rfix_dirty = 0;
 }
 
-static QTArgs qt_args(mdqt_handle* h, int nsub, int do_step, int do_kick) {
+extern "C++" QTArgs mdqt_qt_args(mdqt_handle* h, int nsub, int do_step, int do_kick) {
   QTArgs a;
   memset(&a, 0, sizeof(a));
   const mdqt_params& p = h->p;
@@ -537,9 +507,10 @@ static cudaEvent_t next_event(mdqt_handle* h) {
   return h->ev[h->ev_used++];
 }
 
-static int enqueue_substeps(mdqt_handle* h, int nsub, int do_step, int do_kick) {
+extern "C++" int mdqt_enqueue_substeps(mdqt_handle* h, int nsub, int do_step, int do_kick, bool forces_partial) {
   if (h->forced_u && h->forced_cursor + nsub > h->forced_nsub) return fail(MDQT_ESTATE, "forced uniforms exhausted");
   QTArgs a = qt_args(h, nsub, do_step, do_kick);
+  if (forces_partial && forces_are_partial(force_args(h))) { a.fpart = h->Fpart; a.Fw = h->F; a.fp_jlen = h->jlen; }
   launch_substeps(a, h->qc, h->S, h->stream);
   if (h->forced_u) h->forced_cursor += nsub;
   h->substep += (uint64_t)nsub;
@@ -599,6 +570,7 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
   fa.clock = h->clock; fa.clock_dtq = h->p.dtq; fa.clock_advance = 0;
   QTArgs qa = qt_args(h, ratio, 1, 1);
   qa.clock = h->clock; qa.t0 = 0.0; qa.substep0 = 0;
+  if (forces_are_partial(fa)) { qa.fpart = h->Fpart; qa.Fw = h->F; qa.fp_jlen = h->jlen; }
   const bool stamp = h->timing == 2;
   if (stamp) {
     const size_t need = (size_t)nsteps * 2;
@@ -621,7 +593,7 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
       fk.clock_advance = k ? ratio : 0;  // the clock is set for step 0 before the replay; step k-1's substeps are added here
       QTArgs qk = qa;
       if (stamp) { fk.stamp = h->stamps + (size_t)4 * k; qk.stamp = h->stamps + (size_t)4 * k + 2; }
-      launch_forces(fk, h->stream);
+      launch_forces(fk, h->stream, false);  // the substep kernel adds the item kernel's partial sums while it loads its ion
       launch_substeps(qk, h->qc, h->S, h->stream);
     }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -660,17 +632,23 @@ int mdqt_md_steps(mdqt_handle* h, int nsteps) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   if (h->S != MDQT_SCHEME_SR12) return fail(MDQT_ESTATE, "mdqt_md_steps needs the 12-level scheme");
   if (h->p.substeps_per_md < 1) return fail(MDQT_EINVAL, "substeps_per_md < 1");
-  if (nsteps > 1) NEED_ALL_ROWS(h, "mdqt_md_steps(n > 1)");
   CU(cudaSetDevice(h->p.device));
+  if (h->comm) {  // row-decomposed run with a communicator: the position all-gather is part of every MD step
+    if (h->forced_u) return fail(MDQT_ESTATE, "forced uniforms on a communicating handle");
+    int rc = mdqt_comm_md_steps(h, nsteps);
+    if (rc) return rc;
+    return MDQT_OK;
+  }
+  if (nsteps > 1) NEED_ALL_ROWS(h, "mdqt_md_steps(n > 1)");
   if (nsteps >= 2 && h->timing != 1 && !h->forced_u && graphs_enabled()) return md_steps_graph(h, nsteps);
   const bool timing = h->timing == 1;
   if (timing) h->ev_used = 0;
   for (int k = 0; k < nsteps; k++) {
     refresh_fixed(h);
     if (timing) CU(cudaEventRecord(next_event(h), h->stream));
-    launch_forces(force_args(h), h->stream);
+    launch_forces(force_args(h), h->stream, false);
     if (timing) { CU(cudaEventRecord(next_event(h), h->stream)); CU(cudaEventRecord(next_event(h), h->stream)); }
-    int rc = enqueue_substeps(h, h->p.substeps_per_md, 1, 1);
+    int rc = enqueue_substeps(h, h->p.substeps_per_md, 1, 1, /*forces_partial=*/true);
     if (rc) return rc;
     if (timing) CU(cudaEventRecord(next_event(h), h->stream));
   }
@@ -711,6 +689,23 @@ int mdqt_epot(mdqt_handle* h, double* epot) {
 
 int mdqt_diagnostics(mdqt_handle* h, mdqt_diag* out) {
   if (!h || !out) return fail(MDQT_EINVAL, "null argument");
+  if (h->comm) {  // partial sums over the own rows, completed by two small all-reduces: the whole-system values on every rank
+    CU(cudaSetDevice(h->p.device));
+    double s[5] = {0, 0, 0, 0, 0};
+    launch_diag_partial(h->V, h->row0, h->nrows, h->ld, 1, nullptr, h->scalars, h->stream);
+    CU(cudaMemcpyAsync(s, h->scalars, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int rc = mdqt_comm_allreduce(h, s, 1);
+    if (rc) return rc;
+    const double mean = s[0] / (double)h->N;
+    rc = mdqt_diag_partial(h, &mean, s);
+    if (rc) return rc;
+    rc = mdqt_comm_allreduce(h, s, 5);
+    if (rc) return rc;
+    out[0].t = h->t; out[0].vx_avg = mean; out[0].ekin_x = s[1] / (double)h->N; out[0].ekin_y = s[2] / (double)h->N;
+    out[0].ekin_z = s[3] / (double)h->N; out[0].epot = s[4];
+    return MDQT_OK;
+  }
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_diag_partial and all-reduce the sums");
   CU(cudaSetDevice(h->p.device));
   refresh_fixed(h);
@@ -766,6 +761,19 @@ int mdqt_vel_dist_partial(mdqt_handle* h, const double* vx_mean, double* pvel) {
 
 int mdqt_vel_dist(mdqt_handle* h, double* pvel) {
   if (!h || !pvel) return fail(MDQT_EINVAL, "null argument");
+  if (h->comm) {  // <v_x> over all ranks, the KDE of the own rows about it, then the sum of the bins over the ranks
+    CU(cudaSetDevice(h->p.device));
+    double s0 = 0;
+    launch_diag_partial(h->V, h->row0, h->nrows, h->ld, 1, nullptr, h->scalars, h->stream);
+    CU(cudaMemcpyAsync(&s0, h->scalars, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int rc = mdqt_comm_allreduce(h, &s0, 1);
+    if (rc) return rc;
+    const double mean = s0 / (double)h->N;
+    rc = mdqt_vel_dist_partial(h, &mean, pvel);
+    if (rc) return rc;
+    return mdqt_comm_allreduce(h, pvel, 3 * kVelBins);
+  }
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "row-decomposed handle: use mdqt_vel_dist_partial and all-reduce the bins");
   CU(cudaSetDevice(h->p.device));
   launch_diag(h->V, h->N, h->ld, h->B, h->nb, h->scalars, h->stream);
@@ -783,6 +791,19 @@ int mdqt_populations(mdqt_handle* h, double* pops) {
   CU(cudaSetDevice(h->p.device));
   launch_populations(h->psi, h->S, h->N, h->ld, h->B, h->pops, h->stream);
   CU(cudaMemcpyAsync(pops, h->pops, (size_t)h->B * h->N * 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_populations_rows(mdqt_handle* h, double* pops) {
+  if (!h || !pops) return fail(MDQT_EINVAL, "null argument");
+  if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
+  NEED_UNIFORM_N(h);
+  CU(cudaSetDevice(h->p.device));
+  launch_populations(h->psi, h->S, h->N, h->ld, h->B, h->pops, h->stream);  // rows outside the block hold stale amplitudes: not copied
+  CU(cudaMemcpy2DAsync(pops, (size_t)h->nrows * 24, h->pops + (size_t)h->row0 * 3, (size_t)h->N * 24, (size_t)h->nrows * 24, h->B,
+                       cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   return MDQT_OK;
@@ -1134,7 +1155,7 @@ int mdqt_time_forces(mdqt_handle* h, int reps, double* ms_per_launch) {
   cudaGraph_t graph;
   cudaGraphExec_t exec = nullptr;
   CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  for (int k = 0; k < reps; k++) launch_forces(force_args(h), h->stream);
+  for (int k = 0; k < reps; k++) launch_forces(force_args(h), h->stream, false);  // the force kernel alone
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
   e = cudaGraphInstantiate(&exec, graph, 0);

@@ -48,7 +48,10 @@ static_assert(kExpTable == 128 || kExpTable == 1024, "exp table must have 128 or
 __device__ double c_exp2tab[kExpTable];  // global (L2-resident), not __constant__: the CTA prologue reads it with a per-thread index
 
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER on B200 at N=3500 (114 vs 74 us per MD step)
+  // Programmatic dependent launch between the force and substep kernels (MDQT_PDL=0 turns it off). With the round-1 CTA-tile
+  // force kernel it was SLOWER (waiting grids crowded the SMs); with the persistent item kernel, whose CTAs leave an SM only
+  // when its work is done, the dependent's launch latency and prologue hide behind the tail: 54.4 -> 53.5 us per MD step.
+  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
 
@@ -217,7 +220,9 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
   if (threadIdx.x == 0) stamp_time(a.stamp, 0);
   const int tid = threadIdx.x;
   const int ti = tid % kForceThreads, jh = tid / kForceThreads;
-  const int b = blockIdx.z, js = blockIdx.y, tile = blockIdx.x;
+  const int b = blockIdx.z, tile = blockIdx.x;
+  int js = blockIdx.y + a.js0;  // the j chunk this CTA sums (launches over a subset of the chunks: see ForceArgs)
+  if (a.js_skipn && js >= a.js_skip0) js += a.js_skipn;
   const PairConsts c = make_consts(a, EPOT);
   const long long* __restrict__ X = a.Rfix + (size_t)b * 3 * a.ld;
   const long long* __restrict__ Y = X + a.ld;
@@ -419,55 +424,76 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 // ------------------------------------------------------------------------------------------------------------
 // K1, item-walking form (small and medium systems, any number of batched trajectories).
 //
-// A few thousand ions are only ~24 us of issue work for the whole chip, and a grid of CTA tiles loses a third of that to
-// wave quantisation (1.49 waves at N = 3500), CTA prologues and the last CTA's partial-sum reduction. Here the grid is
-// PERSISTENT -- two 8-warp CTAs per SM -- and the unit of work is an ITEM = (trajectory b, group g of 32 rows, chunk c
-// of jlen positions), handled by ONE warp: lane <-> row, the chunk staged by the warp itself into its private shared-
-// memory buffer (cp.async, double buffered: the next item's tile and rows are in flight while this one computes), no
-// CTA-wide barrier after the prologue. Items are dealt round-robin to the grid's warps; jlen is chosen so that the item
-// count fills all warps evenly when one trajectory runs alone (N = 3500: 110 groups x 21 chunks of 168 = 2310 items on
-// 2368 warps, one each), and a batch simply walks B times as many items.
-// Every item writes one partial sum; the last warp to arrive for a (trajectory, group) adds the partials in ascending
-// chunk order. The summation order of a row is therefore a function of jlen alone -- i.e. of mdqt_params.plan_n, not of
-// the batch size, of the trajectory's position in the batch, or of the number of row-owning ranks: a job gives the same
-// bits alone or batched. Trajectories of an ensemble may hold different ion counts nb[b] (SU:299-337).
+// A few thousand ions are only ~24 us of issue work for the whole chip, and a grid of CTA tiles loses a fifth of that to
+// wave quantisation (1.49 waves at N = 3500), CTA prologues and the cross-CTA reduction of partial sums (fence, arrival
+// counter and dependent L2 round trips while the chip idles). Here the grid is PERSISTENT -- two 8-warp CTAs per SM -- and
+// the unit of work is an ITEM = (trajectory b, group g of 32 x IPT rows, chunk c of jlen positions), handled by ONE warp:
+// lane <-> row(s), the chunk staged by the warp itself into its private shared-memory buffer (cp.async, double buffered:
+// the next item's tile and rows are in flight while this one computes), no CTA-wide barrier after the prologue. Items are
+// dealt round-robin to the grid's warps; jlen is chosen so that the item count fills all warps evenly when one trajectory
+// runs alone (N = 3500: 110 groups x 21 chunks of 168 = 2310 items on 2368 warps, one each); a batch walks B times as many
+// items, two rows per lane (fewer shared-memory reads and index instructions per pair).
+// Every item writes ONE partial sum and the kernel ends there: no fence, no counter, no reduction. The consumer adds the
+// partials of a row in ascending chunk order -- the substep kernel while it loads its ion (mdqt_qt.cu), k_sum_partials for
+// everybody else. The summation order of a row is therefore a function of jlen alone -- i.e. of mdqt_params.plan_n, not of
+// the batch size, of the rows per lane, of the trajectory's position in the batch, or of the number of row-owning ranks:
+// a job gives the same bits alone or batched. Trajectories of an ensemble may hold different ion counts nb[b] (SU:299-337).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kItemWarps = 8;
 constexpr int kItemCtasPerSM = 2;
-constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps + the exp table = 116 KB per CTA
+constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps = 120 KB per CTA at most
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 struct Item { int b, g, ch, Nb; };
 
-template <bool EPOT, bool HL>
+#ifdef MDQT_K1_TRACE  // developer build: per-WARP phase time stamps of the item kernel (scripts/k1_items_trace.py)
+#define WTRACE(slot)                                                                                             \
+  if (lane == 0) {                                                                                               \
+    const int w_ = blockIdx.x * kItemWarps + warp;                                                               \
+    if (w_ < 8192) {                                                                                             \
+      long long gt_;                                                                                             \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                    \
+      g_trace[w_ * 8 + slot] = gt_;                                                                              \
+      if (slot == 0) { unsigned sm_; asm("mov.u32 %0, %%smid;" : "=r"(sm_)); g_trace[w_ * 8 + 7] = sm_; }        \
+    }                                                                                                            \
+  }
+#else
+#define WTRACE(slot)
+#endif
+
+template <int IPT, bool EPOT, bool HL>
 __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double stab[kExpTable];  // static: the table index folds into the LDS immediate offset
+  __shared__ double stab[kExpTable];
+  constexpr int RPG = 32 * IPT;  // rows per group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tj = a.jlen;  // tile capacity (a multiple of 8, <= kItemMaxJ)
-  // per warp and buffer: xy[tj] (16 B), z[tj] (8 B), then the item's 32 rows x, y, z (3 x 32 x 8 B)
-  const unsigned bufbytes = 24u * (unsigned)tj + 768u;
+  // per warp and buffer: xy[tj] (16 B), z[tj] (8 B), then the item's rows x, y, z (3 x RPG x 8 B)
+  const unsigned bufbytes = 24u * (unsigned)tj + 24u * RPG;
   unsigned char* wbase = smem_raw + (size_t)warp * (2 * (size_t)bufbytes);
   const PairConsts c = make_consts(a, EPOT);
   if (tid == 0) stamp_time(a.stamp, 0);
+  WTRACE(0)
   for (int k = tid; k < kExpTable; k += kItemWarps * 32) cp_async8(&stab[k], &c_exp2tab[k]);
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
   if (!EPOT && tid == 0 && blockIdx.x == 0) advance_clock(a);
 
+  const int gcap = (a.nrows + RPG - 1) / RPG;
   const int W = gridDim.x * kItemWarps;
-  const int total = a.B * a.gcap * a.nsplit;
+  const int total = a.B * gcap * a.nsplit;
   const int rowend_cap = a.row0 + a.nrows;
+  const unsigned long long mg_g = (IPT == 2) ? a.mg_gcap2 : a.mg_gcap;
   // item k -> (b, g, ch) by multiplication with host-made reciprocals (k < 2^24, divisors < 2^16: exact)
   auto decode = [&](int k, Item& it) {
     const unsigned t = (unsigned)(((unsigned long long)(unsigned)k * a.mg_chunk) >> 40);
     it.ch = k - (int)t * a.nsplit;
-    it.b = (int)(((unsigned long long)t * a.mg_gcap) >> 40);
-    it.g = (int)t - it.b * a.gcap;
+    it.b = (int)(((unsigned long long)t * mg_g) >> 40);
+    it.g = (int)t - it.b * gcap;
     it.Nb = a.nb ? a.nb[it.b] : a.N;
     // empty when the group or the chunk lies beyond the trajectory's ions
-    return (a.row0 + it.g * 32 < min(rowend_cap, it.Nb)) && (it.ch * a.jlen < it.Nb);
+    return (a.row0 + it.g * RPG < min(rowend_cap, it.Nb)) && (it.ch * a.jlen < it.Nb);
   };
   auto next_valid = [&](int k, Item& it) {
     while (k < total && !decode(k, it)) {
@@ -488,8 +514,11 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
     for (int q = lane; q < cnt; q += 32) {
       cp_async8(&sxy[q].x, X + jbeg + q); cp_async8(&sxy[q].y, Y + jbeg + q); cp_async8(&sz[q], Z + jbeg + q);
     }
-    const int ir = min(a.row0 + it.g * 32 + lane, min(rowend_cap, it.Nb) - 1);  // idle lanes shadow the last row (never stored)
-    cp_async8(&srow[lane], X + ir); cp_async8(&srow[32 + lane], Y + ir); cp_async8(&srow[64 + lane], Z + ir);
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      const int ir = min(a.row0 + it.g * RPG + r * 32 + lane, min(rowend_cap, it.Nb) - 1);  // idle lanes shadow the last row (never stored)
+      cp_async8(&srow[r * 32 + lane], X + ir); cp_async8(&srow[RPG + r * 32 + lane], Y + ir); cp_async8(&srow[2 * RPG + r * 32 + lane], Z + ir);
+    }
   };
 
   Item cur, nxt;
@@ -498,6 +527,7 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();  // the exp table is complete for every warp; the only CTA-wide barrier of the kernel
+  WTRACE(1)
   int buf = 0;
   while (k < total) {
     const int kn = next_valid(k + W, nxt);
@@ -510,78 +540,59 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
     const longlong2* __restrict__ sxy = reinterpret_cast<const longlong2*>(base);
     const long long* __restrict__ sz = reinterpret_cast<const long long*>(base + 16u * (unsigned)tj);
     const long long* __restrict__ srow = reinterpret_cast<const long long*>(base + 24u * (unsigned)tj);
-    const long long xi = srow[lane], yi = srow[32 + lane], zi = srow[64 + lane];
+    long long xi[IPT], yi[IPT], zi[IPT];
+    double ax[IPT], ay[IPT], az[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) {
+      xi[r] = srow[r * 32 + lane]; yi[r] = srow[RPG + r * 32 + lane]; zi[r] = srow[2 * RPG + r * 32 + lane];
+      ax[r] = ay[r] = az[r] = 0.0;
+    }
     const int cnt = min(a.jlen, cur.Nb - cur.ch * a.jlen);
-    double ax = 0.0, ay = 0.0, az = 0.0;
-#pragma unroll 8
+    WTRACE(2)
+#pragma unroll(IPT == 2 ? 4 : 8)
     for (int jj = 0; jj < cnt; jj++) {
       const longlong2 pxy = sxy[jj];
       const long long pz = sz[jj];
-      const double dx = __ll2double_rn((long long)((unsigned long long)xi - (unsigned long long)pxy.x));
-      const double dy = __ll2double_rn((long long)((unsigned long long)yi - (unsigned long long)pxy.y));
-      const double dz = __ll2double_rn((long long)((unsigned long long)zi - (unsigned long long)pz));
-      const double r2 = EPOT ? fma(dx, dx, fma(dy, dy, dz * dz)) : fma(dx, dx, fma(dy, dy, fma(dz, dz, 1.0)));  // see k_pairs
-      double rinv, ef;
-      bool valid;
-      pair_core<HL>(r2, c, stab, rinv, ef, valid);
-      if (EPOT) {
-        const double u = ef * rinv;
-        ax += valid ? u : 0.0;
-      } else {
-        double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);
-        if (HL)
-          asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
-              : "+d"(f) : "r"(__double2hiint(r2)));
-        else
-          asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
-              : "+d"(f) : "d"(r2), "d"(c.rc2_u));
-        ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
+#pragma unroll
+      for (int r = 0; r < IPT; r++) {
+        const double dx = __ll2double_rn((long long)((unsigned long long)xi[r] - (unsigned long long)pxy.x));
+        const double dy = __ll2double_rn((long long)((unsigned long long)yi[r] - (unsigned long long)pxy.y));
+        const double dz = __ll2double_rn((long long)((unsigned long long)zi[r] - (unsigned long long)pz));
+        const double r2 = EPOT ? fma(dx, dx, fma(dy, dy, dz * dz)) : fma(dx, dx, fma(dy, dy, fma(dz, dz, 1.0)));  // see k_pairs
+        double rinv, ef;
+        bool valid;
+        pair_core<HL>(r2, c, stab, rinv, ef, valid);
+        if (EPOT) {
+          const double u = ef * rinv;
+          ax[r] += valid ? u : 0.0;
+        } else {
+          double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);
+          if (HL)
+            asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+                : "+d"(f) : "r"(__double2hiint(r2)));
+          else
+            asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
+                : "+d"(f) : "d"(r2), "d"(c.rc2_u));
+          ax[r] = fma(f, dx, ax[r]); ay[r] = fma(f, dy, ay[r]); az[r] = fma(f, dz, az[r]);
+        }
       }
     }
-    ax *= c.out_scale; ay *= c.out_scale; az *= c.out_scale;
-    const int row = a.row0 + cur.g * 32 + lane;
-    const bool live = row < min(rowend_cap, cur.Nb);
+    WTRACE(3)
     if (EPOT) {
-      double sum = live ? ax : 0.0;
+      static_assert(!EPOT || IPT == 1, "the potential-energy instantiation keeps one row per lane");
+      const int row = a.row0 + cur.g * RPG + lane;
+      double sum = (row < min(rowend_cap, cur.Nb)) ? ax[0] * c.out_scale : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
       if (lane == 0) item_partials[k] = sum;
     } else {
-      const int nch_b = (cur.Nb + a.jlen - 1) / a.jlen;  // chunks this trajectory really has
-      double* Fb = a.F + (size_t)cur.b * 3 * a.ld;
-      if (nch_b == 1) {
-        if (live) { Fb[row] = ax; Fb[a.ld + row] = ay; Fb[2 * a.ld + row] = az; }
-      } else {
-        const size_t stride = (size_t)a.B * 3 * a.ld;
-        if (live) {
-          double* Fp = a.Fpart + (size_t)cur.ch * stride + (size_t)cur.b * 3 * a.ld;
-          __stcg(&Fp[row], ax); __stcg(&Fp[a.ld + row], ay); __stcg(&Fp[2 * a.ld + row], az);
-        }
-        __threadfence();
-        __syncwarp();
-        unsigned old = 0;
-        unsigned* ctr = a.counters + (size_t)cur.b * a.gcap + cur.g;
-        if (lane == 0) old = atomicAdd(ctr, 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old == (unsigned)nch_b - 1) {  // the last warp of this (trajectory, group): add the chunks in ascending order
-          if (lane == 0) *ctr = 0;         // self-reset for the next call
-          __threadfence();
-          if (live) {
-            const double* src = a.Fpart + (size_t)cur.b * 3 * a.ld + row;
-            double sx = 0.0, sy = 0.0, szz = 0.0;
-            for (int s0 = 0; s0 < nch_b; s0 += 12) {  // 36 independent loads per batch: one L2 round trip
-              double vx[12], vy[12], vz[12];
+      // one partial per item -- or the force itself when the whole j range is a single chunk
+      double* dst = (a.nsplit == 1 ? a.F : a.Fpart + (size_t)cur.ch * ((size_t)a.B * 3 * a.ld)) + (size_t)cur.b * 3 * a.ld;
 #pragma unroll
-              for (int q = 0; q < 12; q++) {
-                const bool in = s0 + q < nch_b;
-                const double* pq = src + (size_t)(in ? s0 + q : 0) * stride;
-                vx[q] = in ? __ldcg(pq) : 0.0; vy[q] = in ? __ldcg(pq + a.ld) : 0.0; vz[q] = in ? __ldcg(pq + 2 * a.ld) : 0.0;
-              }
-#pragma unroll
-              for (int q = 0; q < 12; q++) { sx += vx[q]; sy += vy[q]; szz += vz[q]; }  // + 0.0 for absent chunks: exact
-            }
-            Fb[row] = sx; Fb[a.ld + row] = sy; Fb[2 * a.ld + row] = szz;
-          }
+      for (int r = 0; r < IPT; r++) {
+        const int row = a.row0 + cur.g * RPG + r * 32 + lane;
+        if (row < min(rowend_cap, cur.Nb)) {
+          dst[row] = ax[r] * c.out_scale; dst[a.ld + row] = ay[r] * c.out_scale; dst[2 * a.ld + row] = az[r] * c.out_scale;
         }
       }
     }
@@ -589,19 +600,34 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
   }
   pdl_launch_dependents();
   if (lane == 0) stamp_time(a.stamp, 1);
+  WTRACE(4)
+}
+
+// rows per lane of the item kernel: two once every warp has several items anyway (batches), one when a single trajectory
+// must be spread over all warps. Any rule is fine -- the summation order, hence the bits, do not depend on it.
+static int items_ipt(const ForceArgs& a) {
+  static const int force = [] { const char* e = getenv("MDQT_ITEMS_IPT"); return e ? atoi(e) : 0; }();
+  if (force == 1 || force == 2) return force;
+  const long long items1 = (long long)a.B * ((a.nrows + 31) / 32) * a.nsplit;
+  return items1 >= 4LL * 148 * kItemCtasPerSM * kItemWarps ? 2 : 1;
 }
 
 template <bool EPOT>
 static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
-  const size_t smem = (size_t)kItemWarps * 2 * (24 * (size_t)a.jlen + 768);
-  const long long total = (long long)a.B * a.gcap * a.nsplit;
+  const int ipt = EPOT ? 1 : items_ipt(a);  // the potential energy is a diagnostic: one instantiation
+  const size_t smem = (size_t)kItemWarps * 2 * (24 * (size_t)a.jlen + 24 * 32 * ipt);
+  const long long total = (long long)a.B * ((a.nrows + 32 * ipt - 1) / (32 * ipt)) * a.nsplit;
   const int grid = (int)std::min<long long>(148LL * kItemCtasPerSM, (total + kItemWarps - 1) / kItemWarps);
   const bool hl = a.half_l && MDQT_VALID_INT;
-  auto kern = hl ? k_pairs_items<EPOT, true> : k_pairs_items<EPOT, false>;
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
-  if (!attr_done[EPOT][hl]) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kItemWarps * 2 * (24 * (size_t)kItemMaxJ + 768)));
-    attr_done[EPOT][hl] = true;
+  void (*kern)(ForceArgs, double*);
+  if (EPOT) kern = hl ? k_pairs_items<1, EPOT, true> : k_pairs_items<1, EPOT, false>;
+  else if (ipt == 2) kern = hl ? k_pairs_items<2, false, true> : k_pairs_items<2, false, false>;
+  else kern = hl ? k_pairs_items<1, false, true> : k_pairs_items<1, false, false>;
+  static bool attr_done[2][3][2];
+  if (!attr_done[EPOT][ipt][hl]) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kItemWarps * 2 * (24 * (size_t)kItemMaxJ + 24 * 64)));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // room for two CTAs per SM
+    attr_done[EPOT][ipt][hl] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kItemWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
@@ -612,6 +638,21 @@ static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
   cudaLaunchKernelEx(&cfg, kern, a, partials);
 }
 
+// F[b][comp][row] = sum of the row's partials in ascending chunk order: the one formula every consumer of item-kernel
+// partials uses (here, and the substep kernel while it loads its ion), so that F has the same bits whoever adds it up
+__global__ void k_sum_partials(ForceArgs a) {
+  const long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gidx >= (long long)a.B * 3 * a.nrows) return;
+  const int i = a.row0 + (int)(gidx % a.nrows);
+  const int bc = (int)(gidx / a.nrows), b = bc / 3;
+  const int Nb = a.nb ? a.nb[b] : a.N;
+  if (i >= Nb) return;
+  const int nch = (Nb + a.jlen - 1) / a.jlen;
+  const size_t stride = (size_t)a.B * 3 * a.ld;
+  const double* src = a.Fpart + (size_t)bc * a.ld + i;
+  a.F[(size_t)bc * a.ld + i] = sum_partials(src, stride, nch);
+}
+
 template <bool EPOT, bool HL>
 static void launch_pairs_hl(const ForceArgs& a, double* partials, cudaStream_t s, dim3 grid, int ipt, int jsub, bool pdl) {
   // few resident warps (small N): also unroll the j loop further so that one warp carries more independent pairs
@@ -620,7 +661,7 @@ static void launch_pairs_hl(const ForceArgs& a, double* partials, cudaStream_t s
     // at once (two 256-thread or four 128-thread CTAs per SM at ~124 registers); beyond that the placement constraint costs
     // more balance than the reduction saves (N = 3500: 41.5 us against 32.8 us), so larger grids keep the global-memory path
     const long long ctas = (long long)grid.x * grid.y * grid.z;
-    const bool cl = !EPOT && a.nsplit >= 2 && a.nsplit <= 8 && ctas <= 148LL * (jsub == 8 ? 2 : 4) && cluster_enabled();
+    const bool cl = !EPOT && a.js_count == 0 && a.nsplit >= 2 && a.nsplit <= 8 && ctas <= 148LL * (jsub == 8 ? 2 : 4) && cluster_enabled();
     if (cl) {
       if (jsub == 8) launch_kernel(k_pairs<1, 8, false, 8, HL, 32, true>, grid, dim3(256), s, pdl, a, partials, a.nsplit);
       else launch_kernel(k_pairs<1, 4, false, 8, HL, 32, true>, grid, dim3(128), s, pdl, a, partials, a.nsplit);
@@ -644,13 +685,20 @@ static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
   const int rg = a.rg == 32 ? 32 : kForceThreads;
   const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
   const int jsub = (rg == 32) ? (a.jsub == 8 ? 8 : 4) : ((a.jsub == 2 || a.jsub == 4) ? a.jsub : 1);
-  dim3 grid((a.nrows + rg * ipt - 1) / (rg * ipt), a.nsplit, a.B);
+  dim3 grid((a.nrows + rg * ipt - 1) / (rg * ipt), a.js_count > 0 ? a.js_count : a.nsplit, a.B);
   const bool pdl = !EPOT && pdl_enabled();
   if (a.half_l && MDQT_VALID_INT) launch_pairs_hl<EPOT, true>(a, partials, s, grid, ipt, jsub, pdl);
   else launch_pairs_hl<EPOT, false>(a, partials, s, grid, ipt, jsub, pdl);
 }
 
-void launch_forces(const ForceArgs& a, cudaStream_t s) { launch_pairs<false>(a, nullptr, s); }
+// finalize: F must hold the complete forces on return (false: the caller's next kernel adds the item kernel's partials itself)
+void launch_forces(const ForceArgs& a, cudaStream_t s, bool finalize) {
+  launch_pairs<false>(a, nullptr, s);
+  if (finalize && forces_are_partial(a)) {
+    const long long n = (long long)a.B * 3 * a.nrows;
+    k_sum_partials<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a);
+  }
+}
 
 #ifdef MDQT_K1_TRACE
 extern "C" int mdqt_debug_read_trace(long long* out, int n) {
@@ -686,11 +734,35 @@ __global__ void k_epot_final(const double* __restrict__ partials, int per_traj, 
   if (threadIdx.x == 0) out[blockIdx.x] = sred[0] * (half / (double)(nb ? nb[blockIdx.x] : N));
 }
 
+// item kernel: partials[(b * gcap + g) * nchunk + c]. Thread t adds the groups t, t + 256, ... (each group: its chunks in
+// ascending order), then the fixed tree: groups and chunks beyond a trajectory's ions hold 0 and are added last in every
+// thread's sequence, so the result does not depend on the handle's capacity -- a job's energy has the same bits in any batch
+__global__ void k_epot_final_items(const double* __restrict__ partials, int gcap, int nchunk, double half, int N,
+                                   const int* __restrict__ nb, double* __restrict__ out) {
+  __shared__ double sred[256];
+  const double* p = partials + (size_t)blockIdx.x * gcap * nchunk;
+  double s = 0.0;
+  for (int g = threadIdx.x; g < gcap; g += 256) {
+    double sg = 0.0;
+    for (int c = 0; c < nchunk; c++) sg += p[(size_t)g * nchunk + c];
+    s += sg;
+  }
+  sred[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sred[threadIdx.x] += sred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sred[0] * (half / (double)(nb ? nb[blockIdx.x] : N));
+}
+
 void launch_epot(const ForceArgs& a, double* partials, double* result, cudaStream_t s) {
   launch_pairs<true>(a, partials, s);
   int per_traj;
-  if (a.items) per_traj = a.gcap * a.nsplit;
-  else {
+  if (a.items) {
+    k_epot_final_items<<<a.B, 256, 0, s>>>(partials, (a.nrows + 31) / 32, a.nsplit, 0.5, a.N, a.nb, result);
+    return;
+  } else {
     const int rg = a.rg == 32 ? 32 : kForceThreads;
     const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
     per_traj = (a.nrows + rg * ipt - 1) / (rg * ipt) * a.nsplit;

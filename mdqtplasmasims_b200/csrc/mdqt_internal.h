@@ -21,6 +21,10 @@ struct ForceArgs {
   int N, ld, B;
   int row0, nrows;   // rows owned by this handle
   int nsplit, jlen;  // j-range decomposition (depends on N and B only -> rank-count independent sums)
+  // CTA-tile kernel launched over a SUBSET of the j chunks (row-decomposed runs overlap the position all-gather with the
+  // chunks that need local positions only): chunk = blockIdx.y + js0, and chunks >= js_skip0 are shifted by js_skipn.
+  // The partial-sum / arrival-counter protocol still counts all nsplit chunks, across the launches.
+  int js0, js_skip0, js_skipn, js_count;  // js_count = chunks in this launch (0: all nsplit)
   int ipt;           // ion rows per thread (1 or 2)
   int jsub;          // intra-CTA split of each j tile over thread groups (1, 2, 4; 4 or 8 with 32-row groups)
   int rg;            // ion rows per thread group: 128 (default) or 32 (small systems)
@@ -34,7 +38,7 @@ struct ForceArgs {
   // item-walking kernel (small and medium systems, any batch size): every warp of a persistent grid walks a static list of
   // (trajectory, 32-row group, j chunk) items. items = 1 selects it; gcap = row groups per trajectory (at capacity)
   int items, gcap;
-  unsigned long long mg_chunk, mg_gcap;  // ceil(2^40 / nsplit), ceil(2^40 / gcap): item index -> (b, g, chunk) without division
+  unsigned long long mg_chunk, mg_gcap, mg_gcap2;  // ceil(2^40 / nsplit), ceil(2^40 / groups of 32 rows), ... of 64 rows: item index -> (b, g, chunk) without division
   const int* nb;     // [B] ions per trajectory (ensembles whose jobs drew different N, SU:299-337) or null: all N
   unsigned long long* stamp;  // {min start, max end} of this launch in %globaltimer ns (in-graph kernel timing) or null
 };
@@ -56,6 +60,8 @@ struct QTArgs {
   int lanes;                              // lanes per ion of the 12-level kernel: 0 = by (N, B), 2 or 4 = pinned
   double t0; uint64_t substep0; uint64_t seed;
   const int* nb;                          // [B] ions per trajectory or null (all N)
+  const double* fpart; double* Fw;        // item-kernel partials [chunk][B][3][ld] to add up (then written to Fw), or null: F is complete
+  int fp_jlen;                            // chunk length of those partials
   const uint64_t* seeds;                  // [B] Philox key per trajectory or null (all `seed`)
   unsigned long long* stamp;              // {min start, max end} of this launch in %globaltimer ns, or null
   const double* clock;                    // {t, substep index (as uint64 bits)} in device memory: overrides t0/substep0 when non-null
@@ -109,7 +115,23 @@ __device__ __forceinline__ void stamp_time(unsigned long long* stamp, int end) {
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-void launch_forces(const ForceArgs& a, cudaStream_t s);
+void launch_forces(const ForceArgs& a, cudaStream_t s, bool finalize = true);
+// the item kernel with more than one chunk leaves one partial sum per chunk in Fpart[chunk][B][3][ld] instead of F
+inline bool forces_are_partial(const ForceArgs& a) { return a.items && a.nsplit > 1; }
+#ifdef __CUDACC__
+// sum of `nch` partials src[0], src[stride], ... in ascending order, fetched as batches of 12 independent L2 loads
+__device__ __forceinline__ double sum_partials(const double* __restrict__ src, size_t stride, int nch) {
+  double sum = 0.0;
+  for (int s0 = 0; s0 < nch; s0 += 12) {
+    double v[12];
+#pragma unroll
+    for (int q = 0; q < 12; q++) v[q] = (s0 + q < nch) ? __ldcg(src + (size_t)(s0 + q) * stride) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; q++) sum += v[q];  // + 0.0 for absent chunks: exact
+  }
+  return sum;
+}
+#endif
 // Rfix[k] = to_fixed(R[k]) for all B*3*ld entries (after an upload or an external write into R)
 void launch_to_fixed(const double* R, long long* Rfix, size_t n, double invL, double invL_lo, cudaStream_t s);
 void launch_epot(const ForceArgs& a, double* block_partials, double* result, cudaStream_t s);  // result[B]

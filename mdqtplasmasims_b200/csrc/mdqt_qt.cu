@@ -152,6 +152,43 @@ __device__ __forceinline__ void sincos_fast(double phi, double& sn, double& cs) 
   cs = ((q + 1) & 2) ? -b : b;
 }
 
+
+// Forces of ion i, components 0 and c2: either F itself, or -- when the item force kernel left one partial sum per j chunk --
+// the partials added in ascending chunk order (the same formula as k_sum_partials), written back to F by the storing lanes.
+// Kept out of line: inlined into the substep kernels it perturbed ptxas' schedule of their latency-bound main loop
+// (25 substeps: 23 -> 35 us at N = 3500).
+#ifndef MDQT_K2_FLOAD
+#define MDQT_K2_FLOAD 1
+#endif
+#if MDQT_K2_FLOAD == 1
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+double2 load_forces_impl(const double* __restrict__ fpart, double* __restrict__ Fw, const double* __restrict__ F, int Nb, int jlen, int B,
+                         int ld, int b, int i, int c2, int store_mask) {  // scalars only: a by-reference QTArgs would be copied to the stack
+  double2 f;
+  if (fpart) {
+    const int nch = (Nb + jlen - 1) / jlen;
+    const size_t stride = (size_t)B * 3 * ld;
+    f.x = sum_partials(fpart + (size_t)b * 3 * ld + i, stride, nch);
+    f.y = sum_partials(fpart + ((size_t)b * 3 + c2) * ld + i, stride, nch);
+    double* Fo = Fw + (size_t)b * 3 * ld;
+    if (store_mask & 2) Fo[(size_t)c2 * ld + i] = f.y;
+    if (store_mask & 1) Fo[i] = f.x;
+  } else {
+    const double* __restrict__ Fb = F + (size_t)b * 3 * ld;
+    f.x = Fb[i]; f.y = Fb[(size_t)c2 * ld + i];
+  }
+  return f;
+}
+#define load_forces(a, b, i, c2, store_x, store_2, fx, f2)                                                                       \
+  do {                                                                                                                           \
+    const double2 f_ = load_forces_impl((a).fpart, (a).Fw, (a).F, (a).nb ? (a).nb[b] : (a).N, (a).fp_jlen, (a).B, (a).ld, b, i,  \
+                                        c2, ((store_x) ? 1 : 0) | ((store_2) ? 2 : 0));                                          \
+    fx = f_.x; f2 = f_.y;                                                                                                        \
+  } while (0)
+
 template <int NL>
 __device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g) {
   cplx m[NL];
@@ -224,7 +261,7 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   if (a.do_step) {
     rx = Rb[i]; r2 = Rb[(size_t)c2 * a.ld + i];
     v2 = Vb[(size_t)c2 * a.ld + i];
-    fx = Fb[i]; f2 = Fb[(size_t)c2 * a.ld + i];
+    load_forces(a, b, i, c2, active && lane == 0, active, fx, f2);
   }
   if (do_tpart) tp = a.tPart[(size_t)b * a.ld + i];
   double t = a.clock ? a.clock[0] : a.t0;  // device clock inside a replayed CUDA graph
@@ -434,13 +471,36 @@ struct Lane4H {
   double a01r, a01i, a10r, a10i;    // h * complex couplings row0<-w1, row1<-w0
   double a02, b00, a12, b11, a21, a20;
   double G0, G1;                    // h * Gamma weights of |w0|^2, |w1|^2 in dp
+  double Gr0, Gr1;                  // the partner half's weights (of r0 = its w0, r1 = its w1)
 };
 
-__device__ __forceinline__ void stage4(const Lane4H& H, const cplx* w, cplx* g) {
+// Build-time variants of the four-lane kernel (A/B'd on B200; each gives the same bits as the plain form unless noted):
+//   MDQT_K2_DPLOCAL 1: the block's P population is formed from the partner amplitudes every stage fetches anyway (r0, r1)
+//                      instead of one more shuffle round -- same operands, same order, one dependent shuffle less per stage
+//   MDQT_K2_DPSTAGE 1: the jump test uses stage 1's dp (pair sums first: (a+b)+(c+d) instead of the reference's left-to-right
+//                      order: differs by <= 1 ulp, i.e. only if the uniform ties with dp); the four P populations are
+//                      fetched only inside the (rare) jump branch
+//   MDQT_K2_PIPE    1: the next substep's Doppler shift, rotating phase, sin/cos and coefficients are computed right after
+//                      this substep's optical-force kick is known, overlapping the Runge-Kutta chains; recomputed on a jump
+#ifndef MDQT_K2_DPLOCAL
+#define MDQT_K2_DPLOCAL 1  // measured on B200, N = 3500, 25 substeps in the replayed graph: 23.6 us (0: 28.2; DPSTAGE 24.3; PIPE 24.9; all three 28.6)
+#endif
+#ifndef MDQT_K2_DPSTAGE
+#define MDQT_K2_DPSTAGE 0
+#endif
+#ifndef MDQT_K2_PIPE
+#define MDQT_K2_PIPE 0
+#endif
+
+__device__ __forceinline__ double stage4(const Lane4H& H, const cplx* w, cplx* g) {
   const cplx r0 = {__shfl_xor_sync(0xffffffffu, w[0].re, 1), __shfl_xor_sync(0xffffffffu, w[0].im, 1)};
   const cplx r1 = {__shfl_xor_sync(0xffffffffu, w[1].re, 1), __shfl_xor_sync(0xffffffffu, w[1].im, 1)};
   double own = fma(H.G0, cnorm(w[0]), H.G1 * cnorm(w[1]));
+#if MDQT_K2_DPLOCAL
+  own += fma(H.Gr0, cnorm(r0), H.Gr1 * cnorm(r1));  // == the partner lane's `own`, bit for bit
+#else
   own += __shfl_xor_sync(0xffffffffu, own, 1);
+#endif
   own += __shfl_xor_sync(0xffffffffu, own, 2);
   const double pref = rsqrt_near1(1.0 - own);
   cplx m[3];
@@ -468,6 +528,24 @@ __device__ __forceinline__ void stage4(const Lane4H& H, const cplx* w, cplx* g) 
     g[k].re = fma(pref, m[k].re, -w[k].re);
     g[k].im = fma(pref, m[k].im, -w[k].im);
   }
+  return own;
+}
+
+// Doppler shift, rotating phase and the coefficients that depend on them, for a substep that starts (after step()'s velocity
+// update) with velocity vxs, time-since-jump tps (already advanced) and global time ts (SU:447, 481-483, 506-510)
+struct PrepC { double e0_0, e1_0, e0_1, e1_1, e0_2, e1_2, hrot, pv2qv, two_kr, g2E, ed_num, ed_den, ed_c; bool expand; };
+struct Pre { double hE0, hE1, hE2, cr, ci; };
+__device__ __forceinline__ Pre prep4(const PrepC& c, double vxs, double tps, double ts) {
+  double expDet = 0.0;
+  if (c.expand) expDet = c.ed_num * ts / (c.ed_den * sqrt(1 + c.ed_c * ts * ts));
+  const double uu = vxs * c.pv2qv + expDet;
+  Pre p;
+  p.hE0 = fma(c.e1_0, uu, c.e0_0); p.hE1 = fma(c.e1_1, uu, c.e0_1); p.hE2 = fma(c.e1_2, uu, c.e0_2);
+  const double phi = c.two_kr * uu * tps * c.g2E;
+  double sn, cs;
+  sincos_fast(phi, sn, cs);
+  p.cr = c.hrot * cs; p.ci = c.hrot * sn;
+  return p;
 }
 
 template <bool FORCED>
@@ -507,6 +585,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   const double e0_2 = h * dEDP, e1_2 = half ? h * (1 - a.kRat) : h * (a.kRat - 1);               // D3 | D5
   H.hg0 = half ? 0.5 * h * gam2 : 0.0; H.hg1 = half ? 0.0 : 0.5 * h * gam1;
   H.G0 = half ? h * gam2 : 0.0; H.G1 = half ? 0.0 : h * gam1;
+  H.Gr0 = half ? 0.0 : h * gam2; H.Gr1 = half ? h * gam1 : 0.0;
   H.a02 = half ? hc25 : 0.0; H.b00 = hc20; H.a12 = half ? 0.0 : hc13; H.b11 = hc14;
   H.a21 = half ? 0.0 : hc13; H.a20 = half ? hc25 : 0.0;
   H.a01r = hc10; H.a01i = 0.0; H.a10r = hc10; H.a10i = 0.0;  // half1: set from the rotating phase every substep
@@ -528,11 +607,24 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   // quad lane 0 carries (x, y), lane 1 (x, z); lanes 2, 3 shadow (x, y) without storing
   const int c2 = (q == 1) ? 2 : 1;
   double rx = Rb[i], r2 = Rb[(size_t)c2 * a.ld + i], vx = Vb[i], v2 = Vb[(size_t)c2 * a.ld + i];
-  const double fx = Fb[i], f2 = Fb[(size_t)c2 * a.ld + i];
+  double fx_, f2_;
+  load_forces(a, b, i, c2, active && q == 0, active && q < 2, fx_, f2_);
+  const double fx = fx_, f2 = f2_;
   double tp = a.tPart[(size_t)b * a.ld + i];
   double t = a.clock ? a.clock[0] : a.t0;  // device clock inside a replayed CUDA graph
   const uint64_t substep0 = a.clock ? *reinterpret_cast<const unsigned long long*>(a.clock + 1) : a.substep0;
   const double DT = 0.5 * a.dtq;
+
+  // Doppler shift, rotating phase and the coefficients that depend on them, for a substep that starts (after step()'s velocity
+  // update) with velocity vxs, time-since-jump tps (already advanced) and global time ts (SU:447, 481-483, 506-510)
+  const PrepC pc = {e0_0, e1_0, e0_1, e1_1, e0_2, e1_2, hrot, a.pv2qv, 2. * (1 + a.kRat), a.g2E,
+                    0.0126 * a.fracOfSig * a.Te, sqrt(a.density) * a.sig0, 0.00014314 * a.Te / (a.density * a.sig0 * a.sig0), a.fracOfSig != 0.0};
+#define prep(vxs, tps, ts) prep4(pc, (vxs), (tps), (ts))
+#if MDQT_K2_PIPE
+  // the first substep's coefficients: what step() will make of vx, and tp + dtq
+  Pre cur = prep(__dadd_rn(vx, __dmul_rn(a.dtq, fx)), __dadd_rn(tp, a.dtq), t);
+#endif
+  const unsigned quadmask = 0xFu << base;
 
   for (int s = 0; s < a.nsub; s++) {
     {  // step() (SU:356-430)
@@ -556,12 +648,10 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
         }
       }
     }
-    double expDet = 0.0;
-    if (a.fracOfSig != 0.0)
-      expDet = 0.0126 * a.fracOfSig * a.Te * t /
-               (sqrt(a.density) * a.sig0 * sqrt(1 + 0.00014314 * t * t * a.Te / (a.density * a.sig0 * a.sig0)));
-    const double vq = vx * a.pv2qv;
     tp = __dadd_rn(tp, a.dtq);
+#if !MDQT_K2_PIPE
+    const Pre cur = prep(vx, tp, t);
+#endif
 
     double u0, u1;
     const uint64_t sidx = substep0 + (uint64_t)s;
@@ -574,21 +664,19 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
     }
     // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
     const double pn = half ? cnorm(y[0]) : cnorm(y[1]);
+#if !MDQT_K2_DPSTAGE
     const double n3 = __shfl_sync(0xffffffffu, pn, base), n5 = __shfl_sync(0xffffffffu, pn, base + 1);
     const double n2 = __shfl_sync(0xffffffffu, pn, base + 2), n4 = __shfl_sync(0xffffffffu, pn, base + 3);
     const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;
-    const bool jump = !(u0 > dp0);
+#endif
 
-    const double uu = vq + expDet;
-    H.hE0 = fma(e1_0, uu, e0_0); H.hE1 = fma(e1_1, uu, e0_1); H.hE2 = fma(e1_2, uu, e0_2);
-    {
-      const double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;  // SU:508
-      double sn, cs;
-      sincos_fast(phi, sn, cs);
-      if (half) { H.a01r = hrot * cs; H.a01i = -(hrot * sn); H.a10r = hrot * cs; H.a10i = hrot * sn; }
-    }
+    H.hE0 = cur.hE0; H.hE1 = cur.hE1; H.hE2 = cur.hE2;
+    if (half) { H.a01r = cur.cr; H.a01i = -cur.ci; H.a10r = cur.cr; H.a10i = cur.ci; }
     cplx yn[3];
     double kick;
+#if MDQT_K2_PIPE
+    Pre nxt;
+#endif
     {
       cplx w[3], g[3], acc[3];
       // stage 1 also yields the partner amplitudes needed by the optical force (pre-step coherences)
@@ -596,7 +684,18 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
       const cplx r1 = {__shfl_xor_sync(0xffffffffu, y[1].re, 1), __shfl_xor_sync(0xffffffffu, y[1].im, 1)};
       kick = k1 * im_acb(y[0], y[1]) + k2 * im_acb(y[2], y[1]) + k3 * im_acb(r0, y[0]) + k4 * im_acb(y[2], y[0]) +
              k5 * im_acb(y[1], r1);
-      stage4(H, y, g);
+#if MDQT_K2_PIPE
+      // the no-jump kick is final here: sum it over the quad now and start on the next substep's coefficients
+      kick += __shfl_xor_sync(0xffffffffu, kick, 1);
+      kick += __shfl_xor_sync(0xffffffffu, kick, 2);
+      nxt = prep(__dadd_rn(__dadd_rn(vx, kick), __dmul_rn(a.dtq, fx)), __dadd_rn(tp, a.dtq), __dadd_rn(t, a.dtq));
+#endif
+      const double dp1 = stage4(H, y, g);
+#if MDQT_K2_DPSTAGE
+      const double dp0 = dp1;
+#else
+      (void)dp1;
+#endif
 #pragma unroll
       for (int k = 0; k < 3; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
       stage4(H, w, g);
@@ -617,40 +716,50 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
         yn[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
         yn[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
       }
-    }
-    if (!jump) {
+      const bool jump = !(u0 > dp0);
+      if (!jump) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) y[k] = yn[k];
-    } else {  // quantum jump (SU:573-703): all four lanes decide identically
-      double u2, u3, u4;
-      if (FORCED) {
-        const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
-        u2 = up[2]; u3 = up[3]; u4 = up[4];
-      } else {
-        uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
-        u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
-        o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
-        u4 = u52(o.x, o.y);
-      }
-      tp = 0.0;
-      const double tot = n2 + n3 + n4 + n5;
-      const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
-      const bool sDecay = !(u2 < C.dfrac);
-      kick = 0.0;
-      if (q == 0) {
-        double mag = sDecay ? a.vKick : a.vKickDP;
-        kick = (u3 < 0.5) ? mag : -mag;
-      }
-      int dest;
-      if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
-      else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
-      else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
-      else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
+        for (int k = 0; k < 3; k++) y[k] = yn[k];
+      } else {  // quantum jump (SU:573-703): all four lanes of the quad decide identically
+#if MDQT_K2_DPSTAGE
+        const double n3 = __shfl_sync(quadmask, pn, base), n5 = __shfl_sync(quadmask, pn, base + 1);
+        const double n2 = __shfl_sync(quadmask, pn, base + 2), n4 = __shfl_sync(quadmask, pn, base + 3);
+#endif
+        double u2, u3, u4;
+        if (FORCED) {
+          const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
+          u2 = up[2]; u3 = up[3]; u4 = up[4];
+        } else {
+          uint4 o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
+          u2 = u52(o.x, o.y); u3 = u52(o.z, o.w);
+          o = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
+          u4 = u52(o.x, o.y);
+        }
+        tp = 0.0;
+        const double tot = n2 + n3 + n4 + n5;
+        const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
+        const bool sDecay = !(u2 < C.dfrac);
+        const double mag = sDecay ? a.vKick : a.vKickDP;
+#if MDQT_K2_PIPE
+        kick = (u3 < 0.5) ? mag : -mag;  // every lane of the quad holds the total (the sum below is already done)
+        nxt = prep(__dadd_rn(__dadd_rn(vx, kick), __dmul_rn(a.dtq, fx)), a.dtq, __dadd_rn(t, a.dtq));  // tp restarts: 0 + dtq
+#else
+        kick = 0.0;
+        if (q == 0) kick = (u3 < 0.5) ? mag : -mag;
+#endif
+        int dest;
+        if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
+        else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
+        else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
+        else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
 #pragma unroll
-      for (int k = 0; k < 3; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
+        for (int k = 0; k < 3; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
+      }
     }
+#if !MDQT_K2_PIPE
     kick += __shfl_xor_sync(0xffffffffu, kick, 1);
     kick += __shfl_xor_sync(0xffffffffu, kick, 2);
+#endif
     vx = __dadd_rn(vx, kick);  // SU:705
     if (a.renorm) {
       double own = cnorm(y[0]) + cnorm(y[1]) + cnorm(y[2]);
@@ -661,8 +770,13 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
       for (int k = 0; k < 3; k++) { y[k].re /= nn; y[k].im /= nn; }
     }
     t = __dadd_rn(t, a.dtq);  // SU:716
+#if MDQT_K2_PIPE
+    cur = nxt;
+#endif
   }
 
+#undef prep
+  pdl_launch_dependents();  // the force kernel's launch and prologue may overlap the stores below (it waits before reading)
   if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 1);
   if (!active) return;
 #pragma unroll

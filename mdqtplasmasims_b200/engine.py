@@ -47,7 +47,8 @@ ABI_SYMBOLS = [
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
-    "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces",
+    "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces", "mdqt_comm_unique_id", "mdqt_comm_init", "mdqt_comm_destroy",
+    "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows",
 ]
 
 _lib = None
@@ -112,6 +113,12 @@ def load_library():
     L.mdqt_vv_steps.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                 ctypes.c_double]
     L.mdqt_set_ion_counts.argtypes = [vp, vp]
+    L.mdqt_comm_unique_id.argtypes = [vp]
+    L.mdqt_comm_init.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int]
+    L.mdqt_comm_destroy.argtypes = [vp]
+    L.mdqt_comm_exchange_positions.argtypes = [vp]
+    L.mdqt_comm_allreduce.argtypes = [vp, vp, ctypes.c_int]
+    L.mdqt_populations_rows.argtypes = [vp, vp]
     L.mdqt_time_forces.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
@@ -443,6 +450,28 @@ class Engine:
         ms, n = ctypes.c_double(), ctypes.c_int()
         self._ck(self.lib.mdqt_kernel_time_ms(self.h, which, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    # ---- row-decomposed runs: NCCL communicator inside the library -------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (rank 0 makes it and hands it to the other ranks)."""
+        buf = ctypes.create_string_buffer(128)
+        L = load_library()
+        if L.mdqt_comm_unique_id(buf):
+            raise MDQTError(L.mdqt_last_error().decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        """Collective: every rank calls it with the same id; the handle must own rows [rank N/world, (rank+1) N/world)."""
+        self._ck(self.lib.mdqt_comm_init(self.h, ctypes.c_char_p(unique_id), rank, world))
+
+    def comm_exchange_positions(self):
+        self._ck(self.lib.mdqt_comm_exchange_positions(self.h))
+
+    def populations_rows(self):
+        p = np.empty(self._lead() + (self.params.n_rows or self.N, 3))
+        self._ck(self.lib.mdqt_populations_rows(self.h, _ptr(p)))
+        return p
 
     def time_forces(self, reps=20):
         """ms per force-kernel launch: CUDA events around one replayed graph of ``reps`` back-to-back launches."""
