@@ -209,6 +209,9 @@ int mdqt_comm_init(mdqt_handle* h, const void* unique_id /* 128 bytes */, int ra
 int mdqt_comm_destroy(mdqt_handle* h);
 int mdqt_comm_exchange_positions(mdqt_handle* h);
 int mdqt_comm_allreduce(mdqt_handle* h, double* values, int n); /* sum over the ranks, in place, n <= 6019 */
+/* The handle's own rows only, written at their place in host arrays of the usual full layouts (R, V = [3][ld], psi =
+ * [n_ions][S][2], tPart = [n_ions]): the ranks of a row-decomposed run assemble one host state without overlap. n_traj = 1. */
+int mdqt_download_rows(mdqt_handle* h, double* R, double* V, double* psi, double* tPart, int ld);
 /* S/P/D populations of the handle's own rows: pops = double [n_traj][n_rows][3] (row-decomposed handles). */
 int mdqt_populations_rows(mdqt_handle* h, double* pops);
 

@@ -684,6 +684,26 @@ int mdqt_epot(mdqt_handle* h, double* epot) {
   CU(cudaMemcpyAsync(epot, h->scalars + (size_t)h->B * 8, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
+  if (h->comm) return mdqt_comm_allreduce(h, epot, 1);  // the own rows' share -> the whole system's energy on every rank
+  return MDQT_OK;
+}
+
+int mdqt_download_rows(mdqt_handle* h, double* R, double* V, double* psi, double* tPart, int ld) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (ld < h->N) return fail(MDQT_EINVAL, "ld smaller than n_ions");
+  if (h->B != 1) return fail(MDQT_ESTATE, "mdqt_download_rows needs n_traj == 1");
+  CU(cudaSetDevice(h->p.device));
+  const size_t r0 = (size_t)h->row0, nr = (size_t)h->nrows;
+  if (R) CU(cudaMemcpy2DAsync(R + r0, (size_t)ld * 8, h->R + r0, (size_t)h->ld * 8, nr * 8, 3, cudaMemcpyDeviceToHost, h->stream));
+  if (V) CU(cudaMemcpy2DAsync(V + r0, (size_t)ld * 8, h->V + r0, (size_t)h->ld * 8, nr * 8, 3, cudaMemcpyDeviceToHost, h->stream));
+  if (psi) {
+    if (!h->S) return fail(MDQT_ESTATE, "handle has no wavefunctions (scheme NONE)");
+    launch_transpose_psi_out(h->psi, h->psi_stage, h->S, h->N, h->ld, h->B, h->stream);
+    CU(cudaMemcpyAsync(psi + r0 * 2 * h->S, h->psi_stage + r0 * 2 * h->S, nr * 2 * h->S * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (tPart) CU(cudaMemcpyAsync(tPart + r0, h->tPart + r0, nr * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
   return MDQT_OK;
 }
 

@@ -68,21 +68,22 @@ struct mdqt_comm {
     if (r_ != ncclSuccess) return mdqt_fail(MDQT_ECUDA, std::string(#call) + ": " + nccl_api()->GetErrorString(r_)); \
   } while (0)
 
-__global__ void k_pack_rows(const long long* __restrict__ Rfix, long long* __restrict__ block, int row0, int rows, int ld) {
+__global__ void k_pack_rows(const long long* __restrict__ Rfix, long long* __restrict__ block, int row0, int rows, int own, int ld) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= 3LL * rows) return;
   const int c = (int)(g / rows), i = (int)(g % rows);
-  block[g] = Rfix[(size_t)c * ld + row0 + i];
+  block[g] = i < own ? Rfix[(size_t)c * ld + row0 + i] : 0;  // the last rank's block is padded
 }
 // Rfix[c][g*rows + i] = xbuf[g][c][i] for every rank g but `skip`
-__global__ void k_unpack_rows(const long long* __restrict__ xbuf, long long* __restrict__ Rfix, int world, int rows, int ld, int skip) {
+__global__ void k_unpack_rows(const long long* __restrict__ xbuf, long long* __restrict__ Rfix, int world, int rows, int N, int ld, int skip) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= 3LL * rows * world) return;
   const int g = (int)(k / (3LL * rows));
   if (g == skip) return;
   const long long r = k % (3LL * rows);
   const int c = (int)(r / rows), i = (int)(r % rows);
-  Rfix[(size_t)c * ld + (size_t)g * rows + i] = xbuf[k];
+  const long long row = (long long)g * rows + i;
+  if (row < N) Rfix[(size_t)c * ld + row] = xbuf[k];
 }
 
 extern "C" {
@@ -102,14 +103,15 @@ int mdqt_comm_init(mdqt_handle* h, const void* unique_id, int rank, int world) {
   if (h->comm) return mdqt_fail(MDQT_ESTATE, "handle already has a communicator");
   if (world < 1 || rank < 0 || rank >= world) return mdqt_fail(MDQT_EINVAL, "rank outside [0, world)");
   if (h->B != 1) return mdqt_fail(MDQT_ESTATE, "row decomposition needs n_traj == 1");
-  if (h->N % world != 0 || h->nrows != h->N / world || h->row0 != rank * h->nrows)
-    return mdqt_fail(MDQT_EINVAL, "handle must own rows [rank * N/world, (rank+1) * N/world) with N divisible by world");
+  const int rows = (h->N + world - 1) / world;  // rows per rank; the last rank holds the remainder
+  if (h->row0 != rank * rows || h->nrows != std::min(rows, h->N - h->row0) || h->nrows < 1)
+    return mdqt_fail(MDQT_EINVAL, "handle must own rows [rank * R, min(N, (rank+1) * R)) with R = ceil(N / world)");
   NcclApi* n = nccl_api();
   if (!n->error.empty()) return mdqt_fail(MDQT_ESTATE, n->error);
   CU(cudaSetDevice(h->p.device));
   mdqt_comm* c = new mdqt_comm();
   memset(c, 0, sizeof(*c));
-  c->rank = rank; c->world = world; c->rows = h->nrows;
+  c->rank = rank; c->world = world; c->rows = rows;
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof(id));
   ncclResult_t r = n->CommInitRank(&c->comm, world, id, rank);
@@ -169,12 +171,12 @@ static int start_exchange(mdqt_handle* h) {
   mdqt_comm* c = h->comm;
   const long long n = 3LL * c->rows;
   long long* own = c->xbuf + (size_t)c->rank * 3 * c->rows;
-  k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->Rfix, own, h->row0, c->rows, h->ld);
+  k_pack_rows<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->Rfix, own, h->row0, c->rows, h->nrows, h->ld);
   CU(cudaEventRecord(c->ev_packed, h->stream));
   CU(cudaStreamWaitEvent(c->cstream, c->ev_packed, 0));
   NC(nccl_api()->AllGather(own, c->xbuf, (size_t)n, ncclInt64, c->comm, c->cstream));
   const long long m = n * c->world;
-  k_unpack_rows<<<(unsigned)((m + 255) / 256), 256, 0, c->cstream>>>(c->xbuf, h->Rfix, c->world, c->rows, h->ld, c->rank);
+  k_unpack_rows<<<(unsigned)((m + 255) / 256), 256, 0, c->cstream>>>(c->xbuf, h->Rfix, c->world, c->rows, h->N, h->ld, c->rank);
   CU(cudaEventRecord(c->ev_unpacked, c->cstream));
   c->pending = true;
   return MDQT_OK;

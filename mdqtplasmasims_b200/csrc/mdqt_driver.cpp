@@ -3,6 +3,8 @@
 // same output and restart files, hot path on the GPU.
 //
 //   mdqt_run <job>  [options]                     one trajectory, exactly `./runFile <job>` of the reference (SU:1145)
+//   mdqt_run <job> --gpus G [options]             ONE large job (e.g. --N0 1000000) row-decomposed over G GPUs inside the library
+//                                                 (mdqt_comm_init: NCCL all-gather of positions per MD step); same files
 //   mdqt_run --jobs a-b [--batch 64] [--gpus 8]   the SLURM array of the reference (exampleSlurmFile.slurm:3,16:
 //                                                 `--array=a-b`, `srun exe $SLURM_ARRAY_TASK_ID`) on one box: jobs a..b are
 //                                                 dealt to the GPUs in contiguous blocks and advanced `batch` at a time in
@@ -248,6 +250,139 @@ static BatchResult run_batch(const Options& o, unsigned job0, int B, int device,
   return res;
 }
 
+// ---- one LARGE job over G GPUs (BASELINE configs[4]): i-row decomposition inside the library (mdqt_comm_init), one host
+// thread per GPU. Every thread drives the same schedule; the observables of output() are whole-system values on every
+// rank (all-reduce inside the library), per-ion data are assembled in shared host arrays from each rank's own rows and
+// written by rank 0 through the same writer as a single-GPU run: same files.
+class ThreadBarrier {
+ public:
+  explicit ThreadBarrier(int n) : n_(n) {}
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    const long gen = gen_;
+    if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+    else cv_.wait(lk, [&] { return gen_ != gen; });
+  }
+ private:
+  std::mutex m_; std::condition_variable cv_; int n_, count_ = 0; long gen_ = 0;
+};
+
+static int run_rows(const Options& o, unsigned job, int G, std::vector<std::unique_ptr<OutputWriter>>& writers) {
+  const int ld = o.N0 + 1000;  // SU:126
+  char dir[1024];
+  if (mdqt_io_dirname(dir, sizeof(dir), o.saveDirectory.c_str(), o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning, o.detuningDP,
+                      o.Om, o.OmDP, o.N0, job, 1)) { fprintf(stderr, "mdqt_run: directory name too long\n"); return 1; }
+  const long seed = o.seed_add_job ? o.seed + (long)job : o.seed;
+  std::vector<double> R((size_t)3 * ld), V((size_t)3 * ld), psi((size_t)ld * 24), tPart(ld, 0.0), vholder((size_t)3 * MDQT_NUM_VINTERVALS * ld, 0.0);
+  unsigned counter = 0;
+  double t0 = 0.0, L = 0, lDeb = 0;
+  int N, c0_start = o.c0;
+  if (o.newRun == 1) {
+    N = mdqt_io_init_su(seed, o.N0, o.Ge, ld, R.data(), V.data(), psi.data(), tPart.data(), &L, &lDeb);
+    if (N < 0) { fprintf(stderr, "mdqt_run: more than N0+1000 ions drawn\n"); return 1; }
+    printf("%i\n", N);
+    c0_start = -1;
+  } else {
+    N = mdqt_io_read_conditions(dir, o.c0, ld, R.data(), V.data(), psi.data(), &counter, &t0, vholder.data());
+    if (N < 0) { fprintf(stderr, "mdqt_run: cannot read restart files for c0=%d in %s (%d)\n", o.c0, dir, N); return 1; }
+  }
+  if (G > N) G = N;
+  const int rows = (N + G - 1) / G;
+  while ((G - 1) * rows >= N) G--;  // every rank owns at least one row
+  unsigned char uid[128];
+  if (mdqt_comm_unique_id(uid)) { fprintf(stderr, "mdqt_run: %s\n", mdqt_last_error()); return 1; }
+  std::vector<double> pops((size_t)N * 3), pvel(3 * 2001);
+  ThreadBarrier bar(G);
+  std::vector<int> rc(G, 0);
+  int c0_end = 0; double t_end = 0; long nsub_total = 0, nforce = 0, nout = 0; double wall = 0;
+  auto worker = [&](int g) {
+    mdqt_handle* h = NULL;
+    auto bail = [&](const char* what) { fprintf(stderr, "mdqt_run: rank %d: %s: %s\n", g, what, mdqt_last_error()); rc[g] = 1; };
+#define CKR(call) do { if ((call) != 0) { bail(#call); if (h) mdqt_destroy(h); return; } } while (0)
+    mdqt_params p;
+    CKR(mdqt_params_su(&p, o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning, o.detuningDP, o.Om, o.OmDP, o.N0, N));
+    p.traj0 = (int)job; p.seed = (uint64_t)seed; p.device = o.device + g; p.renormalize = o.renorm;
+    p.row0 = g * rows; p.n_rows = std::min(rows, N - g * rows);
+    p.plan_n = o.fast_single ? 0 : o.N0;  // the same bits as the one-GPU run of this job
+    CKR(mdqt_create(&p, &h));
+    CKR(mdqt_comm_init(h, uid, g, G));
+    CKR(mdqt_upload_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
+    const uint64_t sub0 = o.newRun == 1 ? 0 : (uint64_t)llround(t0 / p.dtq);
+    CKR(mdqt_set_time(h, t0, sub0));
+    double Epot0 = 0.0;
+    CKR(mdqt_epot(h, &Epot0));
+    if (o.newRun != 1) Epot0 = 0.0;  // Q8
+    int c0 = c0_start, tsc = p.substeps_per_md;
+    double t = t0;
+    long nsub = 0, nf = 0, no = 0;
+    std::vector<double> pops_rows((size_t)p.n_rows * 3), pv(3 * 2001);
+    auto wall0 = std::chrono::steady_clock::now();
+    for (;;) {
+      int do_output, do_forces;
+      int n = mdqt_schedule_next(&c0, &tsc, &t, p.substeps_per_md, o.sampleFreq, p.dtq, o.tmax, &do_output, &do_forces);
+      if (n == 0) break;
+      if (do_output) {
+        mdqt_diag d;
+        CKR(mdqt_diagnostics(h, &d));
+        CKR(mdqt_vel_dist(h, pv.data()));
+        CKR(mdqt_populations_rows(h, pops_rows.data()));
+        std::copy(pops_rows.begin(), pops_rows.end(), pops.begin() + (size_t)p.row0 * 3);
+        CKR(mdqt_download_rows(h, NULL, V.data(), NULL, NULL, ld));
+        bar.wait();
+        if (g == 0) {
+          OutputJob oj;
+          oj.dir = dir; oj.counter = counter; oj.N = N; oj.d = d; oj.Epot0 = Epot0;
+          oj.pvel = pv; oj.pops = pops; oj.vx.assign(V.begin(), V.begin() + N);
+          writers[0]->push(std::move(oj));
+          counter++;
+        }
+        bar.wait();
+        no++;
+      }
+      if (do_forces && !do_output && n == p.substeps_per_md) {
+        int k = 1;
+        for (;;) {
+          int c0b = c0, tscb = tsc, o2, f2;
+          double tb = t;
+          int n2 = mdqt_schedule_next(&c0b, &tscb, &tb, p.substeps_per_md, o.sampleFreq, p.dtq, o.tmax, &o2, &f2);
+          if (n2 != p.substeps_per_md || !f2 || o2) break;
+          c0 = c0b; tsc = tscb; t = tb; k++;
+        }
+        CKR(mdqt_md_steps(h, k));
+        nf += k; nsub += (long)k * n;
+        continue;
+      }
+      // a partial MD step (around output()): forces over the own rows, n fused substeps, then the position all-gather
+      if (do_forces) { CKR(mdqt_forces(h)); nf++; }
+      CKR(mdqt_substeps(h, n));
+      CKR(mdqt_comm_exchange_positions(h));
+      nsub += n;
+    }
+    CKR(mdqt_download_rows(h, R.data(), V.data(), psi.data(), tPart.data(), ld));
+    bar.wait();
+    if (g == 0) {
+      c0_end = c0; t_end = t; nsub_total = nsub; nforce = nf; nout = no;
+      wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    }
+    mdqt_destroy(h);
+#undef CKR
+  };
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; g++) th.emplace_back(worker, g);
+  for (auto& x : th) x.join();
+  for (int g = 0; g < G; g++) if (rc[g]) return 1;
+  for (auto& w : writers) w->finish();
+  if (mdqt_io_write_conditions(dir, c0_end, N, counter, R.data(), V.data(), psi.data(), ld, vholder.data())) {
+    fprintf(stderr, "mdqt_run: cannot write restart files into %s\n", dir);
+    return 1;
+  }
+  if (!o.quiet)
+    fprintf(stderr, "mdqt_run: job %u, N=%d row-decomposed over %d GPUs (%d rows each), t=%.6f, c0=%d: %ld substeps, %ld force calls, %ld outputs in %.3f s "
+                    "(%.3e ion-steps/s, %.3e pair-interactions/s); files in %s\n", job, N, G, rows, t_end, c0_end, nsub_total, nforce, nout, wall,
+            (double)N * nsub_total / wall, (double)N * N * nforce / wall, dir);
+  return 0;
+}
+
 static void usage() {
   fprintf(stderr, "usage: mdqt_run <job> | --jobs a-b [--batch n] [--gpus n]\n"
                   "       [--Ge x] [--density x] [--sig0 x] [--Te x] [--fracOfSig x] [--N0 n] [--detuning x] [--detuningDP x] [--Om x]\n"
@@ -306,7 +441,9 @@ int main(int argc, char** argv) {
   std::vector<BatchResult> results;
   std::mutex rm;
   int failed = 0;
-  if (!array) {
+  if (!array && gpus > 1) {
+    failed = run_rows(o, (unsigned)job_a, std::min(gpus, ndev), writers);
+  } else if (!array) {
     BatchResult r = run_batch(o, (unsigned)job_a, 1, o.device, writers);
     failed = !r.ok;
   } else {

@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kItemWarps = 8;
 constexpr int kItemCtasPerSM = 2;
+constexpr int kItemMaxB = 512;   // per-trajectory ion counts cached in shared memory up to this batch size
 constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps = 120 KB per CTA at most
 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -467,6 +468,7 @@ template <int IPT, bool EPOT, bool HL>
 __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double stab[kExpTable];
+  __shared__ int snb[kItemMaxB];  // the trajectories' ion counts: read at every item decode, so not from L2
   constexpr int RPG = 32 * IPT;  // rows per group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tj = a.jlen;  // tile capacity (a multiple of 8, <= kItemMaxJ)
@@ -477,6 +479,9 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
   if (tid == 0) stamp_time(a.stamp, 0);
   WTRACE(0)
   for (int k = tid; k < kExpTable; k += kItemWarps * 32) cp_async8(&stab[k], &c_exp2tab[k]);
+  const bool nb_smem = a.nb && a.B <= kItemMaxB;
+  if (nb_smem) for (int k = tid; k < a.B; k += kItemWarps * 32) snb[k] = a.nb[k];  // constant for the handle's lifetime
+  __syncthreads();
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
   if (!EPOT && tid == 0 && blockIdx.x == 0) advance_clock(a);
 
@@ -491,7 +496,7 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
     it.ch = k - (int)t * a.nsplit;
     it.b = (int)(((unsigned long long)t * mg_g) >> 40);
     it.g = (int)t - it.b * gcap;
-    it.Nb = a.nb ? a.nb[it.b] : a.N;
+    it.Nb = nb_smem ? snb[it.b] : (a.nb ? a.nb[it.b] : a.N);
     // empty when the group or the chunk lies beyond the trajectory's ions
     return (a.row0 + it.g * RPG < min(rowend_cap, it.Nb)) && (it.ch * a.jlen < it.Nb);
   };
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
   if (k < total) issue(cur, 0);
   cp_async_commit();
   cp_async_wait_all();
-  __syncthreads();  // the exp table is complete for every warp; the only CTA-wide barrier of the kernel
+  __syncthreads();  // the exp table is complete for every warp; the last CTA-wide barrier of the kernel
   WTRACE(1)
   int buf = 0;
   while (k < total) {

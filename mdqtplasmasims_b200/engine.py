@@ -48,7 +48,7 @@ ABI_SYMBOLS = [
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
     "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces", "mdqt_comm_unique_id", "mdqt_comm_init", "mdqt_comm_destroy",
-    "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows",
+    "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows", "mdqt_download_rows",
 ]
 
 _lib = None
@@ -119,6 +119,7 @@ def load_library():
     L.mdqt_comm_exchange_positions.argtypes = [vp]
     L.mdqt_comm_allreduce.argtypes = [vp, vp, ctypes.c_int]
     L.mdqt_populations_rows.argtypes = [vp, vp]
+    L.mdqt_download_rows.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int]
     L.mdqt_time_forces.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]

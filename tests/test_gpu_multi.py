@@ -2,6 +2,9 @@
 library -- mdqt_comm_init + mdqt_md_steps with one in-place ncclAllGather of fixed-point positions per MD step, overlapped with
 the local j chunks of the next force call -- against the same run on one GPU. One Python thread per GPU (ctypes releases the
 GIL, so the collective calls run concurrently), one handle and one communicator each."""
+import filecmp
+import os
+import subprocess
 import threading
 
 import numpy as np
@@ -81,3 +84,28 @@ def test_comm_md_steps_equal_the_single_gpu_run_bitwise(n):
             assert abs(d["vx_avg"] - d0["vx_avg"]) <= 1e-15
             assert np.abs(pv - pv0).max() <= 1e-11 * pv0.max() and np.array_equal(pv, res[0][3])
     full.close()
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs at least 2 GPUs")
+def test_mdqt_run_row_decomposed_writes_the_single_gpu_files(tmp_path):
+    """`mdqt_run <job> --gpus G`: one job row-decomposed over G GPUs inside the library (unequal row blocks when G does not divide
+    N) writes byte-identical files to the one-GPU run of the same job, lasers on."""
+    from mdqtplasmasims_b200 import hostio
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    drv = os.path.join(root, "mdqtplasmasims_b200", "mdqt_run")
+    common = ["4", "--seed", "21", "--N0", "1200", "--tmax", "0.17", "--quiet"]
+    s1 = str(tmp_path / "one") + "/"
+    os.mkdir(s1)
+    r = subprocess.run([drv] + common + ["--saveDirectory", s1], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    d1 = hostio.dirname(s1, N0=1200, job=4)
+    files = sorted(os.listdir(d1))
+    for G in [g for g in (2, 3, 8) if g <= _ndev()]:
+        sg = str(tmp_path / ("g%d" % G)) + "/"
+        os.mkdir(sg)
+        r = subprocess.run([drv] + common + ["--gpus", str(G), "--saveDirectory", sg], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        dg = hostio.dirname(sg, N0=1200, job=4)
+        assert sorted(os.listdir(dg)) == files
+        match, mismatch, err = filecmp.cmpfiles(d1, dg, files, shallow=False)
+        assert not mismatch and not err, (G, mismatch[:4], err[:4])
