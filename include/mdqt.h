@@ -178,6 +178,18 @@ int mdqt_vstore_upload(mdqt_handle* h, const double* v);
 /* recordVAF / recordLongViscAutoCorr / recordVCubeAutoCorr / recordVFourthAutoCorr (MD:654-823) over the stored
  * velocities: each output is double [n_traj][T] (NULL = skip); Gamma enters the subtracted constants (MD:710, 785). */
 int mdqt_autocorrelations(mdqt_handle* h, double Gamma, double* vaf, double* longvisc, double* vcube, double* vfourth);
+/* MD-family recorders that are reductions over the velocities: recordTemperature() (MD:525-546), recordTempForEachAxis()
+ * (MD:560-582), recordTaggedParticleMoments() (MD:923-1029, MC408L:1069). tags = uint8 [n_traj][n_ions], bit k = member of tag
+ * set k (the reference's taggedOne..taggedFour, MD:809-921; NULL clears). mdqt_moments_begin(nslots) allocates a device log,
+ * mdqt_moments_record(slot) writes one record there WITHOUT synchronising (call it every MD step), mdqt_moments_download copies
+ * the first nslots records: double [nslots][n_traj][23] = { sum v_x^2, sum v_y^2, sum v_z^2 over all ions; then for each tag set:
+ * count, sum v_x, sum v_x^2, sum v_x^3, sum v_x^4 }. The caller divides and subtracts the equilibrium constants as the reference does. */
+int mdqt_set_tags(mdqt_handle* h, const uint8_t* tags);
+int mdqt_moments_begin(mdqt_handle* h, int nslots);
+int mdqt_moments_record(mdqt_handle* h, int slot);
+int mdqt_moments_download(mdqt_handle* h, double* out, int nslots);
+/* anisotropizeVelocities() (MD:548-558): V_x *= sx, V_y *= sy, V_z *= sz. */
+int mdqt_scale_velocities(mdqt_handle* h, double sx, double sy, double sz);
 /* Test hook: uniforms u[n_ions][2] for the next mdqt_tag_particles calls (n_traj must be 1). NULL restores Philox. */
 int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u);
 /* Test hook for the MD-family Andersen thermostat: per-ion collision uniforms u[n_ions] and the velocities

@@ -12,7 +12,7 @@ DRIVER = os.path.join(HERE, "mdqt_run")
 SOURCES = ["mdqt_force.cu", "mdqt_qt.cu", "mdqt_diag.cu", "mdqt_capi.cu", "mdqt_comm.cu", "mdqt_io.cpp"]
 HEADERS = ["mdqt_internal.h", "mdqt_handle.h", "mdqt_fixed.cuh", "mdqt_qtconsts.h", os.path.join("..", "..", "include", "mdqt.h"),
            os.path.join("..", "..", "include", "mdqt_io.h")]
-DRIVER_SOURCES = ["mdqt_driver.cpp"]
+DRIVER_SOURCES = ["mdqt_driver.cpp", "mdqt_programs.cpp"]
 
 
 def _nvcc():

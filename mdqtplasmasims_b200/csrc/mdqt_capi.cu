@@ -257,6 +257,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
   h->gr_counts = nullptr; h->vstore = h->ac_partials = h->ac_out = nullptr; h->vstore_T = 0;
   h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr; h->comm = nullptr;
+  h->tags = nullptr; h->moments = nullptr; h->moments_slots = 0;
   h->timing = 0; h->ev_used = 0; h->stamps = nullptr; h->stamps_cap = 0;
   for (int k = 0; k < 4; k++) { h->time_ms[k] = 0; h->time_n[k] = 0; }
   plan_force(h);
@@ -306,6 +307,8 @@ int mdqt_destroy(mdqt_handle* h) {
   if (h->tagged) cudaFree(h->tagged);
   if (h->clock) cudaFree(h->clock);
   if (h->nb) cudaFree(h->nb);
+  if (h->tags) cudaFree(h->tags);
+  if (h->moments) cudaFree(h->moments);
   if (h->stamps) cudaFree(h->stamps);
   if (h->seeds) cudaFree(h->seeds);
   for (GraphEntry& g : h->graphs) cudaGraphExecDestroy(g.exec);
@@ -1076,6 +1079,62 @@ int mdqt_autocorrelations(mdqt_handle* h, double Gamma, double* vaf, double* lon
   for (int b = 0; b < h->B; b++)
     for (int p = 0; p < 4; p++)
       if (dst[p]) memcpy(dst[p] + (size_t)b * T, o.data() + ((size_t)b * 4 + p) * T, (size_t)T * 8);
+  return MDQT_OK;
+}
+
+int mdqt_set_tags(mdqt_handle* h, const uint8_t* tags) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  NEED_UNIFORM_N(h);
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!tags) { if (h->tags) { cudaFree(h->tags); h->tags = nullptr; } return MDQT_OK; }
+  const size_t n = (size_t)h->B * h->N;
+  if (!h->tags) CU(cudaMalloc((void**)&h->tags, n));
+  CU(cudaMemcpy(h->tags, tags, n, cudaMemcpyHostToDevice));
+  return MDQT_OK;
+}
+
+int mdqt_moments_begin(mdqt_handle* h, int nslots) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (nslots < 1 || nslots > (1 << 22)) return fail(MDQT_EINVAL, "nslots outside [1, 2^22]");
+  NEED_UNIFORM_N(h);
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_moments: a row-decomposed handle holds the velocities of its own rows only");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (h->moments) { cudaFree(h->moments); h->moments = nullptr; }
+  CU(cudaMalloc((void**)&h->moments, sizeof(double) * (size_t)nslots * h->B * kMomentsPerRecord));
+  CU(cudaMemsetAsync(h->moments, 0, sizeof(double) * (size_t)nslots * h->B * kMomentsPerRecord, h->stream));
+  h->moments_slots = nslots;
+  return MDQT_OK;
+}
+
+int mdqt_moments_record(mdqt_handle* h, int slot) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  if (!h->moments) return fail(MDQT_ESTATE, "mdqt_moments_begin not called");
+  if (slot < 0 || slot >= h->moments_slots) return fail(MDQT_EINVAL, "slot outside [0, nslots)");
+  CU(cudaSetDevice(h->p.device));
+  launch_moments(h->V, h->tags, h->N, h->ld, h->B, h->moments + (size_t)slot * h->B * kMomentsPerRecord, h->stream);
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_moments_download(mdqt_handle* h, double* out, int nslots) {
+  if (!h || !out) return fail(MDQT_EINVAL, "null argument");
+  if (!h->moments) return fail(MDQT_ESTATE, "mdqt_moments_begin not called");
+  if (nslots < 1 || nslots > h->moments_slots) return fail(MDQT_EINVAL, "nslots outside [1, slots recorded]");
+  CU(cudaSetDevice(h->p.device));
+  CU(cudaMemcpyAsync(out, h->moments, sizeof(double) * (size_t)nslots * h->B * kMomentsPerRecord, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
+int mdqt_scale_velocities(mdqt_handle* h, double sx, double sy, double sz) {
+  if (!h) return fail(MDQT_EINVAL, "null handle");
+  NEED_UNIFORM_N(h);
+  CU(cudaSetDevice(h->p.device));
+  launch_scale_velocities(h->V, h->N, h->ld, h->B, sx, sy, sz, h->stream);
+  CU(cudaGetLastError());
   return MDQT_OK;
 }
 

@@ -252,6 +252,56 @@ void launch_autocorr(const double* vstore, int N, int B, int T, double sub2, dou
   k_autocorr_final<<<g2, 256, 0, s>>>(partials, nchunks, T, N, sub2, sub4, out);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// MD-family recorders that are plain reductions over the velocities: recordTemperature() (MD:525-546),
+// recordTempForEachAxis() (MD:560-582) and recordTaggedParticleMoments() (MD:923-1029; MC408L:1069). One record =
+// 23 sums per trajectory: sum v_x^2, v_y^2, v_z^2 over all ions, then for each of the four tag sets (bit k of tags[i]):
+// count, sum v_x, v_x^2, v_x^3, v_x^4 (powers formed left to right as the reference writes them). The host divides and
+// subtracts the equilibrium constants. One CTA per trajectory, thread-strided sums + a fixed tree: reproducible.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_moments(const double* __restrict__ V, const unsigned char* __restrict__ tags, int N, int ld,
+                                                  double* __restrict__ out) {
+  __shared__ double sred[32];
+  const int b = blockIdx.x;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const double* vy = vx + ld;
+  const double* vz = vy + ld;
+  const unsigned char* tg = tags ? tags + (size_t)b * N : nullptr;
+  double acc[kMomentsPerRecord];
+#pragma unroll
+  for (int k = 0; k < kMomentsPerRecord; k++) acc[k] = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const double x = vx[i], y = vy[i], z = vz[i];
+    acc[0] += x * x; acc[1] += y * y; acc[2] += z * z;
+    const unsigned m = tg ? tg[i] : 0u;
+    const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (m & (1u << k)) { acc[3 + 5 * k] += 1.0; acc[4 + 5 * k] += x; acc[5 + 5 * k] += x2; acc[6 + 5 * k] += x3; acc[7 + 5 * k] += x4; }
+  }
+#pragma unroll
+  for (int k = 0; k < kMomentsPerRecord; k++) {
+    const double tot = block_sum_1024(acc[k], sred);
+    if (threadIdx.x == 0) out[(size_t)b * kMomentsPerRecord + k] = tot;
+  }
+}
+void launch_moments(const double* V, const unsigned char* tags, int N, int ld, int B, double* out, cudaStream_t s) {
+  k_moments<<<B, 1024, 0, s>>>(V, tags, N, ld, out);
+}
+
+// anisotropizeVelocities() (MD:548-558): V_c *= scale_c
+__global__ void k_scale_velocities(double* __restrict__ V, int N, int ld, int B, double sx, double sy, double sz) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= 3LL * N * B) return;
+  const int i = (int)(g % N), bc = (int)(g / N), c = bc % 3;
+  double* v = V + (size_t)bc * ld + i;
+  *v = __dmul_rn(c == 0 ? sx : (c == 1 ? sy : sz), *v);
+}
+void launch_scale_velocities(double* V, int N, int ld, int B, double sx, double sy, double sz, cudaStream_t s) {
+  const long long n = 3LL * N * B;
+  k_scale_velocities<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, N, ld, B, sx, sy, sz);
+}
+
 // pops[b][i][3] = popS, popP, popD with the reference's state grouping (12/7-level: S 0,1; P 2..5; D 6..S-1)
 __global__ void k_populations(const double* __restrict__ psi, int S, int N, int ld, double* __restrict__ pops) {
   const int b = blockIdx.y;

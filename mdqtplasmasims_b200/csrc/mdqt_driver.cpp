@@ -384,14 +384,30 @@ static int run_rows(const Options& o, unsigned job, int G, std::vector<std::uniq
 }
 
 static void usage() {
-  fprintf(stderr, "usage: mdqt_run <job> | --jobs a-b [--batch n] [--gpus n]\n"
+  fprintf(stderr, "usage: mdqt_run [--program su|md|fz408l] <job> | --jobs a-b [--batch n] [--gpus n]\n"
                   "       [--Ge x] [--density x] [--sig0 x] [--Te x] [--fracOfSig x] [--N0 n] [--detuning x] [--detuningDP x] [--Om x]\n"
                   "       [--OmDP x] [--saveDirectory dir/] [--newRun 0|1] [--c0 n] [--tmax x] [--reNormalizewvFns 0|1] [--sampleFreq n]\n"
                   "       [--seed n] [--device n] [--writers n] [--fast-single] [--quiet]\n");
 }
 
+int mdqt_program_md(int argc, char** argv);      // mdqt_programs.cpp
+int mdqt_program_fz408l(int argc, char** argv);
+
 int main(int argc, char** argv) {
   if (argc < 2) { usage(); return 2; }
+  // mdqt_run --program md|fz408l <job> [options]: the host loops of the reference's other programs (mdqt_programs.cpp)
+  if (argc >= 3 && !strcmp(argv[1], "--program")) {
+    std::vector<char*> av;
+    av.push_back(argv[0]);
+    for (int i = 3; i < argc; i++) av.push_back(argv[i]);
+    if (!strcmp(argv[2], "md")) return mdqt_program_md((int)av.size(), av.data());
+    if (!strcmp(argv[2], "fz408l")) return mdqt_program_fz408l((int)av.size(), av.data());
+    if (strcmp(argv[2], "su")) { fprintf(stderr, "mdqt_run: unknown program %s (su, md, fz408l)\n", argv[2]); return 2; }
+    argc = (int)av.size();
+    static std::vector<char*> keep;
+    keep = av;
+    argv = keep.data();
+  }
   // defaults = the reference's globals (SU:56-78)
   std::map<std::string, std::string> opt = {
       {"Ge", "0.1"}, {"density", "2"}, {"sig0", "4.0"}, {"Te", "19.0"}, {"fracOfSig", "0"}, {"N0", "3500"}, {"detuning", "-1"},

@@ -45,6 +45,8 @@ struct mdqt_handle {
   double time_ms[4]; int time_n[4];  // force kernel, substep kernel, gap force->substep, gap substep->force
   double* clock;                    // device {t, substep index}: the simulation clock inside replayed graphs
   std::vector<GraphEntry> graphs;   // small cache keyed by nsteps
+  unsigned char* tags;              // [B][N] four tag bits per ion (MD-family tagged-particle recorders) or null
+  double* moments; int moments_slots;  // [slots][B][23] recorded sums (mdqt_moments_begin / _record / _download)
   mdqt_comm* comm;                  // row-decomposed runs: NCCL communicator and exchange buffers (mdqt_comm_init), or null
 };
 

@@ -48,7 +48,8 @@ ABI_SYMBOLS = [
     "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
     "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces", "mdqt_comm_unique_id", "mdqt_comm_init", "mdqt_comm_destroy",
-    "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows", "mdqt_download_rows",
+    "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows", "mdqt_download_rows", "mdqt_set_tags", "mdqt_moments_begin", "mdqt_moments_record",
+    "mdqt_moments_download", "mdqt_scale_velocities",
 ]
 
 _lib = None
@@ -120,6 +121,11 @@ def load_library():
     L.mdqt_comm_allreduce.argtypes = [vp, vp, ctypes.c_int]
     L.mdqt_populations_rows.argtypes = [vp, vp]
     L.mdqt_download_rows.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int]
+    L.mdqt_set_tags.argtypes = [vp, vp]
+    L.mdqt_moments_begin.argtypes = [vp, ctypes.c_int]
+    L.mdqt_moments_record.argtypes = [vp, ctypes.c_int]
+    L.mdqt_moments_download.argtypes = [vp, vp, ctypes.c_int]
+    L.mdqt_scale_velocities.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
     L.mdqt_time_forces.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
@@ -451,6 +457,25 @@ class Engine:
         ms, n = ctypes.c_double(), ctypes.c_int()
         self._ck(self.lib.mdqt_kernel_time_ms(self.h, which, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    # ---- MD-family recorders over the velocities (MD:525-582, 923-1029) ------------------------------------------------
+    def set_tags(self, tags):
+        t = None if tags is None else np.ascontiguousarray(tags, dtype=np.uint8)
+        self._ck(self.lib.mdqt_set_tags(self.h, None if t is None else ctypes.c_void_p(t.ctypes.data)))
+
+    def moments_begin(self, nslots):
+        self._ck(self.lib.mdqt_moments_begin(self.h, nslots))
+
+    def moments_record(self, slot):
+        self._ck(self.lib.mdqt_moments_record(self.h, slot))
+
+    def moments_download(self, nslots):
+        out = np.empty((nslots,) + self._lead() + (23,))
+        self._ck(self.lib.mdqt_moments_download(self.h, _ptr(out), nslots))
+        return out
+
+    def scale_velocities(self, sx, sy, sz):
+        self._ck(self.lib.mdqt_scale_velocities(self.h, sx, sy, sz))
 
     # ---- row-decomposed runs: NCCL communicator inside the library -------------------------------------------------
     @staticmethod

@@ -9,6 +9,7 @@ Run in the build container (where /root/reference exists):
 The reference has no golden vectors of its own; these files pin the oracle restatement and
 the CUDA path to the reference's actual outputs and travel to the GPU box, where /root/reference does not exist.
 """
+import ctypes
 import os
 import sys
 
@@ -400,6 +401,35 @@ def gen_fz_loop():
     print("fz408l_loop: N=%d, %d iterations, %d pump sweeps, c0=%d, %d spin-up, VAF %s" % (n, r["iters"], k, r["c0"], r["nspin"], r["vaf"]))
 
 
+def gen_md_program():
+    """The MD program's recording, instantaneous-anisotropy and laser-force stages (main() stages 5, 7, 8; MD:1090-1165) run by
+    the reference's own functions in its own order through ref_md_run_stages, with run-time step counts (40, 30, 20, 20 instead of
+    the compile-time 2500, 2500, 1012, 2000), from init() with std::mt19937 seeded 4321 (lattice + Maxwellian; no Monte-Carlo, no
+    collisions: fully deterministic). The files its recorders write are the fixture of `mdqt_run --program md`."""
+    import gzip
+    import shutil
+    import tempfile
+    md = po.RefMD()
+    md.seed(4321)
+    md.init()
+    d = tempfile.mkdtemp() + "/"
+    md.lib.ref_md_run_stages.argtypes = [ctypes.c_char_p] + [ctypes.c_int] * 4
+    md.lib.ref_md_run_stages(d.encode(), 40, 30, 20, 20)
+    tags = np.zeros(md.N, dtype=np.uint8)
+    md.lib.ref_md_get_tags(tags.ctypes.data_as(ctypes.c_void_p))
+    out = os.path.join(OUT, "md_program")
+    os.makedirs(out, exist_ok=True)
+    files = sorted(os.listdir(d))
+    for f in files:
+        with open(os.path.join(d, f), "rb") as src, gzip.GzipFile(os.path.join(out, f + ".gz"), "wb", mtime=0) as dst:
+            shutil.copyfileobj(src, dst)
+    np.save(os.path.join(out, "tags.npy"), tags)
+    with open(os.path.join(out, "README"), "w") as f:
+        f.write("reference MD program stages 5, 7, 8 (MD:1090-1165) via oracle/ref_md_harness.cpp: ref_md_run_stages(40, 30, 20, 20), "
+                "mt19937 seed 4321, N = 4096; files written by the reference's own recorders (oracle/gen_golden.py: gen_md_program)\n")
+    print("md_program:", files, "tag counts", [(int((tags >> k) & 1).sum()) if False else int(((tags >> k) & 1).sum()) for k in range(4)])
+
+
 def seed_stream(ref, seed):
     """srand48(seed) inside the harness process (the reference's drand48 stream is then its own, un-injected)."""
     import ctypes
@@ -475,6 +505,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--ensemble" in sys.argv:
         gen_su_ensemble_stats()
+        sys.exit(0)
+    if "--mdprogram" in sys.argv:
+        gen_md_program()
         sys.exit(0)
     if "--coupled" in sys.argv:
         gen_su_coupled()

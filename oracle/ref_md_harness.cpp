@@ -64,6 +64,41 @@ int ref_md_pair_correlation(const char* scratch, double* r_out, double* g_out, i
   fclose(f);
   return k;
 }
+// main()'s stages 5, 7 and 8 (MD:1090-1165) with run-time step counts (the reference's are compile-time constants), every
+// call the reference's own function in the reference's order, files written by its own recorders into `dir` (trailing '/'):
+//   stage 5: collisionFreq = 0; tagParticles(); k < nrec: recordTaggedParticleMoments(k); k % 100 == 0 -> recordPairPairCorr(k);
+//            recordTemperature(); MDStep(k); recordVelsForAutocorrelations(k)
+//   stage 7: anisotropizeVelocities(); k < ninst: recordTempForEachAxis(Instantaneous, k); MDStep(k)   (its cout prints muted)
+//   stage 8: addLaserForce = 1; k < nest: recordTempForEachAxis(DuringForcePeriod, k); MDStep(k);
+//            addLaserForce = 0; k < nrelax: recordTempForEachAxis(AfterForcePeriod, k); MDStep(k)
+void ref_md_run_stages(const char* dir, int nrec, int ninst, int nest, int nrelax) {
+  ::mkdir(dir, 0777);
+  strcpy(saveDirectory, dir);
+  collisionFreq = 0;
+  tagParticles();
+  for (int k = 0; k < nrec; k++) {
+    recordTaggedParticleMoments(k);
+    if (k % 100 == 0) recordPairPairCorr(k);
+    recordTemperature();
+    MDStep(k);
+    recordVelsForAutocorrelations(k);
+  }
+  std::streambuf* old = std::cout.rdbuf(nullptr);  // anisotropizeVelocities() prints every velocity twice
+  anisotropizeVelocities();
+  std::cout.rdbuf(old);
+  char fileName[256];
+  strcpy(fileName, saveDirectory); strcat(fileName, "TemperaturesAlongAxesInstantaneous.dat");
+  for (int k = 0; k < ninst; k++) { recordTempForEachAxis(fileName, k); MDStep(k); }
+  addLaserForce = 1; collisionFreq = 0;
+  strcpy(fileName, saveDirectory); strcat(fileName, "TemperaturesAlongAxesDuringForcePeriod.dat");
+  for (int k = 0; k < nest; k++) { recordTempForEachAxis(fileName, k); MDStep(k); }
+  addLaserForce = 0;
+  strcpy(fileName, saveDirectory); strcat(fileName, "TemperaturesAlongAxesAfterForcePeriod.dat");
+  for (int k = 0; k < nrelax; k++) { recordTempForEachAxis(fileName, k); MDStep(k); }
+}
+void ref_md_get_tags(unsigned char* out) {
+  for (int i = 0; i < N; i++) out[i] = (taggedOne[i] ? 1 : 0) | (taggedTwo[i] ? 2 : 0) | (taggedThree[i] ? 4 : 0) | (taggedFour[i] ? 8 : 0);
+}
 int ref_md_autocorr_steps() { return numVelAutoCorrsSteps; }
 double ref_md_pair_step() { return pairPairStep; }
 double ref_md_pair_max() { return pairPairMax; }

@@ -107,5 +107,12 @@ def test_mdqt_run_row_decomposed_writes_the_single_gpu_files(tmp_path):
         assert r.returncode == 0, r.stderr
         dg = hostio.dirname(sg, N0=1200, job=4)
         assert sorted(os.listdir(dg)) == files
-        match, mismatch, err = filecmp.cmpfiles(d1, dg, files, shallow=False)
+        # per-ion files (restart files, populations): byte-identical. energies.dat and the velocity distributions are sums over the
+        # ranks' partial sums (a different order than the one-GPU reduction): equal to the printed precision up to its last digit
+        exact = [f for f in files if not (f == "energies.dat" or f.startswith("vel_dist"))]
+        match, mismatch, err = filecmp.cmpfiles(d1, dg, exact, shallow=False)
         assert not mismatch and not err, (G, mismatch[:4], err[:4])
+        for f in files:
+            if f not in exact:
+                a, b = np.loadtxt(os.path.join(d1, f), ndmin=2), np.loadtxt(os.path.join(dg, f), ndmin=2)
+                assert a.shape == b.shape and np.allclose(a, b, rtol=3e-6, atol=1e-300), f

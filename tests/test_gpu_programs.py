@@ -1,0 +1,119 @@
+"""GPU suite: the C++ host loops of the reference's other programs (`mdqt_run --program md|fz408l`, csrc/mdqt_programs.cpp) and
+the files they write, against files written by the reference's own recorders (tests/golden/md_program) and against the
+golden-tested Python loop on the same engine (FZ408L)."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from mdqtplasmasims_b200 import Engine, SCHEME_NONE, SCHEME_SR7, drivers, hostio, md_params, su_params
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "mdqtplasmasims_b200", "mdqt_run")
+
+
+def _table(text):
+    return np.array([[float(x) for x in line.split()] for line in text.strip().splitlines()])
+
+
+def test_md_program_files_match_the_reference_recorders(tmp_path, golden_dir):
+    """`mdqt_run --program md` with the fixture's step counts (no collisional stages: deterministic) and std::mt19937 seed:
+    same lattice + Maxwellian init(), same velocity-dependent tags, then taggedV*Moments.dat, temperature.dat, g(r) and the three
+    TemperaturesAlongAxes files as the reference's recordTaggedParticleMoments / recordTemperature / recordPairPairCorr /
+    recordTempForEachAxis wrote them (MD:525-582, 584-652, 923-1029)."""
+    gdir = os.path.join(golden_dir, "md_program")
+    save = str(tmp_path) + "/"
+    r = subprocess.run([DRIVER, "--program", "md", "1", "--seed", "4321", "--preSteps", "0", "--recordSteps", "40", "--instSteps", "30",
+                        "--reequilSteps", "0", "--establishSteps", "20", "--relaxSteps", "20", "--saveDirectory", save, "--quiet"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    d = os.path.join(save, "Gamma300Kappa50NumIons4096", "job1")
+    gold = {f[:-3]: gzip.open(os.path.join(gdir, f), "rt").read() for f in os.listdir(gdir) if f.endswith(".gz")}
+    assert len(gold) >= 9
+    for f, g in gold.items():
+        path = os.path.join(d, f)
+        assert os.path.exists(path), f
+        a, b = _table(open(path).read()), _table(g)
+        assert a.shape == b.shape, f
+        lo, lg = open(path).read().strip().splitlines(), g.strip().splitlines()
+        same = sum(x == y for x, y in zip(lo, lg))
+        if f.startswith("pairPairCorr"):
+            assert np.array_equal(a, b), f                       # integer pair counts, the reference's normalisation: exact text
+        elif f.startswith("tagged"):
+            # means over ~2000 tagged ions minus an O(1) equilibrium constant: cancellation leaves ~1e-13 absolute noise
+            assert np.allclose(a, b, rtol=2e-5, atol=2e-9) and same >= 0.85 * len(lg), (f, same, len(lg))
+        else:
+            assert np.allclose(a, b, rtol=2e-6, atol=1e-12) and same >= 0.95 * len(lg), (f, same, len(lg))
+    # the autocorrelation files exist with one row per recorded step (their values: test_gpu_schemes autocorrelation goldens)
+    for f in ("VAF.dat", "longViscAutoCorr.dat", "vCubeAutoCorr.dat", "vFourthAutoCorr.dat"):
+        assert _table(open(os.path.join(d, f)).read()).shape == (40, 2)
+
+
+def test_md_program_tags_and_moments_api(golden_dir):
+    """mdqt_set_tags / mdqt_moments_record against numpy on the fixture's tag sets."""
+    tags = np.load(os.path.join(golden_dir, "md_program", "tags.npy"))
+    n = tags.shape[0]
+    rng = np.random.default_rng(5)
+    V = rng.normal(size=(3, n)) * 0.6
+    e = Engine(md_params(scheme=SCHEME_NONE, n_ions=n))
+    e.upload(R=rng.uniform(0, e.params.L, size=(3, n)), V=V)
+    e.set_tags(tags)
+    e.moments_begin(3)
+    e.moments_record(1)
+    e.scale_velocities(1.1, 0.9, 0.8)
+    e.moments_record(2)
+    rec = e.moments_download(3)
+    assert np.all(rec[0] == 0)
+    for slot, W in ((1, V), (2, V * np.array([1.1, 0.9, 0.8])[:, None])):
+        assert np.allclose(rec[slot][:3], (W ** 2).sum(axis=1), rtol=1e-13)
+        for k in range(4):
+            m = ((tags >> k) & 1).astype(bool)
+            want = [m.sum()] + [(W[0][m] ** p).sum() for p in (1, 2, 3, 4)]
+            assert np.allclose(rec[slot][3 + 5 * k:8 + 5 * k], want, rtol=1e-12, atol=1e-12)
+    e.close()
+
+
+def test_fz408l_program_files_match_the_python_loop(tmp_path):
+    """`mdqt_run --program fz408l` against drivers.fz_main_loop (itself pinned to the reference's loop by
+    tests/golden/fz408l_loop.npz) on the same engine calls: same spin-up list, same VAF.dat rows, same final positions."""
+    save = str(tmp_path) + "/"
+    args = dict(N0=700, seed=99, tstartV0=0.0061, tpumpreal=2e-9, tmax=0.0201, sampleFreq=5)
+    r = subprocess.run([DRIVER, "--program", "fz408l", "2", "--N0", "700", "--seed", "99", "--tstartV0", "0.0061", "--tpumpreal", "2e-9",
+                        "--tmax", "0.0201", "--sampleFreq", "5", "--saveDirectory", save, "--quiet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    sub = [x for x in os.listdir(save)][0]
+    d = os.path.join(save, sub, "job2")
+    files = os.listdir(d)
+    c0 = int([f for f in files if f.startswith("ions_")][0][len("ions_timestep"):-4])
+    # the same run through the Python loop
+    st = hostio.init_su(99, N0=700)
+    n = st["N"]
+    p = su_params(Ge=0.1, density=2.0, detuning=-2.5, detuningDP=0.0, Om=0.7, OmDP=0.0, N0=700, n_ions=n, scheme=SCHEME_SR7, traj0=2, seed=99)
+    p.substeps_per_md = int(round(34.81 / np.sqrt(2.0)))
+    p.dtq = 0.002 / p.substeps_per_md
+    e = Engine(p)
+    psi = np.zeros((n, 7, 2))
+    psi[:, :2] = st["psi"][:, :2]
+    e.upload(R=st["R"], V=st["V"], psi=psi, t=0.0, substep=0)
+    tend = 0.0061 + 2e-9 * 813490 * np.sqrt(2.0)
+    events = []
+    out = drivers.fz_main_loop(e, 0.0201, 0.0061, tend, sampleFreq=5, on_measure=lambda t, tg, nu, v: events.append((t, v)),
+                               on_sample=lambda t, c, v: events.append((t, v)))
+    assert out["c0"] == c0
+    spin = np.loadtxt(os.path.join(d, "spinUpIonsList_timestep%06d.dat" % c0), dtype=int)
+    assert np.array_equal(spin, out["tagged"])
+    vaf = _table(open(os.path.join(d, "VAF.dat")).read())
+    assert vaf.shape == (len(events), 2)
+    assert np.allclose(vaf, np.array(events), rtol=2e-6, atol=1e-300)
+    s = e.download()
+    cond = _table(open(os.path.join(d, "conditions_timestep%06d.dat" % c0)).read())
+    assert np.allclose(cond[:, :3], s["R"].T, rtol=2e-6) and np.allclose(cond[:, 3:6], s["V"].T, rtol=2e-6, atol=1e-12)
+    en = _table(open(os.path.join(d, "energies.dat")).read())
+    assert en.shape == (len(events), 6) and np.all(np.abs(en[:, 5]) < 1e-3)   # energy conserved from the frozen start
+    tm = _table(open(os.path.join(d, "taggedMoments.dat")).read())
+    assert tm.shape == (len(events), 5)
+    assert any(f.startswith("vel_distX_timestep") for f in files)
+    e.close()
