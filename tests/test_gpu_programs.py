@@ -107,10 +107,10 @@ def test_fz408l_program_files_match_the_python_loop(tmp_path):
     assert np.array_equal(spin, out["tagged"])
     vaf = _table(open(os.path.join(d, "VAF.dat")).read())
     assert vaf.shape == (len(events), 2)
-    assert np.allclose(vaf, np.array(events), rtol=2e-6, atol=1e-300)
+    assert np.allclose(vaf, np.array(events), rtol=6e-6, atol=1e-300)
     s = e.download()
     cond = _table(open(os.path.join(d, "conditions_timestep%06d.dat" % c0)).read())
-    assert np.allclose(cond[:, :3], s["R"].T, rtol=2e-6) and np.allclose(cond[:, 3:6], s["V"].T, rtol=2e-6, atol=1e-12)
+    assert np.allclose(cond[:, :3], s["R"].T, rtol=6e-6) and np.allclose(cond[:, 3:6], s["V"].T, rtol=6e-6, atol=1e-12)  # %lg: 6 digits
     en = _table(open(os.path.join(d, "energies.dat")).read())
     assert en.shape == (len(events), 6) and np.all(np.abs(en[:, 5]) < 1e-3)   # energy conserved from the frozen start
     tm = _table(open(os.path.join(d, "taggedMoments.dat")).read())
