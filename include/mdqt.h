@@ -199,7 +199,9 @@ int mdqt_set_forced_collisions(mdqt_handle* h, const double* u, const double* v)
 int mdqt_philox_uniforms(uint64_t seed, uint32_t traj, uint32_t ion, uint64_t substep, double u[5]);
 
 /* Multi-GPU plumbing (row decomposition): raw device pointers so that the caller's NCCL all-gather can write
- * remote rows of R in place. which: 0 = R, 1 = V, 2 = F. Layout on device: double [n_traj][3][mdqt_device_ld]. */
+ * remote rows of R in place. which: 0 = R, 1 = V, 2 = F. Layout on device: double [n_traj][3][mdqt_device_ld].
+ * The F pointer is valid until the next mdqt_vv_step(s) call only: MDStep() exchanges the A and oldA buffers (MD:505-506).
+ * (Row-decomposed runs no longer need this plumbing: see mdqt_comm_init.) */
 void* mdqt_device_ptr(mdqt_handle* h, int which);
 int mdqt_device_ld(mdqt_handle* h);
 void* mdqt_stream(mdqt_handle* h);

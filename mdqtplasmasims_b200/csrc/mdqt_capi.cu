@@ -138,10 +138,13 @@ static int plan_items_jlen(int np) {
 constexpr int kItemsMaxN = 8192;  // beyond this the partial-sum buffer (chunks x 3 x N) grows and CTA tiles win anyway
 
 static void plan_force(mdqt_handle* h) {
+  // developer knobs (kernel A/B runs) are honoured on whole-system handles only: the ranks of a row-decomposed run must take the
+  // same plan whatever their environments, or the rank-count-independent bits are gone
+  auto knob = [h](const char* name) -> const char* { return h->nrows == h->N ? getenv(name) : nullptr; };
   h->items = 0;
   {
     const int np = h->p.plan_n > 0 ? h->p.plan_n : h->N;
-    const char* e = getenv("MDQT_K1_ITEMS");  // developer knob (A/B runs): 0 = CTA-tile kernel everywhere
+    const char* e = knob("MDQT_K1_ITEMS");  // developer knob (A/B runs): 0 = CTA-tile kernel everywhere
     const bool off = e && e[0] == '0' && h->p.plan_n == 0;
     // the chunk length must cover every trajectory's ions in <= 64 chunks even when n_ions exceeds the nominal plan_n
     const long long total_items = (long long)h->B * ((h->nrows + 31) / 32) * ((h->N + 7) / 8);  // bound for any chunk length
@@ -186,7 +189,7 @@ static void plan_force(mdqt_handle* h) {
   // B200 (profiles/r01c_k1_trace.txt): time = (largest number of CTAs on one SM) x (warp-pairs per CTA) x ~81 issue
   // cycles / 4 sub-partitions + a plan-independent ~5.5 us; what separates plans is almost only the first term, i.e.
   // how evenly the CTA count divides over 148 SMs (measured launch times move in ~2 us steps).
-  if (h->ipt == 1 && !getenv("MDQT_FORCE_IPT") && !getenv("MDQT_FORCE_NSPLIT")) {
+  if (h->ipt == 1 && !knob("MDQT_FORCE_IPT") && !knob("MDQT_FORCE_NSPLIT")) {
     auto model = [&](long long ctas, int warps, double pairs_per_warp, int ns) {
       const double per_sm = (double)((ctas + 147) / 148);
       const double resident = std::min(per_sm * warps, 32.0);
@@ -209,18 +212,18 @@ static void plan_force(mdqt_handle* h) {
         if (t < best_t * 0.98) { best_t = t; h->rg = 32; h->jsub = js; h->nsplit = ns; h->jlen = jlen; h->ipt = 1; }
       }
   }
-  if (const char* e = getenv("MDQT_FORCE_RG")) {  // developer knob: MDQT_FORCE_RG=32 with MDQT_FORCE_JSUB=4|8 and MDQT_FORCE_NSPLIT
+  if (const char* e = knob("MDQT_FORCE_RG")) {  // developer knob: MDQT_FORCE_RG=32 with MDQT_FORCE_JSUB=4|8 and MDQT_FORCE_NSPLIT
     if (atoi(e) == 32) { h->rg = 32; h->ipt = 1; h->jsub = 8; }
     else h->rg = kForceThreads;
   }
-  if (const char* e = getenv("MDQT_FORCE_JSUB")) {
+  if (const char* e = knob("MDQT_FORCE_JSUB")) {
     int js = atoi(e);
     if (h->rg == 32) h->jsub = js == 4 ? 4 : 8;
-    else h->jsub = (js == 2 || (js == 4 && getenv("MDQT_FORCE_IPT") && atoi(getenv("MDQT_FORCE_IPT")) == 2)) ? js : 1;
+    else h->jsub = (js == 2 || (js == 4 && knob("MDQT_FORCE_IPT") && atoi(knob("MDQT_FORCE_IPT")) == 2)) ? js : 1;
   }
   // developer tuning knobs (kernel A/B runs): override the plan
-  if (const char* e = getenv("MDQT_FORCE_IPT")) h->ipt = (atoi(e) == 2 && h->rg != 32) ? 2 : 1;
-  if (const char* e = getenv("MDQT_FORCE_NSPLIT")) {
+  if (const char* e = knob("MDQT_FORCE_IPT")) h->ipt = (atoi(e) == 2 && h->rg != 32) ? 2 : 1;
+  if (const char* e = knob("MDQT_FORCE_NSPLIT")) {
     int ns = std::max(1, std::min(1024, atoi(e)));
     h->jlen = ((N + ns - 1) / ns + 7) & ~7;
     h->nsplit = (N + h->jlen - 1) / h->jlen;

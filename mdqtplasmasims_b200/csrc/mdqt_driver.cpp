@@ -26,6 +26,7 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <deque>
@@ -41,9 +42,10 @@
 // batch of 64. Writer threads do the formatting while the time loop keeps the GPU busy; a job's outputs always go to the
 // same writer, in call order, so its files are byte-for-byte what a synchronous writer produces.
 struct OutputJob {
+  int kind = 0;  // 0: energies.dat line (appended: a job's lines stay in call order on one writer), 1: vel_dist files, 2: populations file
   std::string dir;
-  unsigned counter; int N;
-  mdqt_diag d; double Epot0;
+  unsigned counter = 0; int N = 0;
+  mdqt_diag d; double Epot0 = 0;
   std::vector<double> pvel, pops, vx;  // vx = V[0][0..N): the only velocity row write_populations prints
 };
 class OutputWriter {
@@ -52,7 +54,7 @@ class OutputWriter {
   ~OutputWriter() { finish(); }
   void push(OutputJob&& j) {
     std::unique_lock<std::mutex> lk(m_);
-    cv_space_.wait(lk, [this] { return q_.size() < 16; });  // bounded: at most 16 outputs in flight per writer
+    cv_space_.wait(lk, [this] { return q_.size() < 48; });  // bounded: at most 48 pieces in flight per writer
     q_.push_back(std::move(j));
     cv_work_.notify_one();
   }
@@ -73,9 +75,9 @@ class OutputWriter {
         q_.pop_front();
         cv_space_.notify_one();
       }
-      mdqt_io_append_energies(j.dir.c_str(), j.d.t, j.d.ekin_x, j.d.ekin_y, j.d.ekin_z, j.d.epot, j.Epot0, j.d.vx_avg);
-      mdqt_io_write_vel_dist(j.dir.c_str(), j.counter, j.pvel.data(), j.d.vx_avg);
-      mdqt_io_write_populations(j.dir.c_str(), j.counter, j.N, j.vx.data(), j.pops.data());
+      if (j.kind == 0) mdqt_io_append_energies(j.dir.c_str(), j.d.t, j.d.ekin_x, j.d.ekin_y, j.d.ekin_z, j.d.epot, j.Epot0, j.d.vx_avg);
+      else if (j.kind == 1) mdqt_io_write_vel_dist(j.dir.c_str(), j.counter, j.pvel.data(), j.d.vx_avg);
+      else mdqt_io_write_populations(j.dir.c_str(), j.counter, j.N, j.vx.data(), j.pops.data());
     }
   }
   std::mutex m_;
@@ -84,6 +86,21 @@ class OutputWriter {
   bool done_ = false;
   std::thread th_;
 };
+typedef std::vector<std::unique_ptr<OutputWriter>> Writers;
+// one output() of one job = three independent pieces of text: the energies line goes to the job's own writer (order), the two bulky
+// files (3 x 2001 + N lines) to the writers in turn, so that even a single job's formatting is spread over several threads
+static std::atomic<unsigned> g_rr{0};
+static void push_output(Writers& w, unsigned job, OutputJob&& full) {
+  OutputJob a;
+  a.kind = 0; a.dir = full.dir; a.d = full.d; a.Epot0 = full.Epot0;
+  OutputJob b;
+  b.kind = 1; b.dir = full.dir; b.counter = full.counter; b.d = full.d; b.pvel = std::move(full.pvel);
+  OutputJob c;
+  c.kind = 2; c.dir = std::move(full.dir); c.counter = full.counter; c.N = full.N; c.vx = std::move(full.vx); c.pops = std::move(full.pops);
+  w[job % w.size()]->push(std::move(a));
+  w[g_rr.fetch_add(1) % w.size()]->push(std::move(b));
+  w[g_rr.fetch_add(1) % w.size()]->push(std::move(c));
+}
 
 struct Options {
   double Ge = 0.1, density = 2, sig0 = 4.0, Te = 19.0, fracOfSig = 0, detuning = -1, detuningDP = 1, Om = 1, OmDP = 1, tmax = 30;
@@ -196,7 +213,7 @@ static BatchResult run_batch(const Options& o, unsigned job0, int B, int device,
         job.pvel.assign(pvel.begin() + (size_t)b * 3 * 2001, pvel.begin() + (size_t)(b + 1) * 3 * 2001);
         job.pops.assign(pops.begin() + (size_t)b * Ncap * 3, pops.begin() + ((size_t)b * Ncap + Nb[b]) * 3);
         job.vx.assign(V.begin() + (size_t)b * 3 * ld, V.begin() + (size_t)b * 3 * ld + Nb[b]);
-        writers[(job0 + b) % writers.size()]->push(std::move(job));
+        push_output(writers, job0 + b, std::move(job));
         counter[b]++;
       }
       res.nout++;
@@ -333,7 +350,7 @@ static int run_rows(const Options& o, unsigned job, int G, std::vector<std::uniq
           OutputJob oj;
           oj.dir = dir; oj.counter = counter; oj.N = N; oj.d = d; oj.Epot0 = Epot0;
           oj.pvel = pv; oj.pops = pops; oj.vx.assign(V.begin(), V.begin() + N);
-          writers[0]->push(std::move(oj));
+          push_output(writers, job, std::move(oj));
           counter++;
         }
         bar.wait();
@@ -449,7 +466,7 @@ int main(int argc, char** argv) {
   if (array && gpus > ndev) gpus = ndev;
   const long njobs = job_b - job_a + 1;
   int nwriters = atoi(opt["writers"].c_str());
-  if (nwriters <= 0) nwriters = array ? (int)std::min<long>(std::max(1u, std::thread::hardware_concurrency()), std::min<long>(njobs, 32)) : 1;
+  if (nwriters <= 0) nwriters = (int)std::min<long>(std::max(1u, std::thread::hardware_concurrency()), array ? std::min<long>(3 * njobs, 48) : 4);
   std::vector<std::unique_ptr<OutputWriter>> writers;
   for (int w = 0; w < nwriters; w++) writers.emplace_back(new OutputWriter());
 

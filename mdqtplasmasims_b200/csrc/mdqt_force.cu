@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
 
 namespace mdqt {
 
@@ -628,11 +629,15 @@ static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
   if (EPOT) kern = hl ? k_pairs_items<1, EPOT, true> : k_pairs_items<1, EPOT, false>;
   else if (ipt == 2) kern = hl ? k_pairs_items<2, false, true> : k_pairs_items<2, false, false>;
   else kern = hl ? k_pairs_items<1, false, true> : k_pairs_items<1, false, false>;
-  static bool attr_done[2][3][2];
-  if (!attr_done[EPOT][ipt][hl]) {
+  // function attributes are per DEVICE (one process may drive several GPUs from several threads: mdqt_run --gpus): set them once
+  // on every device this instantiation is launched on
+  static std::atomic<bool> attr_done[64][2][3][2];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 64 || !attr_done[dev][EPOT][ipt][hl].load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kItemWarps * 2 * (24 * (size_t)kItemMaxJ + 24 * 64)));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // room for two CTAs per SM
-    attr_done[EPOT][ipt][hl] = true;
+    if (dev < 64) attr_done[dev][EPOT][ipt][hl].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kItemWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;

@@ -31,3 +31,23 @@ cnt = np.bincount(sm, minlength=148)
 print("warps per SM: min %d max %d ; SMs used %d" % (cnt[cnt > 0].min(), cnt.max(), (cnt > 0).sum()))
 per_sm_end = np.array([rel[sm == k, 3].max() if (sm == k).any() else 0 for k in range(148)])
 print("per-SM last loop end us: min %.2f med %.2f max %.2f" % (per_sm_end[per_sm_end > 0].min(), np.median(per_sm_end[per_sm_end > 0]), per_sm_end.max()))
+# structure of the unfairness: mean pair-loop time by warp index within the CTA and by CTA residency order on its SM
+w_idx = np.arange(len(tr)) % 8            # trace slot = blockIdx.x * 8 + warp
+cta = np.arange(len(tr)) // 8
+dur = rel[:, 3] - rel[:, 2]
+print("pair loop us by warp index:", " ".join("%.1f" % dur[(w_idx == k) & busy].mean() for k in range(8)))
+print("loop END us by warp index :", " ".join("%.1f" % rel[(w_idx == k) & busy, 3].mean() for k in range(8)))
+first = np.zeros(len(tr), dtype=bool)
+for s_ in range(148):
+    ids = np.unique(cta[sm == s_])
+    if len(ids) >= 1:
+        first[cta == ids.min()] = True
+print("pair loop us: lower-index CTA on its SM %.2f, the other %.2f" % (dur[first & busy].mean(), dur[~first & busy].mean()))
+for k in range(4):
+    sel = busy & ((w_idx % 4) == k)
+    print("scheduler slot %d (warps %d, %d): loop end us mean %.2f max %.2f" % (k, k, k + 4, rel[sel, 3].mean(), rel[sel, 3].max()))
+# one SM in detail
+s0 = int(np.argmax(per_sm_end))
+print("SM %d: (cta, warp, loop start, loop end)" % s0)
+for i in np.where(sm == s0)[0]:
+    print("   cta %4d warp %d  %.2f -> %.2f" % (cta[i], w_idx[i], rel[i, 2], rel[i, 3]))

@@ -74,7 +74,7 @@ def test_forces_vs_oracle_small_and_ragged(oracle, n, kappa_ge):
 
 
 def test_forces_unwrapped_positions_general_image(oracle):
-    """Coordinates outside [0,L] (several box lengths away) take the general rint() minimum-image path."""
+    """Coordinates outside [0,L] (several box lengths away): the periodic fixed-point difference is the minimum image for any input."""
     n = 500
     p = su_params(N0=n, n_ions=n)
     rng = np.random.default_rng(3)
