@@ -125,7 +125,7 @@ static int plan_items_jlen(int np) {
   const long long G = (np + 31) / 32;
   double best = 1e300;
   int best_jl = 8;
-  for (int jl = 8; jl <= 256; jl += 8) {
+  for (int jl = 8; jl <= 256; jl += 8) {  // kItemMaxJ
     const long long nch = (np + jl - 1) / jl;
     const long long rounds = (G * nch + W - 1) / W;
     // per item: jl pair iterations + ~14 iterations' worth of tile wait, partial store, fence and arrival; the last warp of
@@ -227,6 +227,20 @@ static void plan_force(mdqt_handle* h) {
     int ns = std::max(1, std::min(1024, atoi(e)));
     h->jlen = ((N + ns - 1) / ns + 7) & ~7;
     h->nsplit = (N + h->jlen - 1) / h->jlen;
+  }
+  // Row-decomposed handle: rows per thread do not enter the summation order (only the j chunking does), so each rank may choose
+  // them for ITS row count -- the split that wastes less of the last CTA wave (592 CTA slots of 128 threads). N = 2e5 on 8 ranks:
+  // 98 tiles x 15 chunks = 2.48 waves with two rows per thread, 4.97 waves with one.
+  if (h->nrows != h->N && h->rg == kForceThreads && h->jsub == 1) {
+    double best = 1e300;
+    int best_ipt = h->ipt;
+    for (int ipt = 1; ipt <= 2; ipt++) {
+      const double ctas = (double)((h->nrows + kForceThreads * ipt - 1) / (kForceThreads * ipt)) * h->nsplit * h->B;
+      const double waves = ctas / (148.0 * 4);
+      const double cost = ceil(waves) / waves * (ipt == 2 ? 0.97 : 1.0);
+      if (cost < best) { best = cost; best_ipt = ipt; }
+    }
+    h->ipt = best_ipt;
   }
   h->itiles = (h->nrows + 31) / 32;  // upper bound on i-tiles of this handle (32-row groups)
 }

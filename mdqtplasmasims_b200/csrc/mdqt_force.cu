@@ -49,10 +49,12 @@ static_assert(kExpTable == 128 || kExpTable == 1024, "exp table must have 128 or
 __device__ double c_exp2tab[kExpTable];  // global (L2-resident), not __constant__: the CTA prologue reads it with a per-thread index
 
 bool pdl_enabled() {
-  // Programmatic dependent launch between the force and substep kernels (MDQT_PDL=0 turns it off). With the round-1 CTA-tile
-  // force kernel it was SLOWER (waiting grids crowded the SMs); with the persistent item kernel, whose CTAs leave an SM only
-  // when its work is done, the dependent's launch latency and prologue hide behind the tail: 54.4 -> 53.5 us per MD step.
-  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return !(e && e[0] == '0'); }();
+  // Programmatic dependent launch between the force and substep kernels: opt-in (MDQT_PDL=1). With the persistent item kernel it
+  // hides the dependent's launch latency and prologue behind the tail when all warps finish together (N = 3500: 54.4 -> 53.5 us per
+  // MD step) -- but whenever the force kernel's warps finish at different times (N = 3653 planned for 3500: two item rounds) the
+  // dependent's CTAs pile onto the SMs that free up first and the substep kernel runs unbalanced: 79.9 instead of 67.6 us. With the
+  // round-1 CTA-tile kernel it was slower everywhere (114 vs 74 us).
+  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();
   return on;
 }
 
@@ -105,7 +107,7 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
 }
 
 // From r2 (in units u^2): rinv = 1/r, ef = exp(-kappa r), valid = 0 < r2 < rcut^2.
-template <bool HL>
+template <bool HL, bool TAB32 = false>
 __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const double* tab, double& rinv, double& ef,
                                           bool& valid) {
   if (HL) valid = (unsigned)(__double2hiint(r2) - 1) < 0x47D00000u - 1u;  // 0 < r2 < 2^126 on the high word alone
@@ -138,7 +140,15 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
   }
   q = fma(q, rr, c.c1);
   q = fma(q, rr, 1.0);
-  double T = tab[n & (kExpTable - 1)];
+  double T;
+  if (TAB32) {
+    // the item kernel keeps the table 8 KB-aligned in shared memory and passes its 32-bit shared address: base | offset is ONE
+    // three-input logic instruction (inside its per-warp item loop the compiler keeps the base in a vector register and would add it)
+    const unsigned addr = (((unsigned)n << 3) & ((kExpTable - 1) << 3)) | (unsigned)(size_t)tab;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(addr));
+  } else {
+    T = tab[n & (kExpTable - 1)];
+  }
   int hi = __double2hiint(T) + (n << kExpShift);  // table high words carry -(idx << kExpShift): net += floor(n/T) << 20
   ef = __hiloint2double(hi, __double2loint(T)) * q;
   rinv = y;
@@ -440,8 +450,14 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 // the batch size, of the rows per lane, of the trajectory's position in the batch, or of the number of row-owning ranks:
 // a job gives the same bits alone or batched. Trajectories of an ensemble may hold different ion counts nb[b] (SU:299-337).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kItemWarps = 8;
-constexpr int kItemCtasPerSM = 2;
+// MDQT_TAB32 1: 8 KB-aligned table addressed as base | offset in one logic instruction (saves the base add the compiler emits inside
+// the per-warp item loop: 44.6 -> 43.6 instructions per pair) -- measured on B200: no gain (28.98 vs 28.66 us at N = 3500), so off
+#ifndef MDQT_TAB32
+#define MDQT_TAB32 0
+#endif
+// 16 resident warps per SM either way: two CTAs of 8 warps, or -- for batches (two rows per lane), where it is 4 % faster
+// (5.08e11 vs 4.88e11 pairs/s at 64 x 3500) -- one CTA of 16; the bits do not depend on it
+constexpr int kItemResidentWarps = 16;
 constexpr int kItemMaxB = 512;   // per-trajectory ion counts cached in shared memory up to this batch size
 constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps = 120 KB per CTA at most
 
@@ -453,7 +469,7 @@ struct Item { int b, g, ch, Nb; };
 #ifdef MDQT_K1_TRACE  // developer build: per-WARP phase time stamps of the item kernel (scripts/k1_items_trace.py)
 #define WTRACE(slot)                                                                                             \
   if (lane == 0) {                                                                                               \
-    const int w_ = blockIdx.x * kItemWarps + warp;                                                               \
+    const int w_ = blockIdx.x * NW + warp;                                                               \
     if (w_ < 8192) {                                                                                             \
       long long gt_;                                                                                             \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                                    \
@@ -465,10 +481,10 @@ struct Item { int b, g, ch, Nb; };
 #define WTRACE(slot)
 #endif
 
-template <int IPT, bool EPOT, bool HL>
-__global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
+template <int NW, int IPT, bool EPOT, bool HL>
+__global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double stab[kExpTable];
+  __shared__ __align__(8192) double stab_mem[kExpTable];  // 8 KB-aligned: see pair_core<.., TAB32>
   __shared__ int snb[kItemMaxB];  // the trajectories' ion counts: read at every item decode, so not from L2
   constexpr int RPG = 32 * IPT;  // rows per group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -477,17 +493,18 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
   const unsigned bufbytes = 24u * (unsigned)tj + 24u * RPG;
   unsigned char* wbase = smem_raw + (size_t)warp * (2 * (size_t)bufbytes);
   const PairConsts c = make_consts(a, EPOT);
+  const double* const stab = MDQT_TAB32 ? reinterpret_cast<const double*>((size_t)(unsigned)__cvta_generic_to_shared(stab_mem)) : stab_mem;
   if (tid == 0) stamp_time(a.stamp, 0);
   WTRACE(0)
-  for (int k = tid; k < kExpTable; k += kItemWarps * 32) cp_async8(&stab[k], &c_exp2tab[k]);
+  for (int k = tid; k < kExpTable; k += NW * 32) cp_async8(&stab_mem[k], &c_exp2tab[k]);
   const bool nb_smem = a.nb && a.B <= kItemMaxB;
-  if (nb_smem) for (int k = tid; k < a.B; k += kItemWarps * 32) snb[k] = a.nb[k];  // constant for the handle's lifetime
+  if (nb_smem) for (int k = tid; k < a.B; k += NW * 32) snb[k] = a.nb[k];  // constant for the handle's lifetime
   __syncthreads();
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
   if (!EPOT && tid == 0 && blockIdx.x == 0) advance_clock(a);
 
   const int gcap = (a.nrows + RPG - 1) / RPG;
-  const int W = gridDim.x * kItemWarps;
+  const int W = gridDim.x * NW;
   const int total = a.B * gcap * a.nsplit;
   const int rowend_cap = a.row0 + a.nrows;
   const unsigned long long mg_g = (IPT == 2) ? a.mg_gcap2 : a.mg_gcap;
@@ -567,7 +584,7 @@ __global__ void __launch_bounds__(kItemWarps * 32, kItemCtasPerSM) k_pairs_items
         const double r2 = EPOT ? fma(dx, dx, fma(dy, dy, dz * dz)) : fma(dx, dx, fma(dy, dy, fma(dz, dz, 1.0)));  // see k_pairs
         double rinv, ef;
         bool valid;
-        pair_core<HL>(r2, c, stab, rinv, ef, valid);
+        pair_core<HL, MDQT_TAB32 != 0>(r2, c, stab, rinv, ef, valid);
         if (EPOT) {
           const double u = ef * rinv;
           ax[r] += valid ? u : 0.0;
@@ -615,37 +632,44 @@ static int items_ipt(const ForceArgs& a) {
   static const int force = [] { const char* e = getenv("MDQT_ITEMS_IPT"); return e ? atoi(e) : 0; }();
   if (force == 1 || force == 2) return force;
   const long long items1 = (long long)a.B * ((a.nrows + 31) / 32) * a.nsplit;
-  return items1 >= 4LL * 148 * kItemCtasPerSM * kItemWarps ? 2 : 1;
+  return items1 >= 4LL * 148 * kItemResidentWarps ? 2 : 1;
 }
 
-template <bool EPOT>
-static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
-  const int ipt = EPOT ? 1 : items_ipt(a);  // the potential energy is a diagnostic: one instantiation
-  const size_t smem = (size_t)kItemWarps * 2 * (24 * (size_t)a.jlen + 24 * 32 * ipt);
-  const long long total = (long long)a.B * ((a.nrows + 32 * ipt - 1) / (32 * ipt)) * a.nsplit;
-  const int grid = (int)std::min<long long>(148LL * kItemCtasPerSM, (total + kItemWarps - 1) / kItemWarps);
+template <int NW, int IPT, bool EPOT>
+static void launch_items_nw(const ForceArgs& a, double* partials, cudaStream_t s) {
+  const size_t smem = (size_t)NW * 2 * (24 * (size_t)a.jlen + 24 * 32 * IPT);
+  const long long total = (long long)a.B * ((a.nrows + 32 * IPT - 1) / (32 * IPT)) * a.nsplit;
+  const int grid = (int)std::min<long long>(148LL * (kItemResidentWarps / NW), (total + NW - 1) / NW);
   const bool hl = a.half_l && MDQT_VALID_INT;
-  void (*kern)(ForceArgs, double*);
-  if (EPOT) kern = hl ? k_pairs_items<1, EPOT, true> : k_pairs_items<1, EPOT, false>;
-  else if (ipt == 2) kern = hl ? k_pairs_items<2, false, true> : k_pairs_items<2, false, false>;
-  else kern = hl ? k_pairs_items<1, false, true> : k_pairs_items<1, false, false>;
+  void (*kern)(ForceArgs, double*) = hl ? k_pairs_items<NW, IPT, EPOT, true> : k_pairs_items<NW, IPT, EPOT, false>;
   // function attributes are per DEVICE (one process may drive several GPUs from several threads: mdqt_run --gpus): set them once
   // on every device this instantiation is launched on
-  static std::atomic<bool> attr_done[64][2][3][2];
+  static std::atomic<bool> attr_done[64][2];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 64 || !attr_done[dev][EPOT][ipt][hl].load(std::memory_order_acquire)) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kItemWarps * 2 * (24 * (size_t)kItemMaxJ + 24 * 64)));
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // room for two CTAs per SM
-    if (dev < 64) attr_done[dev][EPOT][ipt][hl].store(true, std::memory_order_release);
+  if (dev >= 64 || !attr_done[dev][hl].load(std::memory_order_acquire)) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)std::min<size_t>((size_t)NW * 2 * (24 * (size_t)kItemMaxJ + 24 * 32 * IPT), (size_t)(227 - 12) * 1024));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);  // room for all resident CTAs
+    if (dev < 64) attr_done[dev][hl].store(true, std::memory_order_release);
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kItemWarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   int n = 0;
   if (!EPOT && pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; n++; }
   cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, a, partials);
+}
+
+template <bool EPOT>
+static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
+  const int ipt = EPOT ? 1 : items_ipt(a);  // the potential energy is a diagnostic: one instantiation
+  if (EPOT) { launch_items_nw<8, 1, EPOT>(a, partials, s); return; }
+  if (ipt == 1) { launch_items_nw<8, 1, false>(a, partials, s); return; }
+  // two rows per lane (batches): one 16-warp CTA per SM when its tiles fit (chunks of up to 192 positions), else two of 8
+  if ((size_t)16 * 2 * (24 * (size_t)a.jlen + 24 * 64) + 12 * 1024 <= (size_t)227 * 1024) launch_items_nw<16, 2, false>(a, partials, s);
+  else launch_items_nw<8, 2, false>(a, partials, s);
 }
 
 // F[b][comp][row] = sum of the row's partials in ascending chunk order: the one formula every consumer of item-kernel

@@ -51,6 +51,10 @@ e = Engine(su_params(n_ions=256, N0=256))
 print("fp64 peak TFLOP/s:", e.fp64_peak_tflops(), flush=True)
 e.close()
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "k1ab":
+    run("items", 3500)
+    run("items", 3653, plan_n=3500)
+    run("items", 3500, B=64, nmd=4)
 if which in ("all", "small"):
     run("items, auto lanes", 3500)
     run("items, plan_n (2 lanes)", 3500, plan_n=3500)
