@@ -794,246 +794,6 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
 }
 
 
-// ------------------------------------------------------------------------------------------------------------
-// K2, EIGHT lanes per ion (12-level scheme, one small trajectory). The four-lane kernel leaves a quarter of the chip's
-// warp schedulers idle at N ~ 3500 (438 warps on 592 schedulers) and each busy one executes ~370 FP64 instructions per
-// substep in order. Here every lane of the four-lane mapping is split once more into the REAL and the IMAGINARY parts of its
-// three amplitudes: lane (blk, half, part) holds a_k = Re w_k or Im w_k, k = 0..2. With sigma = +1 (re) / -1 (im) and b_k
-// the other part of the same amplitudes (one shuffle with the neighbour lane), the rows of m = w - i h H w read
-//   m0 = a0 - g0 a0 + A01i a1 + sigma (E0 b0 + A01r b1 + a02 b2 + b00 rb0)
-//   m1 = a1 - g1 a1 + A10i a0 + sigma (E1 b1 + A10r b0 + a12 b2 + b11 rb1)
-//   m2 = a2                   + sigma (E2 b2 + a21 b1 + a20 b0)
-// (rb0, rb1 = the other part of the partner half's w0, w1: lane ^ 3), 17 FMAs per lane and stage instead of 36; all lanes
-// run one instruction stream with per-lane (sigma-scaled) coefficients. P populations are formed as fma(re, re, im * im) in both
-// part lanes (identical bits), so all eight lanes of an ion agree on dp, on the renormalisation prefactor and on the jump.
-// 876 warps at N = 3500: every scheduler has one or two. Same physics, uniforms and jump logic as the other mappings; sums that
-// cross lanes are formed in a different fixed order, so results agree to rounding.
-// ------------------------------------------------------------------------------------------------------------
-struct Lane8H {
-  double g0, g1;                          // h Gamma/2 on rows 0, 1
-  double sE0, sE1, sE2;                   // sigma h E (per substep)
-  double a01i, a10i, sa01r, sa10r;        // rotating coupling (per substep on half 1), real part sigma-scaled
-  double sa02, sb00, sa12, sb11, sa21, sa20;
-  double G0, G1;                          // h Gamma weights of |w0|^2, |w1|^2 in dp
-};
-
-__device__ __forceinline__ void stage8(const Lane8H& H, bool im, const double* a, double* g) {
-  const double b0 = __shfl_xor_sync(0xffffffffu, a[0], 1), b1 = __shfl_xor_sync(0xffffffffu, a[1], 1), b2 = __shfl_xor_sync(0xffffffffu, a[2], 1);
-  const double rb0 = __shfl_xor_sync(0xffffffffu, a[0], 3), rb1 = __shfl_xor_sync(0xffffffffu, a[1], 3);
-  // |w0|^2, |w1|^2 as fma(re, re, im * im) in both part lanes
-  const double x0 = im ? b0 : a[0], y0 = im ? a[0] : b0, x1 = im ? b1 : a[1], y1 = im ? a[1] : b1;
-  double own = fma(H.G0, fma(x0, x0, y0 * y0), H.G1 * fma(x1, x1, y1 * y1));
-  own += __shfl_xor_sync(0xffffffffu, own, 2);
-  own += __shfl_xor_sync(0xffffffffu, own, 4);
-  const double pref = rsqrt_near1(1.0 - own);
-  double m0 = fma(-H.g0, a[0], a[0]);
-  m0 = fma(H.a01i, a[1], m0);
-  m0 = fma(H.sE0, b0, m0); m0 = fma(H.sa01r, b1, m0); m0 = fma(H.sa02, b2, m0); m0 = fma(H.sb00, rb0, m0);
-  double m1 = fma(-H.g1, a[1], a[1]);
-  m1 = fma(H.a10i, a[0], m1);
-  m1 = fma(H.sE1, b1, m1); m1 = fma(H.sa10r, b0, m1); m1 = fma(H.sa12, b2, m1); m1 = fma(H.sb11, rb1, m1);
-  double m2 = fma(H.sE2, b2, a[2]);
-  m2 = fma(H.sa21, b1, m2); m2 = fma(H.sa20, b0, m2);
-  g[0] = fma(pref, m0, -a[0]); g[1] = fma(pref, m1, -a[1]); g[2] = fma(pref, m2, -a[2]);
-}
-
-template <bool FORCED>
-__global__ void __launch_bounds__(128) k_substeps8(QTArgs a, QTConsts C) {
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int o = gid & 7, part = o & 1, half = (o >> 1) & 1, blk = o >> 2;
-  const bool im = part != 0;
-  const long long slot = gid >> 3;
-  const bool inrange = slot < (long long)a.nrows * a.B;
-  const int b = inrange ? (int)(slot / a.nrows) : 0;
-  const int i0 = inrange ? a.row0 + (int)(slot % a.nrows) : a.row0;
-  const bool active = inrange && i0 < (a.nb ? a.nb[b] : a.N);
-  const int i = active ? i0 : a.row0;
-  const uint64_t seed = a.seeds ? a.seeds[b] : a.seed;
-
-  double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
-  double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
-  double* __restrict__ Pb = a.psi + (size_t)b * 24 * a.ld;
-
-  const QTLane& LA = C.lane[0];
-  const QTLane& LB = C.lane[1];
-#define LSEL(f) (blk ? LB.f : LA.f)
-  int map[3];
-  map[0] = half ? LSEL(map[2]) : LSEL(map[0]);
-  map[1] = half ? LSEL(map[4]) : LSEL(map[1]);
-  map[2] = half ? LSEL(map[5]) : LSEL(map[3]);
-  const double h = C.h, sg = im ? -1.0 : 1.0;
-  const double hc10 = h * LSEL(c10), hc20 = h * LSEL(c20), hc13 = h * LSEL(c13), hc14 = h * LSEL(c14), hc25 = h * LSEL(c25);
-  const double hrot = h * LSEL(rot);
-  const double gam1 = LSEL(gam1), gam2 = LSEL(gam2);
-  const double dEDP = -a.detuning + a.detuningDP;
-  const double e0_0 = half ? -h * a.detuning : 0.0, e1_0 = half ? h : 0.0;
-  const double e0_1 = half ? h * dEDP : -h * a.detuning, e1_1 = half ? -h * (1 + a.kRat) : -h;
-  const double e0_2 = h * dEDP, e1_2 = half ? h * (1 - a.kRat) : h * (a.kRat - 1);
-  Lane8H H;
-  H.g0 = half ? 0.5 * h * gam2 : 0.0; H.g1 = half ? 0.0 : 0.5 * h * gam1;
-  H.G0 = half ? h * gam2 : 0.0; H.G1 = half ? 0.0 : h * gam1;
-  H.sa02 = sg * (half ? hc25 : 0.0); H.sb00 = sg * hc20; H.sa12 = sg * (half ? 0.0 : hc13); H.sb11 = sg * hc14;
-  H.sa21 = sg * (half ? 0.0 : hc13); H.sa20 = sg * (half ? hc25 : 0.0);
-  H.sa01r = sg * hc10; H.a01i = 0.0; H.sa10r = sg * hc10; H.a10i = 0.0;  // half 1: set from the rotating phase every substep
-  const double k1 = half ? -C.kick_dp * LSEL(gD[0]) : C.kick_sp * LSEL(gA);
-  const double k2 = half ? 0.0 : C.kick_dp * LSEL(gD[1]);
-  const double k3 = half ? -C.kick_sp * LSEL(gB) : 0.0;
-  const double k4 = half ? -C.kick_dp * LSEL(gD[2]) : 0.0;
-  const double k5 = half ? -C.kick_dp * LSEL(gD[3]) : 0.0;
-#undef LSEL
-  const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
-  const int base = threadIdx.x & 24;  // first lane of this ion's octet within the warp
-
-  pdl_wait();
-  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 0);
-  double y[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) y[k] = Pb[(size_t)(2 * map[k] + part) * a.ld + i];
-  // octet lane 0 carries (x, y), lane 1 (x, z); the others shadow (x, y) without storing
-  const int c2 = (o == 1) ? 2 : 1;
-  double rx = Rb[i], r2 = Rb[(size_t)c2 * a.ld + i], vx = Vb[i], v2 = Vb[(size_t)c2 * a.ld + i];
-  double fx_, f2_;
-  load_forces(a, b, i, c2, active && o == 0, active && o < 2, fx_, f2_);
-  const double fx = fx_, f2 = f2_;
-  double tp = a.tPart[(size_t)b * a.ld + i];
-  double t = a.clock ? a.clock[0] : a.t0;
-  const uint64_t substep0 = a.clock ? *reinterpret_cast<const unsigned long long*>(a.clock + 1) : a.substep0;
-  const double DT = 0.5 * a.dtq;
-  const PrepC pc = {e0_0, e1_0, e0_1, e1_1, e0_2, e1_2, hrot, a.pv2qv, 2. * (1 + a.kRat), a.g2E,
-                    0.0126 * a.fracOfSig * a.Te, sqrt(a.density) * a.sig0, 0.00014314 * a.Te / (a.density * a.sig0 * a.sig0), a.fracOfSig != 0.0};
-
-  for (int s = 0; s < a.nsub; s++) {
-    {  // step() (SU:356-430)
-      const bool started = t > 0;
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++) {
-        if (started) {
-          rx = __dadd_rn(rx, __dmul_rn(DT, vx));
-          r2 = __dadd_rn(r2, __dmul_rn(DT, v2));
-        } else {
-          rx = __dadd_rn(rx, __dadd_rn(__dmul_rn(DT, vx), __dmul_rn(__dmul_rn(DT, DT), fx)));
-          r2 = __dadd_rn(r2, __dadd_rn(__dmul_rn(DT, v2), __dmul_rn(__dmul_rn(DT, DT), f2)));
-        }
-        if (rx < 0) rx = __dadd_rn(rx, a.L);
-        if (rx > a.L) rx = __dadd_rn(rx, -a.L);
-        if (r2 < 0) r2 = __dadd_rn(r2, a.L);
-        if (r2 > a.L) r2 = __dadd_rn(r2, -a.L);
-        if (hf == 0) {
-          vx = __dadd_rn(vx, __dmul_rn(a.dtq, fx));
-          v2 = __dadd_rn(v2, __dmul_rn(a.dtq, f2));
-        }
-      }
-    }
-    tp = __dadd_rn(tp, a.dtq);
-    const Pre cur = prep4(pc, vx, tp, t);
-
-    double u0, u1;
-    const uint64_t sidx = substep0 + (uint64_t)s;
-    if (FORCED) {
-      const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
-      u0 = up[0]; u1 = up[1];
-    } else {
-      uint4 q4 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
-      u0 = u52(q4.x, q4.y); u1 = u52(q4.z, q4.w);
-    }
-    H.sE0 = sg * cur.hE0; H.sE1 = sg * cur.hE1; H.sE2 = sg * cur.hE2;
-    if (half) { H.sa01r = sg * cur.cr; H.a01i = -cur.ci; H.sa10r = sg * cur.cr; H.a10i = cur.ci; }
-
-    // the pre-step amplitudes in full: own (x, y) and the partner half's w0, w1 -- for the P populations and the optical force
-    const double pb0 = __shfl_xor_sync(0xffffffffu, y[0], 1), pb1 = __shfl_xor_sync(0xffffffffu, y[1], 1), pb2 = __shfl_xor_sync(0xffffffffu, y[2], 1);
-    const double ra0 = __shfl_xor_sync(0xffffffffu, y[0], 2), ra1 = __shfl_xor_sync(0xffffffffu, y[1], 2);
-    const double rb0 = __shfl_xor_sync(0xffffffffu, y[0], 3), rb1 = __shfl_xor_sync(0xffffffffu, y[1], 3);
-    const cplx w0 = {im ? pb0 : y[0], im ? y[0] : pb0}, w1 = {im ? pb1 : y[1], im ? y[1] : pb1}, w2 = {im ? pb2 : y[2], im ? y[2] : pb2};
-    const cplx r0 = {im ? rb0 : ra0, im ? ra0 : rb0}, r1 = {im ? rb1 : ra1, im ? ra1 : rb1};
-    // P populations of the octet in the reference's state order 2,3,4,5: (blk, half) lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
-    const double pn = half ? cnorm(w0) : cnorm(w1);
-    const double n3 = __shfl_sync(0xffffffffu, pn, base), n5 = __shfl_sync(0xffffffffu, pn, base + 2);
-    const double n2 = __shfl_sync(0xffffffffu, pn, base + 4), n4 = __shfl_sync(0xffffffffu, pn, base + 6);
-    const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;
-    const bool jump = !(u0 > dp0);
-    // optical force from the pre-step coherences (SU:490-503): every (blk, half) pair of lanes holds the same terms, the real-part lane counts them
-    double kick = im ? 0.0 : (k1 * im_acb(w0, w1) + k2 * im_acb(w2, w1) + k3 * im_acb(r0, w0) + k4 * im_acb(w2, w0) + k5 * im_acb(w1, r1));
-
-    double yn[3];
-    {
-      double w[3], g[3], acc[3];
-      stage8(H, im, y, g);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { acc[k] = g[k]; w[k] = fma(0.5, g[k], y[k]); }
-      stage8(H, im, w, g);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { acc[k] = fma(3.0, g[k], acc[k]); w[k] = fma(0.5, g[k], y[k]); }
-      stage8(H, im, w, g);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { acc[k] = fma(3.0, g[k], acc[k]); w[k] = y[k] + g[k]; }
-      stage8(H, im, w, g);
-#pragma unroll
-      for (int k = 0; k < 3; k++) yn[k] = fma(0.125, acc[k] + g[k], y[k]);
-    }
-    if (!jump) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) y[k] = yn[k];
-    } else {  // quantum jump (SU:573-703): all eight lanes decide identically
-      double u2, u3, u4;
-      if (FORCED) {
-        const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
-        u2 = up[2]; u3 = up[3]; u4 = up[4];
-      } else {
-        uint4 q4 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
-        u2 = u52(q4.x, q4.y); u3 = u52(q4.z, q4.w);
-        q4 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
-        u4 = u52(q4.x, q4.y);
-      }
-      tp = 0.0;
-      const double tot = n2 + n3 + n4 + n5;
-      const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
-      const bool sDecay = !(u2 < C.dfrac);
-      kick = 0.0;
-      if (o == 0) {
-        const double mag = sDecay ? a.vKick : a.vKickDP;
-        kick = (u3 < 0.5) ? mag : -mag;
-      }
-      int dest;
-      if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
-      else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
-      else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
-      else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
-#pragma unroll
-      for (int k = 0; k < 3; k++) y[k] = (!im && map[k] == dest) ? 1.0 : 0.0;
-    }
-    kick += __shfl_xor_sync(0xffffffffu, kick, 1);
-    kick += __shfl_xor_sync(0xffffffffu, kick, 2);
-    kick += __shfl_xor_sync(0xffffffffu, kick, 4);
-    vx = __dadd_rn(vx, kick);  // SU:705
-    if (a.renorm) {
-      double own = fma(y[0], y[0], fma(y[1], y[1], y[2] * y[2]));
-      own += __shfl_xor_sync(0xffffffffu, own, 1);
-      own += __shfl_xor_sync(0xffffffffu, own, 2);
-      own += __shfl_xor_sync(0xffffffffu, own, 4);
-      const double nn = sqrt(own);
-#pragma unroll
-      for (int k = 0; k < 3; k++) y[k] /= nn;
-    }
-    t = __dadd_rn(t, a.dtq);  // SU:716
-  }
-
-  pdl_launch_dependents();
-  if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 1);
-  if (!active) return;
-#pragma unroll
-  for (int k = 0; k < 3; k++) Pb[(size_t)(2 * map[k] + part) * a.ld + i] = y[k];
-  if (o < 2) {
-    long long* __restrict__ Xf = a.Rfix + (size_t)b * 3 * a.ld;
-    Rb[(size_t)c2 * a.ld + i] = r2;
-    Xf[(size_t)c2 * a.ld + i] = to_fixed(r2, a.invL, a.invL_lo);
-    Vb[(size_t)c2 * a.ld + i] = v2;
-    if (o == 0) {
-      Rb[i] = rx; Xf[i] = to_fixed(rx, a.invL, a.invL_lo);
-      Vb[i] = vx; a.tPart[(size_t)b * a.ld + i] = tp;
-    }
-  }
-}
-
 void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s) {
   long long threads = 2LL * a.nrows * a.B;
   int block = threads >= 148LL * 4 * 128 ? 128 : 64;
@@ -1049,20 +809,7 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   const bool small = 4LL * a.N * a.B <= 148LL * 4 * 32;  // four-lane warps fit one per sub-partition
   // a.lanes (mdqt_params.plan_n != 0: batch-reproducible mode) pins the mapping so that a job gives the same bits alone or batched
   const int want = lanes_override ? lanes_override : a.lanes;
-  const bool four = scheme == 12 && a.do_step && (want == 4 || (want != 2 && want != 8 && small));
-  // eight lanes per ion: MDQT_QT_LANES=8 (A/B), or by default while the warps still number at most two per sub-partition
-#ifndef MDQT_K2_EIGHT_DEFAULT
-#define MDQT_K2_EIGHT_DEFAULT 0
-#endif
-  const bool small8 = 8LL * a.N * a.B <= 148LL * 4 * 32 * 2;
-  const bool eight = scheme == 12 && a.do_step && (want == 8 || (MDQT_K2_EIGHT_DEFAULT && want == 0 && small8));
-  if (eight) {
-    long long th = 8LL * a.nrows * a.B;
-    int g8 = (int)((th + 31) / 32);
-    if (forced) launch_kernel(k_substeps8<true>, dim3(g8), dim3(32), s, false, a, C);
-    else launch_kernel(k_substeps8<false>, dim3(g8), dim3(32), s, pdl_enabled(), a, C);
-    return;
-  }
+  const bool four = scheme == 12 && a.do_step && (want == 4 || (want != 2 && small));
   if (four) {
     long long th = 4LL * a.nrows * a.B;
     int g4 = (int)((th + 31) / 32);
