@@ -58,9 +58,9 @@ typedef struct mdqt_params {
   int32_t renormalize;  /* reNormalizewvFns (SU:74) */
   int32_t quad;         /* 7-level only: circular-pump coupling mask of MC408Q:596 */
   int32_t plan_n;       /* 0, or the NOMINAL ion number (the reference's N0) that fixes the summation order of the force
-                           kernel and the lane mapping of the substep kernel: handles created with the same plan_n give
-                           the same bits for a trajectory whether it runs alone or batched with others (n_traj > 1),
-                           whatever each trajectory's actual ion count. 0: planned from n_ions and n_traj for speed. */
+                           kernel: handles created with the same plan_n give the same bits for a trajectory whether it runs
+                           alone or batched with others (n_traj > 1), whatever each trajectory's actual ion count. 0: the
+                           order is planned from n_ions (the lane mappings of the substep kernel give identical bits anyway). */
   double L;             /* box length (SU:297, MD:73) */
   double kappa;         /* 1/lDeb = sqrt(3 Ge) (SU:295) or kappa (MD:67) */
   double rcut;          /* L/2 (SU:195, MD:74) */

@@ -509,7 +509,7 @@ extern "C++" QTArgs mdqt_qt_args(mdqt_handle* h, int nsub, int do_step, int do_k
   a.nsub = nsub; a.do_step = do_step; a.do_kick = do_kick; a.do_tpart = do_kick;  // tPart lives where the kick does (SU, TS)
   a.scheme = h->S; a.S = h->S; a.renorm = p.renormalize; a.quad = p.quad;
   a.nb = h->nb; a.seeds = h->seeds;
-  a.lanes = p.plan_n > 0 ? 2 : 0;  // batch-reproducible mode: one lane mapping whatever the batch size
+  a.lanes = 0;  // lanes per ion by (N, B): the two- and four-lane kernels give the same bits (tests/test_gpu_variants.py)
   a.t0 = h->t; a.substep0 = h->substep; a.seed = p.seed;
   a.L = p.L; a.dtq = p.dtq;
   a.detuning = p.detuning; a.detuningDP = p.detuningDP; a.Om = p.Om; a.OmDP = p.OmDP; a.dR = p.dR; a.kRat = p.kRat;

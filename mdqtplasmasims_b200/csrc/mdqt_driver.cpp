@@ -15,9 +15,10 @@
 //            [--Om 1] [--OmDP 1] [--saveDirectory dataLaserCool/] [--newRun 1] [--c0 0] [--tmax 30]
 //            [--reNormalizewvFns 0] [--sampleFreq 40] [--seed n] [--device 0] [--writers n] [--fast-single] [--quiet]
 //
-// A job gives the same bits whether it runs alone or inside any batch: the force summation plan and the substep kernel's
-// lane mapping are fixed by N0 (mdqt_params.plan_n), not by the batch. --fast-single lifts that for a lone job (the plan is
-// then chosen for speed from N and n_traj = 1; ~3 % faster, results differ in the last bits).
+// A job gives the same bits whether it runs alone or inside any batch: the force summation plan is fixed by N0
+// (mdqt_params.plan_n), not by the batch, and the substep kernel's lane mappings are bitwise equivalent. --fast-single lifts the
+// former for a lone job (the plan is then made for the job's own N: faster when N exceeds what the N0 plan fits in one round of
+// items, e.g. N = 3653 at N0 = 3500; results differ in the last bits).
 #include "../../include/mdqt.h"
 #include "../../include/mdqt_io.h"
 #include <math.h>

@@ -203,6 +203,79 @@ __device__ __forceinline__ void stage(const LaneH& H, const cplx* w, cplx* g) {
   }
 }
 
+// Doppler shift, rotating phase and the coefficients that depend on them, for a substep that starts (after step()'s velocity
+// update) with velocity vxs, time-since-jump tps (already advanced) and global time ts (SU:447, 481-483, 506-510). The two
+// helpers are shared by the two- and the four-lane kernel: same expressions, same roundings.
+struct PrepC { double e0_0, e1_0, e0_1, e1_1, e0_2, e1_2, hrot, pv2qv, two_kr, g2E, ed_num, ed_den, ed_c; bool expand; };
+struct Pre { double hE0, hE1, hE2, cr, ci; };
+__device__ __forceinline__ double prep_uu(const PrepC& c, double vxs, double ts) {
+  double expDet = 0.0;
+  if (c.expand) expDet = __ddiv_rn(__dmul_rn(c.ed_num, ts), __dmul_rn(c.ed_den, sqrt(fma(__dmul_rn(c.ed_c, ts), ts, 1.0))));
+  return fma(vxs, c.pv2qv, expDet);
+}
+__device__ __forceinline__ void prep_rot(const PrepC& c, double uu, double tps, double& cr, double& ci) {
+  const double phi = __dmul_rn(__dmul_rn(__dmul_rn(c.two_kr, uu), tps), c.g2E);  // 2 u (1 + kRat) tPart g2E (SU:508)
+  double sn, cs;
+  sincos_fast(phi, sn, cs);
+  cr = __dmul_rn(c.hrot, cs); ci = __dmul_rn(c.hrot, sn);
+}
+__device__ __forceinline__ Pre prep4(const PrepC& c, double vxs, double tps, double ts) {
+  const double uu = prep_uu(c, vxs, ts);
+  Pre p;
+  p.hE0 = fma(c.e1_0, uu, c.e0_0); p.hE1 = fma(c.e1_1, uu, c.e0_1); p.hE2 = fma(c.e1_2, uu, c.e0_2);
+  prep_rot(c, uu, tps, p.cr, p.ci);
+  return p;
+}
+
+// The 12-level rows of m = w - i h H w in the two-lane kernel, written with EXACTLY the operations (and their order) that the
+// four-lane kernel's generic rows perform on non-zero coefficients -- so that the two lane mappings give the same bits, and a
+// job's results do not depend on which mapping the batch size selects. Local states: 0 S, 1 P1, 2 P2, 3 D3, 4 D4, 5 D5.
+struct LaneH6 {
+  double hc10, hc20, hc13, hc14, hc25, cr, ci;   // h * couplings; rotating coupling h rot (cos, sin)
+  double hE1, hE2, hE3, hE4, hE5, hg1, hg2, G1, G2;
+};
+__device__ __forceinline__ double stage6c(const LaneH6& H, const cplx* w, cplx* g) {
+  // dp: (G1 |P1|^2) + (G2 |P2|^2), then the other block
+  double own = __dadd_rn(__dmul_rn(H.G1, cnorm(w[1])), __dmul_rn(H.G2, cnorm(w[2])));
+  own = __dadd_rn(own, __shfl_xor_sync(0xffffffffu, own, 1));
+  const double pref = rsqrt_near1(1.0 - own);
+  cplx m[6];
+  double hr, hi;
+  // S:  c10 P1, c20 P2
+  hr = __dmul_rn(H.hc10, w[1].re); hi = __dmul_rn(H.hc10, w[1].im);
+  hr = fma(H.hc20, w[2].re, hr); hi = fma(H.hc20, w[2].im, hi);
+  m[0].re = __dadd_rn(w[0].re, hi); m[0].im = __dadd_rn(w[0].im, -hr);
+  // P1: (E1 - i g1) P1, c10 S, c13 D3, c14 D4
+  hr = fma(H.hE1, w[1].re, __dmul_rn(H.hg1, w[1].im)); hi = fma(H.hE1, w[1].im, -__dmul_rn(H.hg1, w[1].re));
+  hr = fma(H.hc10, w[0].re, hr); hi = fma(H.hc10, w[0].im, hi);
+  hr = fma(H.hc13, w[3].re, hr); hi = fma(H.hc13, w[3].im, hi);
+  hr = fma(H.hc14, w[4].re, hr); hi = fma(H.hc14, w[4].im, hi);
+  m[1].re = __dadd_rn(w[1].re, hi); m[1].im = __dadd_rn(w[1].im, -hr);
+  // D3: E3 D3, c13 P1
+  hr = fma(H.hE3, w[3].re, __dmul_rn(H.hc13, w[1].re)); hi = fma(H.hE3, w[3].im, __dmul_rn(H.hc13, w[1].im));
+  m[3].re = __dadd_rn(w[3].re, hi); m[3].im = __dadd_rn(w[3].im, -hr);
+  // P2: (E2 - i g2) P2, conj(rot) D4, c25 D5, c20 S
+  hr = fma(H.hE2, w[2].re, __dmul_rn(H.hg2, w[2].im)); hi = fma(H.hE2, w[2].im, -__dmul_rn(H.hg2, w[2].re));
+  hr = fma(H.cr, w[4].re, fma(H.ci, w[4].im, hr)); hi = fma(H.cr, w[4].im, fma(-H.ci, w[4].re, hi));
+  hr = fma(H.hc25, w[5].re, hr); hi = fma(H.hc25, w[5].im, hi);
+  hr = fma(H.hc20, w[0].re, hr); hi = fma(H.hc20, w[0].im, hi);
+  m[2].re = __dadd_rn(w[2].re, hi); m[2].im = __dadd_rn(w[2].im, -hr);
+  // D4: E4 D4, rot P2, c14 P1
+  hr = __dmul_rn(H.hE4, w[4].re); hi = __dmul_rn(H.hE4, w[4].im);
+  hr = fma(H.cr, w[2].re, fma(-H.ci, w[2].im, hr)); hi = fma(H.cr, w[2].im, fma(H.ci, w[2].re, hi));
+  hr = fma(H.hc14, w[1].re, hr); hi = fma(H.hc14, w[1].im, hi);
+  m[4].re = __dadd_rn(w[4].re, hi); m[4].im = __dadd_rn(w[4].im, -hr);
+  // D5: E5 D5, c25 P2
+  hr = fma(H.hE5, w[5].re, __dmul_rn(H.hc25, w[2].re)); hi = fma(H.hE5, w[5].im, __dmul_rn(H.hc25, w[2].im));
+  m[5].re = __dadd_rn(w[5].re, hi); m[5].im = __dadd_rn(w[5].im, -hr);
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    g[k].re = fma(pref, m[k].re, -w[k].re);
+    g[k].im = fma(pref, m[k].im, -w[k].im);
+  }
+  return own;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // the fused kernel: nsub x { step(); qstep(); } for one ion per lane pair
 // ------------------------------------------------------------------------------------------------------------
@@ -246,6 +319,19 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
   const double kd0 = C.kick_dp * (lane ? LB.gD[0] : LA.gD[0]), kd1 = C.kick_dp * (lane ? LB.gD[1] : LA.gD[1]);
   const double kd2 = C.kick_dp * (lane ? LB.gD[2] : LA.gD[2]), kd3 = C.kick_dp * (lane ? LB.gD[3] : LA.gD[3]);
   const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
+  // 12-level path: the operations of the four-lane kernel (stage6c), its energy formulas and its optical-force weights
+  LaneH6 H6;
+  H6.hc10 = H.hc10; H6.hc20 = H.hc20; H6.hc13 = H.hc13; H6.hc14 = H.hc14; H6.hc25 = H.hc25;
+  H6.hg1 = H.hg1; H6.hg2 = H.hg2; H6.G1 = H.G1; H6.G2 = H.G2;
+  H6.cr = H6.ci = 0.0; H6.hE1 = H6.hE2 = H6.hE3 = H6.hE4 = H6.hE5 = 0.0;
+  const double dEDP6 = -a.detuning + a.detuningDP;
+  const double e0P = -h * a.detuning, e0D = h * dEDP6;
+  const double e1P1 = -h, e1P2 = h, e1D3 = h * (a.kRat - 1), e1D4 = -h * (1 + a.kRat), e1D5 = h * (1 - a.kRat);
+  const PrepC pc6 = {0, 0, 0, 0, 0, 0, hrot, a.pv2qv, 2. * (1 + a.kRat), a.g2E,
+                     0.0126 * a.fracOfSig * a.Te, sqrt(a.density) * a.sig0, 0.00014314 * a.Te / (a.density * a.sig0 * a.sig0), a.fracOfSig != 0.0};
+  const double k1a = C.kick_sp * (lane ? LB.gA : LA.gA), k2a = C.kick_dp * (lane ? LB.gD[1] : LA.gD[1]);
+  const double k1b = -C.kick_dp * (lane ? LB.gD[0] : LA.gD[0]), k3b = -C.kick_sp * (lane ? LB.gB : LA.gB);
+  const double k4b = -C.kick_dp * (lane ? LB.gD[2] : LA.gD[2]), k5b = -C.kick_dp * (lane ? LB.gD[3] : LA.gD[3]);
 
   pdl_wait();  // forces / state come from the previous kernels in the stream
   if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 0);
@@ -327,47 +413,52 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     //      exchanges on plain full-mask shuffles); lanes that jump discard the result below ----
     double kick = 0.0;
     if (do_kick) {  // optical force from the pre-step coherences (SU:490-503; TS:170-174)
-      kick = ksA * im_acb(y[0], y[1]) - ksB * im_acb(y[0], y[2]);
-      if (NL == 6)
-        kick += kd0 * im_acb(y[4], y[2]) + kd1 * im_acb(y[3], y[1]) - kd2 * im_acb(y[5], y[2]) - kd3 * im_acb(y[4], y[1]);
+      if (NL == 6) {  // the four-lane kernel's two half-block chains, then their sum
+        const double kA = fma(k2a, im_acb(y[3], y[1]), __dmul_rn(k1a, im_acb(y[0], y[1])));
+        double kB = __dmul_rn(k1b, im_acb(y[2], y[4]));
+        kB = fma(k3b, im_acb(y[0], y[2]), kB); kB = fma(k4b, im_acb(y[5], y[2]), kB); kB = fma(k5b, im_acb(y[4], y[1]), kB);
+        kick = __dadd_rn(kA, kB);
+      } else {
+        kick = ksA * im_acb(y[0], y[1]) - ksB * im_acb(y[0], y[2]);
+      }
     }
-    const double uu = vq + expDet;
-    H.hE1 = h * (-a.detuning - vq - expDet);                        // totalDetRightSP (SU:506)
-    H.hE2 = h * (-a.detuning + vq + expDet);                        // totalDetLeftSP  (SU:507)
     if (NL == 6) {
-      H.hE3 = h * (dEDP + (a.kRat - 1) * uu);                       // states 11,12 (SU:510)
-      H.hE4 = h * (dEDP - vq - expDet - a.kRat * uu);               // states 9,10
-      H.hE5 = h * (dEDP + (1 - a.kRat) * uu);                       // states 7,8
-      const double phi = 2. * uu * (1 + a.kRat) * tp * a.g2E;       // SU:508
-      double sn, cs;
-      sincos_fast(phi, sn, cs);
-      H.hrr = hrot * cs; H.hri = hrot * sn;
+      // energies e0 + e1 (vq + expDetuning) and the rotating coupling exactly as the four-lane kernel forms them (SU:506-510)
+      const double uu = prep_uu(pc6, vx, t);
+      H6.hE1 = fma(e1P1, uu, e0P); H6.hE2 = fma(e1P2, uu, e0P);
+      H6.hE3 = fma(e1D3, uu, e0D); H6.hE4 = fma(e1D4, uu, e0D); H6.hE5 = fma(e1D5, uu, e0D);
+      prep_rot(pc6, uu, tp, H6.cr, H6.ci);
+    } else {
+      H.hE1 = h * (-a.detuning - vq - expDet);                      // totalDetRightSP (MC408L:595)
+      H.hE2 = h * (-a.detuning + vq + expDet);                      // totalDetLeftSP
     }
+#define STAGE(v) do { if (NL == 6) stage6c(H6, v, g); else stage<NL>(H, v, g); } while (0)
     cplx yn[NL];
     {
       cplx w[NL], g[NL], acc[NL];
-      stage<NL>(H, y, g);
+      STAGE(y);
 #pragma unroll
       for (int k = 0; k < NL; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
-      stage<NL>(H, w, g);
+      STAGE(w);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
         acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
         w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im);
       }
-      stage<NL>(H, w, g);
+      STAGE(w);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
         acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
         w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
       }
-      stage<NL>(H, w, g);
+      STAGE(w);
 #pragma unroll
       for (int k = 0; k < NL; k++) {
         yn[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
         yn[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
       }
     }
+#undef STAGE
     if (!jump) {
 #pragma unroll
       for (int k = 0; k < NL; k++) y[k] = yn[k];
@@ -422,8 +513,12 @@ __global__ void __launch_bounds__(128) k_substeps(QTArgs a, QTConsts C) {
     }
     if (a.renorm) {  // SU:706-712
       double own = 0.0;
+      if (NL == 6) {  // half-block sums first, as the four-lane kernel adds them
+        own = __dadd_rn(__dadd_rn(__dadd_rn(cnorm(y[0]), cnorm(y[1])), cnorm(y[3])), __dadd_rn(__dadd_rn(cnorm(y[2]), cnorm(y[4])), cnorm(y[5])));
+      } else {
 #pragma unroll
-      for (int k = 0; k < NL; k++) own += cnorm(y[k]);
+        for (int k = 0; k < NL; k++) own += cnorm(y[k]);
+      }
       double nn = sqrt(own + __shfl_xor_sync(0xffffffffu, own, 1));
 #pragma unroll
       for (int k = 0; k < NL; k++) { y[k].re /= nn; y[k].im /= nn; }
@@ -529,23 +624,6 @@ __device__ __forceinline__ double stage4(const Lane4H& H, const cplx* w, cplx* g
     g[k].im = fma(pref, m[k].im, -w[k].im);
   }
   return own;
-}
-
-// Doppler shift, rotating phase and the coefficients that depend on them, for a substep that starts (after step()'s velocity
-// update) with velocity vxs, time-since-jump tps (already advanced) and global time ts (SU:447, 481-483, 506-510)
-struct PrepC { double e0_0, e1_0, e0_1, e1_1, e0_2, e1_2, hrot, pv2qv, two_kr, g2E, ed_num, ed_den, ed_c; bool expand; };
-struct Pre { double hE0, hE1, hE2, cr, ci; };
-__device__ __forceinline__ Pre prep4(const PrepC& c, double vxs, double tps, double ts) {
-  double expDet = 0.0;
-  if (c.expand) expDet = c.ed_num * ts / (c.ed_den * sqrt(1 + c.ed_c * ts * ts));
-  const double uu = vxs * c.pv2qv + expDet;
-  Pre p;
-  p.hE0 = fma(c.e1_0, uu, c.e0_0); p.hE1 = fma(c.e1_1, uu, c.e0_1); p.hE2 = fma(c.e1_2, uu, c.e0_2);
-  const double phi = c.two_kr * uu * tps * c.g2E;
-  double sn, cs;
-  sincos_fast(phi, sn, cs);
-  p.cr = c.hrot * cs; p.ci = c.hrot * sn;
-  return p;
 }
 
 template <bool FORCED>
@@ -682,8 +760,10 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
       // stage 1 also yields the partner amplitudes needed by the optical force (pre-step coherences)
       const cplx r0 = {__shfl_xor_sync(0xffffffffu, y[0].re, 1), __shfl_xor_sync(0xffffffffu, y[0].im, 1)};
       const cplx r1 = {__shfl_xor_sync(0xffffffffu, y[1].re, 1), __shfl_xor_sync(0xffffffffu, y[1].im, 1)};
-      kick = k1 * im_acb(y[0], y[1]) + k2 * im_acb(y[2], y[1]) + k3 * im_acb(r0, y[0]) + k4 * im_acb(y[2], y[0]) +
-             k5 * im_acb(y[1], r1);
+      // one explicit chain (zero weights are exact no-ops): the two-lane kernel forms the same sums in the same order
+      kick = __dmul_rn(k1, im_acb(y[0], y[1]));
+      kick = fma(k2, im_acb(y[2], y[1]), kick); kick = fma(k3, im_acb(r0, y[0]), kick);
+      kick = fma(k4, im_acb(y[2], y[0]), kick); kick = fma(k5, im_acb(y[1], r1), kick);
 #if MDQT_K2_PIPE
       // the no-jump kick is final here: sum it over the quad now and start on the next substep's coefficients
       kick += __shfl_xor_sync(0xffffffffu, kick, 1);

@@ -9,7 +9,7 @@ sys.path.insert(0, %r)
 import numpy as np
 from mdqtplasmasims_b200 import Engine, su_params, synthetic
 N = 3500
-for label, over in (("auto lanes", {}),):
+for label, over in (("auto lanes", {}), ("two lanes ", {"plan_n": 3500})):
     p = su_params(n_ions=N, N0=N, seed=99, **over)
     e = Engine(p)
     e.upload(R=synthetic.random_positions(N, p.L, seed=1), V=np.zeros((3, N)), psi=synthetic.random_s_state(N, seed=1), tPart=np.zeros(N), t=0.0, substep=0)
