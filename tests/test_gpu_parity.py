@@ -263,10 +263,10 @@ def test_ensemble_batch_equals_single_trajectories():
         e1.upload(R=R[b], V=V[b], psi=psi[b], tPart=tp[b], t=0.0, substep=0)
         e1.md_steps(3)
         s1 = e1.download()
-        # the j-split plan depends on (N, B), so sums may differ in rounding between B=3 and B=1 handles
-        assert np.abs(sb["R"][b] - s1["R"]).max() <= 1e-9
-        assert np.abs(sb["psi"][b] - s1["psi"]).max() <= 1e-7
-        assert np.array_equal(sb["tPart"][b] == 0.0, s1["tPart"] == 0.0)
+        # round 2: the force summation order depends on N alone (item kernel) and the lane mappings of the substep kernel are
+        # bitwise equivalent, so a shard equals the single-trajectory runs bit for bit (round 1 allowed 1e-9 / 1e-7 here)
+        for k in ("R", "V", "psi", "tPart"):
+            assert np.array_equal(sb[k][b], s1[k]), k
 
 
 def test_row_decomposition_bitwise_identical():
