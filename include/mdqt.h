@@ -188,6 +188,9 @@ int mdqt_set_tags(mdqt_handle* h, const uint8_t* tags);
 int mdqt_moments_begin(mdqt_handle* h, int nslots);
 int mdqt_moments_record(mdqt_handle* h, int slot);
 int mdqt_moments_download(mdqt_handle* h, double* out, int nslots);
+/* Velocity distribution of the tagged ions (bit 0 of the tags), x component: pv = double [n_traj][4001] on the bins
+ * (j - 2000) * 0.0025, as recordTaggedParticleMoments() / output() of the tagging programs write it (MC408L:1069-1137, FZ408L:835-893). */
+int mdqt_vel_dist_tagged(mdqt_handle* h, double* pv);
 /* anisotropizeVelocities() (MD:548-558): V_x *= sx, V_y *= sy, V_z *= sz. */
 int mdqt_scale_velocities(mdqt_handle* h, double sx, double sy, double sz);
 /* Test hook: uniforms u[n_ions][2] for the next mdqt_tag_particles calls (n_traj must be 1). NULL restores Philox. */

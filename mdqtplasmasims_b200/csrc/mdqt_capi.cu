@@ -1146,6 +1146,20 @@ int mdqt_moments_download(mdqt_handle* h, double* out, int nslots) {
   return MDQT_OK;
 }
 
+int mdqt_vel_dist_tagged(mdqt_handle* h, double* pv) {
+  if (!h || !pv) return fail(MDQT_EINVAL, "null argument");
+  if (!h->tags) return fail(MDQT_ESTATE, "mdqt_set_tags not called");
+  NEED_UNIFORM_N(h);
+  if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_vel_dist_tagged: a row-decomposed handle holds the velocities of its own rows only");
+  CU(cudaSetDevice(h->p.device));
+  if ((size_t)h->B * kTagBins > (size_t)h->B * 3 * kVelBins) return fail(MDQT_ESTATE, "internal: pvel scratch too small");
+  launch_vel_dist_tagged(h->V, h->tags, h->N, h->ld, h->B, h->pvel, h->stream);  // 4001 <= 3 x 2001 doubles per trajectory
+  CU(cudaMemcpyAsync(pv, h->pvel, (size_t)h->B * kTagBins * 8, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaGetLastError());
+  return MDQT_OK;
+}
+
 int mdqt_scale_velocities(mdqt_handle* h, double sx, double sy, double sz) {
   if (!h) return fail(MDQT_EINVAL, "null handle");
   NEED_UNIFORM_N(h);

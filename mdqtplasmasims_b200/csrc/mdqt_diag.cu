@@ -289,6 +289,29 @@ void launch_moments(const double* V, const unsigned char* tags, int N, int ld, i
   k_moments<<<B, 1024, 0, s>>>(V, tags, N, ld, out);
 }
 
+// Velocity distribution of the TAGGED ions (bit 0 of tags), x component, as recordTaggedParticleMoments() of the tagging programs
+// forms it (MC408L:1069-1137; output() FZ408L:835-893): 4001 bins vel_j = (j - 2000) * 0.0025, Gaussian weights of width 0.002,
+// divided by 6 sqrt(2 pi 0.002^2). grid (ceil(4001/8), B), 256 threads = 8 bins x 32 lanes striding over the ions.
+__global__ void __launch_bounds__(256) k_vel_dist_tagged(const double* __restrict__ V, const unsigned char* __restrict__ tags, int N, int ld,
+                                                         double* __restrict__ pv) {
+  const int b = blockIdx.y;
+  const int bin = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const unsigned char* tg = tags + (size_t)b * N;
+  const double V2 = 1. / (2. * 0.002 * 0.002), vb = (double)(bin - 2000) * 0.0025;
+  double s = 0.0;
+  if (bin < kTagBins)
+    for (int i = lane; i < N; i += 32)
+      if (tg[i] & 1) { const double d = vb - vx[i]; s += exp(-V2 * d * d); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0 && bin < kTagBins) pv[(size_t)b * kTagBins + bin] = s / (6.0 * sqrt(2 * M_PI * 0.002 * 0.002));
+}
+void launch_vel_dist_tagged(const double* V, const unsigned char* tags, int N, int ld, int B, double* pv, cudaStream_t s) {
+  dim3 grid((kTagBins + 7) / 8, B);
+  k_vel_dist_tagged<<<grid, 256, 0, s>>>(V, tags, N, ld, pv);
+}
+
 // anisotropizeVelocities() (MD:548-558): V_c *= scale_c
 __global__ void k_scale_velocities(double* __restrict__ V, int N, int ld, int B, double sx, double sy, double sz) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -11,6 +11,7 @@ constexpr int kForceThreads = 128;   // threads per CTA of the pair kernels
 #endif
 constexpr int kExpTable = MDQT_EXP_T; // entries of the 2^(j/T) table used by the fp64 exp (128: degree-5 polynomial, 1024: degree-3)
 constexpr int kVelBins = 2001;       // KDE bins of output() (SU:120-123)
+constexpr int kTagBins = 4001;        // velocity bins of the tagged-ion distribution (MC408L:1069, FZ408L:835)
 constexpr int kMomentsPerRecord = 23; // 3 axis sums of v^2 + 4 tag sets x {count, sum v_x^1..4}
 
 struct ForceArgs {
@@ -148,6 +149,7 @@ void launch_diag_partial(const double* V, int row0, int nrows, int ld, int B, co
 void launch_vel_dist_rows(const double* V, const double* diag, int row0, int nrows, int ld, int B, double* pvel, cudaStream_t s);
 // recorders over the velocities (mdqt_diag.cu): one 23-entry record per trajectory; V_c *= scale_c
 void launch_moments(const double* V, const unsigned char* tags, int N, int ld, int B, double* out, cudaStream_t s);
+void launch_vel_dist_tagged(const double* V, const unsigned char* tags, int N, int ld, int B, double* pv, cudaStream_t s);
 void launch_scale_velocities(double* V, int N, int ld, int B, double sx, double sy, double sz, cudaStream_t s);
 void launch_populations(const double* psi, int S, int N, int ld, int B, double* pops, cudaStream_t s);
 // projective spin measurement after the pump (tagParticles MC408L:1022-1067 / MC422L:992-1036; measureSpinUps

@@ -6,6 +6,9 @@
 //            autocorrelations, the instantaneous-anisotropy stage, re-equilibration, and the laser-force anisotropy stages.
 //   fz408l   randomFrozenStartTag408Linear.cpp main() (FZ408L:981-1076): frozen random start, leap-frog time loop with the
 //            408 nm pump window, spin measurement and the tagged velocity autocorrelation.
+//   mc408l   MonteCarloFollowedByQTTagging408Linear.cpp main() (MC408L:1140-1254), stages 1, 4-7: collisional MD, the pump stage
+//            (62 x 7-level qstep() per MDStep), the projective spin measurement, the recording stage with the tagged ions' moments
+//            and velocity distribution, the autocorrelations.
 //
 // The Metropolis Monte-Carlo pre-equilibration of the MD family (MD:207-382, stage 3 of its main) is one sequential
 // accept/reject chain -- "replicas only"  -- and is NOT run here: the MD program starts from the lattice of
@@ -409,6 +412,131 @@ int mdqt_program_fz408l(int argc, char** argv) {
   if (!quiet)
     fprintf(stderr, "mdqt_run: program fz408l, job %u, N=%d, t=%.6f, c0=%d: %ld loop iterations, %u outputs in %.3f s; files in %s\n", job, N, t, c0,
             iters, o.counter, wall, dir.c_str());
+  mdqt_destroy(h);
+  return 0;
+}
+
+// ---- MonteCarloFollowedByQTTagging408Linear.cpp ---------------------------------------------------------------------------------
+// main() (MC408L:1140-1254) without its Monte-Carlo stage: init() (lattice, Maxwellian velocities from std::mt19937, random S-manifold
+// wavefunctions from the UNSEEDED drand48 stream the reference uses, Q14), collisional MD, the pump stage
+// { ratio x qstep(); MDStep(k) } x pumpMDTimeSteps, tagParticles() (projective spin measurement), then the collisionless
+// recording stage -- taggedMoments.dat and vel_distX_timestep%06d.dat every step (MC408L:1069-1137), g(r) every 100 steps,
+// temperature.dat -- and the four autocorrelation files.
+int mdqt_program_mc408l(int argc, char** argv) {
+  OptMap opt = {{"N", "4096"}, {"Gamma", "3"}, {"kappa", "0.5"}, {"density", "2"}, {"timeStep", "0.005"}, {"collisionFreq", "0.25"},
+                {"preSteps", "200"}, {"recordSteps", "1500"}, {"pumpSteps", "-1"}, {"tpumpreal", "0.0000002"}, {"detuning", "-2.5"}, {"Om", "0.7"},
+                {"quad", "0"}, {"pairPairStep", "0.05"}, {"seed", ""}, {"saveDirectory", "data/"}, {"device", "0"}, {"program", "mc408l"}};
+  bool quiet = false;
+  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program mc408l <job> [--N n] [--density x] [--tpumpreal x] ...\n"); return 2; }
+  const unsigned job = (unsigned)atof(argv[1]);
+  if (!parse_opts(argc, argv, 2, opt, &quiet)) return 2;
+  const int N = atoi(opt["N"].c_str());
+  const double Gamma = atof(opt["Gamma"].c_str()), kappa = atof(opt["kappa"].c_str()), n = atof(opt["density"].c_str());
+  const double timeStep = atof(opt["timeStep"].c_str()), collFreq = atof(opt["collisionFreq"].c_str());
+  const double tpumpreal = atof(opt["tpumpreal"].c_str()), detuning = atof(opt["detuning"].c_str()), Om = atof(opt["Om"].c_str());
+  const int preSteps = atoi(opt["preSteps"].c_str()), recSteps = atoi(opt["recordSteps"].c_str());
+  int pumpSteps = atoi(opt["pumpSteps"].c_str());
+  if (pumpSteps < 0) pumpSteps = (int)round(tpumpreal * 813490 * sqrt(n) / timeStep);  // MC408L:119-120
+  const double pairPairStep = atof(opt["pairPairStep"].c_str());
+  const unsigned seed = opt["seed"].empty() ? (unsigned)time(NULL) + job : (unsigned)atol(opt["seed"].c_str());
+  if (recSteps > 5000) { fprintf(stderr, "mdqt_run: recordSteps must be <= 5000\n"); return 2; }
+
+  std::string dir = opt["saveDirectory"];
+  mkdir(dir.c_str(), 0777);
+  char namebuf[256];
+  snprintf(namebuf, sizeof(namebuf), "Gamma%dKappa%dNumIons%dPumpTime%dDet%dOm%dDensity%d", as_unsigned_printed(Gamma * 100),
+           as_unsigned_printed(kappa * 100), N, as_unsigned_printed(1000000000. * tpumpreal), as_unsigned_printed(100. * fabs(detuning)),
+           as_unsigned_printed(100. * Om), as_unsigned_printed(10. * n));  // MC408L:1153
+  dir += namebuf;
+  mkdir(dir.c_str(), 0777);
+  snprintf(namebuf, sizeof(namebuf), "/job%d/", (int)job);
+  dir += namebuf;
+  mkdir(dir.c_str(), 0777);
+
+  mdqt_params p;
+  CKP(mdqt_params_md(&p, MDQT_SCHEME_SR7, N, kappa, n, timeStep, detuning, Om, atoi(opt["quad"].c_str())));
+  p.traj0 = (int)job; p.seed = seed; p.device = atoi(opt["device"].c_str());
+  const double L = p.L;
+  // init() (MC408L:196-250): per lattice site three normal draws (mt19937), then rand1..rand4 from drand48 in its default state
+  std::mt19937 rng(seed);
+  std::normal_distribution<double> velocityDistribution(0, sqrt(1 / Gamma));
+  unsigned short xs[3] = {0x330E, 0xABCD, 0x1234};  // the initial state of an unseeded drand48 (the reference never calls srand48, Q14)
+  std::vector<double> R((size_t)3 * N, 0.0), V((size_t)3 * N, 0.0), psi((size_t)N * 14, 0.0);
+  {
+    int N0 = 0;
+    const int side = (int)round(pow(N, 1. / 3));
+    for (int i = 0; i < side; i++)
+      for (int j = 0; j < side; j++)
+        for (int k = 0; k < side; k++) {
+          if (N0 >= N) break;
+          R[N0] = i * L / pow(N, 1 / 3.) + 0.5; R[(size_t)N + N0] = j * L / pow(N, 1 / 3.) + 0.5; R[(size_t)2 * N + N0] = k * L / pow(N, 1 / 3.) + 0.5;
+          V[N0] = velocityDistribution(rng); V[(size_t)N + N0] = velocityDistribution(rng); V[(size_t)2 * N + N0] = velocityDistribution(rng);
+          const double rand1 = erand48(xs), rand2 = erand48(xs), rand3 = erand48(xs);
+          const double sign = rand3 < 0.5 ? -1 : 1;
+          const double rand4 = erand48(xs);
+          const double sign2 = rand4 < 0.5 ? -1 : 1;
+          double* w = &psi[(size_t)N0 * 14];
+          w[0] = sqrt(rand1); w[2] = sign2 * sqrt(1 - rand1) * sqrt(rand2); w[3] = sign * sqrt(1 - rand1) * sqrt(1 - rand2);
+          N0++;
+        }
+    if (N0 != N) { fprintf(stderr, "mdqt_run: N must be a cube (the reference's lattice init, MC408L:79)\n"); return 2; }
+  }
+  mdqt_handle* h = NULL;
+  CKP(mdqt_create(&p, &h));
+  CKP(mdqt_upload_state(h, R.data(), V.data(), psi.data(), NULL, N));
+  const double sigma_v = sqrt(1 / Gamma), rmax = L / 2;
+  auto wall0 = std::chrono::steady_clock::now();
+  if (preSteps > 0) CKP(mdqt_vv_steps(h, preSteps, 0, timeStep, collFreq, sigma_v, 0, 0.0));           // step 4 (MC408L:1211-1219)
+  if (!quiet) printf("pumpMDTimeSteps=%d\nquantumStepsPerMD=%d\n", pumpSteps, p.substeps_per_md);        // MC408L:1225-1226
+  if (pumpSteps > 0) CKP(mdqt_vv_steps(h, pumpSteps, p.substeps_per_md, timeStep, 0.0, sigma_v, 0, 0.0));  // step 5 (MC408L:1227-1232)
+  std::vector<int32_t> spin(N);
+  int32_t nup = 0;
+  CKP(mdqt_tag_particles(h, spin.data(), &nup));                                                         // tagParticles()
+  if (recSteps > 0) {
+    std::vector<uint8_t> tags(N);
+    for (int i = 0; i < N; i++) tags[i] = spin[i] ? 1 : 0;
+    CKP(mdqt_set_tags(h, tags.data()));
+    CKP(mdqt_moments_begin(h, recSteps));
+    CKP(mdqt_vstore_begin(h, recSteps));
+    std::vector<double> pv(4001);
+    for (int k = 0; k < recSteps; k++) {  // step 6 (MC408L:1235-1244)
+      CKP(mdqt_moments_record(h, k));     // recordTaggedParticleMoments(k): the moments; recordTemperature()
+      CKP(mdqt_vel_dist_tagged(h, pv.data()));
+      char name[64];
+      snprintf(name, sizeof(name), "vel_distX_timestep%06d.dat", k);
+      FILE* fa = open_in(dir, name, "w");
+      for (int j = 0; j < 4001; j++) fprintf(fa, "%lg\t%lg\n", (double)(j - 2000) * 0.0025, pv[j]);      // MC408L:1131-1134
+      fclose(fa);
+      if (k % 100 == 0) { if (!quiet) printf("%d\n", k); write_gr(h, dir, k, pairPairStep, rmax); }
+      CKP(mdqt_vv_step(h, timeStep, 0.0, sigma_v, 0, 0.0));
+      CKP(mdqt_vstore_record(h, k));
+    }
+    std::vector<double> rec((size_t)recSteps * 23);
+    CKP(mdqt_moments_download(h, rec.data(), recSteps));
+    FILE* fm = open_in(dir, "taggedMoments.dat", "a");
+    FILE* ft = open_in(dir, "temperature.dat", "a");
+    for (int k = 0; k < recSteps; k++) {
+      const double* r = &rec[(size_t)k * 23];
+      const double cnt = r[3];
+      fprintf(fm, "%lg\t%lg\t%lg\t%lg\t%lg\n", k * timeStep, r[4] / cnt, r[5] / cnt, r[6] / cnt, r[7] / cnt);  // MC408L:1106-1115
+      fprintf(ft, "%lg\n", (r[0] + r[1] + r[2]) / (3.0 * N));
+    }
+    fclose(fm); fclose(ft);
+    std::vector<double> ac[4];
+    for (auto& a : ac) a.resize(recSteps);
+    CKP(mdqt_autocorrelations(h, Gamma, ac[0].data(), ac[1].data(), ac[2].data(), ac[3].data()));  // step 7
+    static const char* acn[4] = {"VAF.dat", "longViscAutoCorr.dat", "vCubeAutoCorr.dat", "vFourthAutoCorr.dat"};
+    for (int s = 0; s < 4; s++) {
+      FILE* fa = open_in(dir, acn[s], "w");
+      for (int tD = 0; tD < recSteps; tD++) fprintf(fa, "%lg\t%lg\n", tD * timeStep, ac[s][tD]);
+      fclose(fa);
+    }
+  }
+  CKP(mdqt_sync(h));
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  if (!quiet)
+    fprintf(stderr, "mdqt_run: program mc408l, job %u, N=%d: %d collisional + %d pump (x %d qstep) + %d recorded MD steps, %d of %d ions tagged, %.3f s; files in %s\n",
+            job, N, preSteps, pumpSteps, p.substeps_per_md, recSteps, (int)nup, N, wall, dir.c_str());
   mdqt_destroy(h);
   return 0;
 }

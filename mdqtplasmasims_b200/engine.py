@@ -49,7 +49,7 @@ ABI_SYMBOLS = [
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
     "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces", "mdqt_comm_unique_id", "mdqt_comm_init", "mdqt_comm_destroy",
     "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows", "mdqt_download_rows", "mdqt_set_tags", "mdqt_moments_begin", "mdqt_moments_record",
-    "mdqt_moments_download", "mdqt_scale_velocities",
+    "mdqt_moments_download", "mdqt_scale_velocities", "mdqt_vel_dist_tagged",
 ]
 
 _lib = None
@@ -126,6 +126,7 @@ def load_library():
     L.mdqt_moments_record.argtypes = [vp, ctypes.c_int]
     L.mdqt_moments_download.argtypes = [vp, vp, ctypes.c_int]
     L.mdqt_scale_velocities.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+    L.mdqt_vel_dist_tagged.argtypes = [vp, vp]
     L.mdqt_time_forces.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_traj_seeds.argtypes = [vp, vp]
     L.mdqt_diag_partial.argtypes = [vp, vp, vp]
@@ -473,6 +474,11 @@ class Engine:
         out = np.empty((nslots,) + self._lead() + (23,))
         self._ck(self.lib.mdqt_moments_download(self.h, _ptr(out), nslots))
         return out
+
+    def vel_dist_tagged(self):
+        p = np.empty(self._lead() + (4001,))
+        self._ck(self.lib.mdqt_vel_dist_tagged(self.h, _ptr(p)))
+        return p
 
     def scale_velocities(self, sx, sy, sz):
         self._ck(self.lib.mdqt_scale_velocities(self.h, sx, sy, sz))

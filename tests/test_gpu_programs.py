@@ -117,3 +117,47 @@ def test_fz408l_program_files_match_the_python_loop(tmp_path):
     assert tm.shape == (len(events), 5)
     assert any(f.startswith("vel_distX_timestep") for f in files)
     e.close()
+
+
+def test_vel_dist_tagged_vs_numpy():
+    """mdqt_vel_dist_tagged against the formula of recordTaggedParticleMoments (MC408L:1097-1125): Gaussian weights of width 0.002 on
+    4001 bins of 0.0025 centred on 0, tagged ions only, / (6 sqrt(2 pi 0.002^2))."""
+    n = 512
+    rng = np.random.default_rng(8)
+    V = rng.normal(size=(3, n)) * 0.4
+    tags = (rng.uniform(size=n) < 0.4).astype(np.uint8) | ((rng.uniform(size=n) < 0.5).astype(np.uint8) << 1)
+    e = Engine(md_params(scheme=SCHEME_NONE, n_ions=n))
+    e.upload(R=rng.uniform(0, e.params.L, size=(3, n)), V=V)
+    e.set_tags(tags)
+    pv = e.vel_dist_tagged()
+    vel = (np.arange(4001) - 2000) * 0.0025
+    vt = V[0][(tags & 1).astype(bool)]
+    want = np.exp(-(vel[:, None] - vt[None, :]) ** 2 / (2 * 0.002 ** 2)).sum(axis=1) / (6.0 * np.sqrt(2 * np.pi * 0.002 ** 2))
+    assert np.allclose(pv, want, rtol=1e-12, atol=1e-300)
+    e.close()
+
+
+def test_mc408l_program_writes_consistent_files(tmp_path):
+    """`mdqt_run --program mc408l` (collisional MD, pump, spin measurement, recording stage): the files exist in the reference's
+    shapes, and the two things it writes about the tagged ions agree with each other -- the integral of vel_distX_timestep k is
+    numTagged / 6, and its first and second moments are the taggedMoments.dat row k."""
+    save = str(tmp_path) + "/"
+    r = subprocess.run([DRIVER, "--program", "mc408l", "3", "--N", "512", "--seed", "17", "--preSteps", "20", "--pumpSteps", "6", "--recordSteps", "12",
+                        "--saveDirectory", save, "--quiet"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    d = os.path.join(save, "Gamma300Kappa50NumIons512PumpTime200Det250Om70Density20", "job3")
+    assert os.path.isdir(d), os.listdir(save)
+    tm = _table(open(os.path.join(d, "taggedMoments.dat")).read())
+    assert tm.shape == (12, 5) and np.allclose(tm[:, 0], np.arange(12) * 0.005)
+    assert _table(open(os.path.join(d, "temperature.dat")).read()).shape == (12, 1)
+    assert os.path.exists(os.path.join(d, "pairPairCorrStepNum0.dat"))
+    for f in ("VAF.dat", "longViscAutoCorr.dat", "vCubeAutoCorr.dat", "vFourthAutoCorr.dat"):
+        assert _table(open(os.path.join(d, f)).read()).shape == (12, 2)
+    for k in (0, 11):
+        pv = _table(open(os.path.join(d, "vel_distX_timestep%06d.dat" % k)).read())
+        assert pv.shape == (4001, 2)
+        ntag = pv[:, 1].sum() * 0.0025 * 6
+        assert abs(ntag - round(ntag)) < 1e-3 and 0.2 * 512 < ntag < 0.8 * 512     # an integer number of spin-up ions, roughly half
+        m1 = (pv[:, 0] * pv[:, 1]).sum() / pv[:, 1].sum()
+        m2 = (pv[:, 0] ** 2 * pv[:, 1]).sum() / pv[:, 1].sum() - 0.002 ** 2         # minus the kernel's own variance
+        assert abs(m1 - tm[k, 1]) < 2e-5 and abs(m2 - tm[k, 2]) < 2e-5 * max(1.0, tm[k, 2])
