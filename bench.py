@@ -513,7 +513,7 @@ def run_reference(args):
     # reports what was run: ms_per_step is the measured wall time of a step of m MD steps, value = N x 25 x m / that
     t0 = time.perf_counter()
     try:
-        d = cpu_reference_run(threads, budget_s=150.0, steps=K + W)
+        d = cpu_reference_run(threads, budget_s=float(os.environ.get("MDQT_REF_BUDGET_S", "150")), steps=K + W)
     except Exception as e:  # pragma: no cover
         print(json.dumps({"impl": "reference", "unavailable": "CPU reference run failed: %r" % (e,)}), flush=True)
         return

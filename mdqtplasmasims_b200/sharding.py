@@ -71,3 +71,41 @@ def distributed_diagnostics(engine, n_ions, dist, want_vel_dist=False):
     if want_vel_dist:
         out["pvel"] = allreduce_scalars(engine.vel_dist_partial(mean), dist)
     return out
+
+
+# ---- the exchange of the row-decomposed step inside the library (csrc/mdqt_comm.cu), mirrored on the host for the CPU tests -------
+def row_block_ceil(n_ions, world, rank):
+    """(row0, n_rows, R) as mdqt_comm_init expects them: R = ceil(N / world) rows per rank, the last rank holds the remainder."""
+    R = (n_ions + world - 1) // world
+    row0 = rank * R
+    return row0, max(0, min(R, n_ions - row0)), R
+
+
+def pack_rows(X, row0, n_rows, R):
+    """k_pack_rows: the rank's own rows of a ``[3][ld]`` array as one contiguous ``[3][R]`` block, zero padded."""
+    blk = np.zeros((3, R), dtype=X.dtype)
+    blk[:, :n_rows] = X[:, row0:row0 + n_rows]
+    return blk
+
+
+def unpack_rows(xbuf, X, n_ions, skip):
+    """k_unpack_rows: ``xbuf[g][c][i]`` -> ``X[c][g*R + i]`` for every rank g but `skip`, rows beyond n_ions dropped."""
+    G, _, R = xbuf.shape
+    for g in range(G):
+        if g == skip:
+            continue
+        lo, hi = g * R, min(n_ions, (g + 1) * R)
+        if hi > lo:
+            X[:, lo:hi] = xbuf[g, :, :hi - lo]
+    return X
+
+
+def exchange_rows(X, n_ions, world, rank, dist):
+    """One in-place all-gather of a [3][R] block per rank into the rank-major buffer, then the unpack: what mdqt_md_steps does
+    once per MD step with the fixed-point positions (ncclAllGather there, any torch.distributed backend here)."""
+    import torch
+    row0, n_rows, R = row_block_ceil(n_ions, world, rank)
+    own = torch.from_numpy(np.ascontiguousarray(pack_rows(X, row0, n_rows, R))).reshape(-1)
+    xbuf = torch.zeros(world * 3 * R, dtype=own.dtype)
+    dist.all_gather_into_tensor(xbuf, own)
+    return unpack_rows(xbuf.numpy().reshape(world, 3, R), X, n_ions, rank)

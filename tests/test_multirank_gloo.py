@@ -96,3 +96,35 @@ def test_partition_helpers():
     assert sharding.padded_ions(3500, 8) == 3504
     assert [len(sharding.ensemble_jobs(512, 8, r)) for r in range(8)] == [64] * 8
     assert sharding.ensemble_jobs(5, 2, 0) == [1, 2, 3] and sharding.ensemble_jobs(5, 2, 1) == [4, 5]
+
+
+def _worker_exchange(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mdqtplasmasims_b200 import sharding
+    rng = np.random.default_rng(7)
+    truth = rng.integers(-2 ** 62, 2 ** 62, size=(3, n), dtype=np.int64)   # fixed-point positions after the step, all ranks' rows
+    row0, n_rows, R = sharding.row_block_ceil(n, world, rank)
+    X = np.full((3, ((n + 31) // 32) * 32), -1, dtype=np.int64)             # this rank knows only its own rows
+    X[:, row0:row0 + n_rows] = truth[:, row0:row0 + n_rows]
+    sharding.exchange_rows(X, n, world, rank, dist)
+    ok = np.array_equal(X[:, :n], truth) and np.all(X[:, n:] == -1)
+    blocks = [sharding.row_block_ceil(n, world, r)[:2] for r in range(world)]
+    cover = sum(b[1] for b in blocks) == n and all(blocks[r][0] + blocks[r][1] == (blocks[r + 1][0] if r + 1 < world else n) or blocks[r][1] == 0
+                                                    for r in range(world))
+    np.save(os.path.join(out_dir, "x%d.npy" % rank), np.array([ok, cover]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 1000), (4, 1201)])
+def test_row_exchange_protocol_with_unequal_blocks(tmp_path, world, n):
+    """The exchange protocol of csrc/mdqt_comm.cu (pack own rows -> ONE all-gather of padded [3][R] blocks -> unpack the remote rows),
+    mirrored in sharding.py: with R = ceil(N / world) and a shorter last block, every rank ends with everybody's rows and nothing
+    else is written. gloo, CPU tensors, int64 payload (the fixed-point positions)."""
+    port = _free_port()
+    mp.spawn(_worker_exchange, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(os.path.join(str(tmp_path), "x%d.npy" % r)).all()
