@@ -43,6 +43,21 @@ namespace mdqt {
 #ifndef MDQT_VALID_INT
 #define MDQT_VALID_INT 1
 #endif
+//   MDQT_RSQRT_ORDER 3 (default): MUFU.RSQ64H seed + one third-order step (1/r to 1e-16).
+//                    2: 1/r and r from ONE coupled second-order step on a seed for 1/sqrt(2 r^2) (4 FP64 + 1 integer instruction
+//                       instead of 6 FP64). Measured on B200 (profiles/r02o_ab_pairs.log): +6.0 % at N = 1e5 (5.60e11 pairs/s),
+//                       +8.3 % at 64 trajectories, K1 28.6 -> 26.9 us at N = 3500 -- but the seed only sees the HIGH word of r^2
+//                       (relative input error up to 2^-20), so the second-order remainder 3/8 e^2 reaches 3.4e-13 in 1/r and the
+//                       per-ion force error 5e-13 ... 9.5e-13 of sum_j |f_ij| (third order: 3e-16 ... 8e-16): no margin against the
+//                       1e-12 parity budget. NOT taken; kept as a build option for the record.
+//   MDQT_PRED_ACC    1: the cut-off predicate guards the three accumulating FMAs instead of zeroing f with a 64-bit select. ptxas
+//                       turns the predicated FMAs back into selects on each accumulator (6 FSEL per pair instead of 2): off.
+#ifndef MDQT_RSQRT_ORDER
+#define MDQT_RSQRT_ORDER 3
+#endif
+#ifndef MDQT_PRED_ACC
+#define MDQT_PRED_ACC 0
+#endif
 constexpr int kExpShift = (kExpTable == 1024) ? 10 : 13;  // 20 - log2(kExpTable)
 static_assert(kExpTable == 128 || kExpTable == 1024, "exp table must have 128 or 1024 entries");
 
@@ -91,9 +106,16 @@ struct PairConsts {
 __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot) {
   PairConsts c;
   const double u = a.L / MDQT_2P64;
-  c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
   const double T = (double)kExpTable;
+#if MDQT_RSQRT_ORDER == 2
+  // the pair loop works with r/sqrt2 and 1/(sqrt2 r) (pair_core): kappa and the output scale absorb the factors
+  const double s2 = 1.4142135623730950488016887242096981;
+  c.kappa_u = a.kappa * u / s2; c.negkappa_u = -(a.kappa * u) * s2;
+  c.nk_scale = -(a.kappa * u) * s2 * (T * 1.4426950408889634073599246810018921);
+#else
+  c.kappa_u = a.kappa * u; c.negkappa_u = -c.kappa_u;
   c.nk_scale = -c.kappa_u * (T * 1.4426950408889634073599246810018921);  // T * log2(e)
+#endif
   c.negc = -0.69314718055994530941723212145817657 / T;                   // -ln2 / T
 #if MDQT_EXP_SCALED
   const double w = 0.69314718055994530941723212145817657 / T;            // polynomial in rr' = rr / w
@@ -103,6 +125,9 @@ __device__ __forceinline__ PairConsts make_consts(const ForceArgs& a, bool epot)
 #endif
   c.rc2_u = a.rc2_u;                                 // (rcut/u)^2, or 2^126 = (L/2)^2 exactly: formed on the host (no sqrt /
   c.out_scale = epot ? a.inv_u : a.inv_u * a.inv_u;  // division in every thread's prologue)
+#if MDQT_RSQRT_ORDER == 2
+  c.out_scale *= epot ? s2 : 2.0 * s2;               // u = ef / (sqrt2 r) sqrt2;  f = ef (1/r + kappa) / r^2 = 2 sqrt2 ef y^2 (y + kappa/sqrt2)
+#endif
   return c;
 }
 
@@ -112,6 +137,17 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
                                           bool& valid) {
   if (HL) valid = (unsigned)(__double2hiint(r2) - 1) < 0x47D00000u - 1u;  // 0 < r2 < 2^126 on the high word alone
   else valid = (r2 < c.rc2_u) && (__double2hiint(r2) != 0);  // one DSETP + one ISETP (r2 > 0 <=> high word != 0; SU:222)
+#if MDQT_RSQRT_ORDER == 2
+  // Seed w ~ 1/sqrt(2 r2): MUFU.RSQ64H reads the high word only, so doubling its argument is one integer add on that word.
+  // With g = r2 w ~ r/sqrt2 the residual h = 1/2 - g w = (1 - 2 r2 w^2)/2 is exact to rounding, and ONE coupled step gives
+  // both r/sqrt2 = g (1 + h) and 1/(sqrt2 r) = w (1 + h) to second order (the sqrt2 factors live in the constants).
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(__double2hiint(r2) + 0x00100000, 0)));
+  const double g = r2 * y;
+  const double h = fma(-g, y, 0.5);
+  const double r = fma(g, h, g);
+  y = fma(y, h, y);
+#else
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));  // MUFU.RSQ64H seed
   double t = r2 * y;
@@ -120,6 +156,7 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
   double ye = y * e;
   y = fma(ye, p, y);                          // y (1 + e/2 + 3 e^2/8): the scheme of CUDA's own rsqrt(double)
   double r = r2 * y;
+#endif
   // exp(x), x = -kappa r <= 0:  x = (128 q + idx) ln2/128 + rr
   double tt = fma(r, c.nk_scale, MDQT_MAGIC);
   int n = __double2loint(tt);
@@ -152,6 +189,26 @@ __device__ __forceinline__ void pair_core(double r2, const PairConsts& c, const 
   int hi = __double2hiint(T) + (n << kExpShift);  // table high words carry -(idx << kExpShift): net += floor(n/T) << 20
   ef = __hiloint2double(hi, __double2loint(T)) * q;
   rinv = y;
+}
+
+// F += f * delta for a pair inside the cut-off (0 < r2 < rc2 as ONE predicate: r2 < 2^126 on the high word alone when HL, else
+// one DSETP; the self pair needs none, see k_pairs).
+template <bool HL>
+__device__ __forceinline__ void accumulate_if_inside(double& ax, double& ay, double& az, double f, double dx, double dy, double dz,
+                                                     double r2, double rc2) {
+#if MDQT_PRED_ACC
+  // the predicate guards the three FMAs (predicated DFMA): no select on the 64-bit f
+  const bool inside = HL ? ((unsigned)__double2hiint(r2) < 0x47D00000u) : (r2 < rc2);
+  if (inside) { ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az); }
+#else
+  if (HL)
+    asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
+        : "+d"(f) : "r"(__double2hiint(r2)));
+  else
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
+        : "+d"(f) : "d"(r2), "d"(rc2));
+  ax = fma(f, dx, ax); ay = fma(f, dy, ay); az = fma(f, dz, az);
+#endif
 }
 
 constexpr int kTJ = 512;  // j positions staged per pass
@@ -289,15 +346,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
         } else {
           double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);  // (1/r + 1/lDeb) exp(-r/lDeb)/r^2 (SU:224)
           // 0 < r2 < rc2 as ONE predicate (DSETP, then ISETP chained with .and) and one select
-          if (HL)  // r2 < 2^126 on the high word alone
-            asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
-                : "+d"(f) : "r"(__double2hiint(r2)));
-          else
-            asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
-                : "+d"(f) : "d"(r2), "d"(c.rc2_u));
-          ax[k] = fma(f, dx, ax[k]);
-          ay[k] = fma(f, dy, ay[k]);
-          az[k] = fma(f, dz, az[k]);
+          accumulate_if_inside<HL>(ax[k], ay[k], az[k], f, dx, dy, dz, r2, c.rc2_u);
         }
       }
     }
@@ -590,13 +639,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
           ax[r] += valid ? u : 0.0;
         } else {
           double f = (ef * (rinv * rinv)) * (rinv + c.kappa_u);
-          if (HL)
-            asm("{\n\t.reg .pred q;\n\tsetp.lt.u32 q, %1, 0x47D00000;\n\tselp.f64 %0, %0, 0d0000000000000000, q;\n\t}"
-                : "+d"(f) : "r"(__double2hiint(r2)));
-          else
-            asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %0, 0d0000000000000000, p;\n\t}"
-                : "+d"(f) : "d"(r2), "d"(c.rc2_u));
-          ax[r] = fma(f, dx, ax[r]); ay[r] = fma(f, dy, ay[r]); az[r] = fma(f, dz, az[r]);
+          accumulate_if_inside<HL>(ax[r], ay[r], az[r], f, dx, dy, dz, r2, c.rc2_u);
         }
       }
     }
