@@ -1001,7 +1001,7 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
       const double f = load_force1_impl(a.fpart, a.Fw, a.F, a.nb ? a.nb[b] : a.N, a.fp_jlen, a.B, a.ld, b, i, q, active ? 1 : 0);
       chunk_put(&c_f[me], f, 1ull);
     }
-    // populations and kick partials of y: published for substep 0 here, then after every RK step for the next one
+    // populations and kick partials of y(s), for S's jump test and kick of substep s
     auto publish = [&](int s) {
       const double pn = half ? cnorm(y[0]) : cnorm(y[1]);
       const cplx r0 = {__shfl_xor_sync(0xffffffffu, y[0].re, 1), __shfl_xor_sync(0xffffffffu, y[0].im, 1)};
@@ -1012,29 +1012,22 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
       chunk_put(&c_pn[s & 1][me], pn, (unsigned long long)(s + 1));
       chunk_put(&c_kp[s & 1][me], kick, (unsigned long long)(s + 1));
     };
-    if (a.nsub > 0) publish(0);
-    for (int s = 0; s <= a.nsub; s++) {
-      // {H(s), outcome of substep s-1} from S: five chunks of this lane's type, polled until all carry tag s+1
+    // {H(s), outcome of substep s-1} from S: the five chunks of this lane's type. S writes them a whole RK step ahead, so they
+    // are FETCHED during stage 3 of the step before (no waiting) and only validated here; polled if a tag is not there yet.
+    double v0, v1, v2, v3, v4;
+    unsigned long long m0, m1, m2, m3, m4;
+    auto fetch = [&](int s) {
       const Chunk* hs = (s & 1) ? hsrc1 : hsrc0;
-      double v0, v1, v2, v3, v4;
-      unsigned long long m4;
-      DOG_DECL
-      for (;;) {
+      m0 = chunk_get(hs + half * 3 + 0, v0); m1 = chunk_get(hs + half * 3 + 1, v1); m2 = chunk_get(hs + half * 3 + 2, v2);
+      m3 = chunk_get(hs + 6 + blk * 2, v3); m4 = chunk_get(hs + 7 + blk * 2, v4);
+    };
+    fetch(0);
+    for (int s = 0; s <= a.nsub; s++) {
+      {
         const unsigned tag = (unsigned)(s + 1);
-        m4 = chunk_get(hs + 7 + blk * 2, v4);  // spin on ONE chunk (the last of this lane's five that S writes) ...
-        DOG(1, tag, m4)
-#if MDQT_WS_VARIANT == 2
-        if (!__all_sync(0xffffffffu, (unsigned)m4 == tag)) { __nanosleep(32); continue; }
-#elif MDQT_WS_VARIANT == 3
-        if ((unsigned)m4 != tag) continue;  // per-lane spin; the warp re-joins below
-        __syncwarp();
-#else
-        if (!__all_sync(0xffffffffu, (unsigned)m4 == tag)) continue;
-#endif
-        const unsigned long long m0 = chunk_get(hs + half * 3 + 0, v0), m1 = chunk_get(hs + half * 3 + 1, v1);
-        const unsigned long long m2 = chunk_get(hs + half * 3 + 2, v2), m3 = chunk_get(hs + 6 + blk * 2, v3);
-        const bool ok = (unsigned)m0 == tag && (unsigned)m1 == tag && (unsigned)m2 == tag && (unsigned)m3 == tag;
-        if (__all_sync(0xffffffffu, ok)) break;  // ... then take the others, each validated by its own tag
+        while (!__all_sync(0xffffffffu, (unsigned)m0 == tag && (unsigned)m1 == tag && (unsigned)m2 == tag && (unsigned)m3 == tag &&
+                                            (unsigned)m4 == tag))
+          fetch(s);
       }
       K2TRACE(warp, 0)
       const int dest = (int)(m4 >> 32) - 1;
@@ -1043,8 +1036,14 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
         for (int k = 0; k < 3; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
       }
       if (s == a.nsub) break;
-      H.hE0 = v0; H.hE1 = v1; H.hE2 = v2;
+      H.hE1 = v1; H.hE2 = v2;
       if (half) { H.a01r = v3; H.a01i = -v4; H.a10r = v3; H.a10i = v4; }
+      publish(s);
+      // hE0 is taken again from its chunk AFTER the publishing stores (volatile accesses keep their order), so that the stages
+      // depend on something behind those stores: ptxas otherwise sinks them below stage 3 (they have no consumer in this warp)
+      // and S gets its input three stages late
+      chunk_get(((s & 1) ? hsrc1 : hsrc0) + half * 3 + 0, v0);
+      H.hE0 = v0;
       {
         cplx w[3], g[3], acc[3];
         stage4(H, y, g);
@@ -1062,6 +1061,7 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
           acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
           w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
         }
+        fetch(s + 1);
         stage4(H, w, g);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -1069,7 +1069,7 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
           y[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
         }
       }
-      if (a.renorm) {  // of the no-jump result; a jumped ion restarts from a unit basis state, which this leaves as it is
+      if (a.renorm) {
         double own = cnorm(y[0]) + cnorm(y[1]) + cnorm(y[2]);
         own += __shfl_xor_sync(0xffffffffu, own, 1);
         own += __shfl_xor_sync(0xffffffffu, own, 2);
@@ -1078,8 +1078,6 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
         for (int k = 0; k < 3; k++) { y[k].re /= nn; y[k].im /= nn; }
       }
       K2TRACE(warp, 1)
-      if (s + 1 < a.nsub) publish(s + 1);
-      K2TRACE(warp, 2)
     }
     pdl_launch_dependents();
     if (lane == 0) stamp_time(a.stamp, 1);
@@ -1093,7 +1091,6 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
   const int rw = lane >> 3;  // the R warp this lane serves, and its ion there
   if (rw >= RW) return;
   const unsigned smask = RW >= 4 ? 0xffffffffu : ((1u << (8 * RW)) - 1u);  // the lanes of this warp that stay
-  (void)smask;
   const long long slot = (long long)(blockIdx.x * RW + rw) * 8 + (lane & 7);
   const bool inrange = slot < (long long)a.nrows * a.B;
   const int b = inrange ? (int)(slot / a.nrows) : 0;
@@ -1172,55 +1169,25 @@ __global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QT
       const uint4 o2 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
       u0 = u52(o0.x, o0.y); u1 = u52(o0.z, o0.w); u2 = u52(o1.x, o1.y); u3 = u52(o1.z, o1.w); u4 = u52(o2.x, o2.y);
     }
-    // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4. After a
-    // jump the ion sits in an S or D basis state: populations and coherences are 0, whatever R published from the discarded yn
-    double n3 = 0.0, n5 = 0.0, n2 = 0.0, n4 = 0.0, kick = 0.0;
-#if MDQT_WS_VARIANT == 1 || MDQT_WS_VARIANT == 3
-    {  // every lane takes R's chunks every substep (lock step with R whatever happened), warp-uniform spin
-      const unsigned tag = (unsigned)(s + 1);
-      const Chunk* cp = &c_pn[s & 1][quad];
-      const Chunk* ck = &c_kp[s & 1][quad];
-      double ka, kb, kc, kd, a3, a5, a2, a4;
-      for (;;) {
-        const unsigned long long md = chunk_get(ck + 3, kd);
-        if (!__all_sync(smask, (unsigned)md == tag)) continue;
-        const unsigned long long m0 = chunk_get(cp + 0, a3), m1 = chunk_get(cp + 1, a5), m2 = chunk_get(cp + 2, a2), m3 = chunk_get(cp + 3, a4);
-        const unsigned long long m4 = chunk_get(ck + 0, ka), m5 = chunk_get(ck + 1, kb), m6 = chunk_get(ck + 2, kc);
-        const bool ok = (unsigned)m0 == tag && (unsigned)m1 == tag && (unsigned)m2 == tag && (unsigned)m3 == tag && (unsigned)m4 == tag &&
-                        (unsigned)m5 == tag && (unsigned)m6 == tag;
-        if (__all_sync(smask, ok)) break;
-      }
-      if (dest_prev < 0) {
-        n3 = a3; n5 = a5; n2 = a2; n4 = a4;
-        kick = ka + kb;   // the quad's total in the order of k_substeps4's shuffle tree: (own + neighbour) + (the other pair's sum)
-        kick += kc + kd;
-      }
-    }
-#else
-    if (dest_prev < 0) {
+    // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
+    double n3, n5, n2, n4, kick;
+    {  // every lane takes its quad's chunks every substep; warp-uniform spin (a per-lane, divergent spin here hung intermittently on B200)
       const unsigned tag = (unsigned)(s + 1);
       const Chunk* cp = &c_pn[s & 1][quad];
       const Chunk* ck = &c_kp[s & 1][quad];
       double ka, kb, kc, kd;
-      DOG_DECL
       for (;;) {
-        const unsigned long long md = chunk_get(ck + 3, kd);
-        DOG(2, tag, md)
-#if MDQT_WS_VARIANT == 2
-        if ((unsigned)md != tag) { __nanosleep(32); continue; }
-#else
-        if ((unsigned)md != tag) continue;  // spin on the last chunk the quad writes, then take and validate all
-#endif
-        const unsigned long long m0 = chunk_get(cp + 0, n3), m1 = chunk_get(cp + 1, n5), m2 = chunk_get(cp + 2, n2), m3 = chunk_get(cp + 3, n4);
-        const unsigned long long m4 = chunk_get(ck + 0, ka), m5 = chunk_get(ck + 1, kb), m6 = chunk_get(ck + 2, kc);
-        if ((unsigned)m0 == tag && (unsigned)m1 == tag && (unsigned)m2 == tag && (unsigned)m3 == tag && (unsigned)m4 == tag &&
-            (unsigned)m5 == tag && (unsigned)m6 == tag)
-          break;
+        const unsigned long long md = chunk_get(ck + 3, kd);  // the last chunk the quad writes ...
+        if (!__all_sync(smask, (unsigned)md == tag)) continue;
+        const unsigned long long q0 = chunk_get(cp + 0, n3), q1 = chunk_get(cp + 1, n5), q2 = chunk_get(cp + 2, n2), q3 = chunk_get(cp + 3, n4);
+        const unsigned long long q4 = chunk_get(ck + 0, ka), q5 = chunk_get(ck + 1, kb), q6 = chunk_get(ck + 2, kc);
+        const bool ok = (unsigned)q0 == tag && (unsigned)q1 == tag && (unsigned)q2 == tag && (unsigned)q3 == tag && (unsigned)q4 == tag &&
+                        (unsigned)q5 == tag && (unsigned)q6 == tag;
+        if (__all_sync(smask, ok)) break;  // ... then the others, each validated by its own tag
       }
       kick = ka + kb;   // the quad's total in the order of k_substeps4's shuffle tree: (own + neighbour) + (the other pair's sum)
       kick += kc + kd;
     }
-#endif
     K2TRACE(rw, 4)
     const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;
     const bool jump = !(u0 > dp0);
