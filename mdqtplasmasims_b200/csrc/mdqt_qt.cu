@@ -21,7 +21,6 @@
 #include "mdqt_qtconsts.h"
 #include "mdqt_fixed.cuh"
 #include <math.h>
-#include <algorithm>
 #include <stdlib.h>
 
 namespace mdqt {
@@ -875,360 +874,6 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
 }
 
 
-// ------------------------------------------------------------------------------------------------------------
-// Four lanes per ion, WARP-SPECIALISED (the one-trajectory form: a few hundred warps, at most one per SM sub-partition, each
-// bound by its own in-order instruction stream -- 643 instructions and ~1850 cycles per warp-substep in k_substeps4, of which
-// only ~1050 are issue cycles). Per substep the wavefunction y(s) enters everything else only through two cheap numbers, the
-// optical-force kick and the jump probability dp0, both functions of y(s) at the START of the substep (SU:503, 519); and the
-// Hamiltonian of substep s+1 depends on the velocity after THAT kick, not on y(s+1). So the per-ion scalar recurrence
-// (step(), Doppler shift, rotating phase with its sin/cos, Philox, the jump test and its branch) can run AHEAD of the
-// Runge-Kutta chain, in another warp. A CTA is RW (3 or 4) Runge-Kutta warps and ONE scalar warp on the SM's four sub-partitions:
-//   warp R_r (lanes as in k_substeps4: 8 ions x 4 quarter-blocks): holds y. Per substep: take {H(s), jump outcome of s-1} from S,
-//           run the four RK stages, and publish the P populations and kick partials of the result -- speculatively, i.e. of
-//           yn(s) as if substep s did not jump (if it did, S knows: it decided, and a jumped ion's populations and kick are 0);
-//   warp S  (lane <-> one of the CTA's 8 RW ions): holds R, V, F, tPart, t, the uniforms. Per substep: from R's populations
-//           and partials the jump test and branch, the kick, then step() and the coefficients of substep s+1 for all four
-//           lane types -- hidden behind R's RK chain -- and Philox. One lane per ion: none of this is replicated four times.
-// Hand-over through shared memory in self-validating 16-byte chunks {value, tag}: written and read by ONE 128-bit access per
-// thread and polled by the consumer (a named barrier costs ~120 cycles per wake-up plus the warp-wide rendezvous; a poll costs one
-// shared-memory round trip). Every formula is evaluated by the same expressions as in k_substeps4, only by another warp: the
-// bits are those of k_substeps4 and of the two-lane kernel.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kWsMaxR = 4;
-#ifndef MDQT_WS_VARIANT
-#define MDQT_WS_VARIANT 3  // 0 and 2 (per-lane divergent spin in the scalar warp) hang intermittently on B200; 1 and 3 do not
-#endif
-struct __align__(16) Chunk { double v; unsigned long long meta; };
-__device__ __forceinline__ void chunk_put(Chunk* c, double v, unsigned long long meta) {
-  asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(c)), "l"(__double_as_longlong(v)), "l"(meta) : "memory");
-}
-__device__ __forceinline__ unsigned long long chunk_get(const Chunk* c, double& v) {
-  long long x;
-  unsigned long long m;
-  asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(m) : "r"((unsigned)__cvta_generic_to_shared(c)) : "memory");
-  v = __longlong_as_double(x);
-  return m;
-}
-// one force component of ion i: F itself, or the item kernel's partials added in ascending chunk order (k_sum_partials' formula)
-__device__ __noinline__ double load_force1_impl(const double* __restrict__ fpart, double* __restrict__ Fw, const double* __restrict__ F, int Nb,
-                                                int jlen, int B, int ld, int b, int i, int comp, int store) {
-  const size_t at = ((size_t)b * 3 + comp) * ld + i;
-  if (!fpart) return F[at];
-  const double f = sum_partials(fpart + at, (size_t)B * 3 * ld, (Nb + jlen - 1) / jlen);
-  if (store) Fw[at] = f;
-  return f;
-}
-#ifdef MDQT_K2_WATCHDOG  // developer build: a spin that does not end reports what it saw and gives up
-__device__ unsigned long long g_k2dog[64];
-#define DOG_DECL unsigned dog_ = 0;
-#define DOG(site, want, seen)                                                                                                  \
-  if (++dog_ > 2000000u) {                                                                                                     \
-    if (atomicAdd(&g_k2dog[0], 1ull) < 7) {                                                                                    \
-      const unsigned long long n_ = atomicAdd(&g_k2dog[1], 1ull);                                                              \
-      if (n_ < 7) { g_k2dog[8 + n_ * 8] = site; g_k2dog[9 + n_ * 8] = blockIdx.x; g_k2dog[10 + n_ * 8] = threadIdx.x;          \
-                    g_k2dog[11 + n_ * 8] = (unsigned long long)(s); g_k2dog[12 + n_ * 8] = want; g_k2dog[13 + n_ * 8] = seen; }      \
-    }                                                                                                                          \
-    break;                                                                                                                     \
-  }
-#else
-#define DOG_DECL
-#define DOG(site, want, seen)
-#endif
-#ifdef MDQT_K2_TRACE  // developer build: SM-clock stamps of the hand-over points, CTA 0 (scripts/k2_ws_trace.py)
-__device__ long long g_k2trace[kWsMaxR * 32 * 8];
-#define K2TRACE(w, slot) \
-  if (blockIdx.x == 0 && lane == 0 && s < 32) g_k2trace[((w) * 32 + s) * 8 + slot] = clock64();
-#else
-#define K2TRACE(w, slot)
-#endif
-
-template <bool FORCED>
-__global__ void __launch_bounds__(32 * (kWsMaxR + 1)) k_substeps4ws(QTArgs a, QTConsts C) {
-  __shared__ Chunk c_pn[2][kWsMaxR * 32], c_kp[2][kWsMaxR * 32];  // R -> S: P population / kick partial of every R lane
-  __shared__ Chunk c_f[kWsMaxR * 32];                              // R -> S, once: force component x, y, z from quad lanes 0, 1, 2
-  __shared__ Chunk c_h[2][kWsMaxR * 8][10];  // S -> R per ion: hE0..2 of half 0, of half 1, (cr, ci) of block A, of block B
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int RW = (blockDim.x >> 5) - 1;
-  const double h = C.h;
-  const QTLane& LA = C.lane[0];
-  const QTLane& LB = C.lane[1];
-  // shared memory keeps whatever the previous CTA on this SM left there -- including chunks with exactly these tags: clear them
-  for (int k = threadIdx.x; k < 2 * kWsMaxR * 32; k += blockDim.x) { (&c_pn[0][0])[k].meta = 0; (&c_kp[0][0])[k].meta = 0; }
-  for (int k = threadIdx.x; k < kWsMaxR * 32; k += blockDim.x) c_f[k].meta = 0;
-  for (int k = threadIdx.x; k < 2 * kWsMaxR * 8 * 10; k += blockDim.x) (&c_h[0][0][0])[k].meta = 0;
-  __syncthreads();
-
-  if (warp < RW) {
-    // ---------------------------------------------------------------- warps R: the Runge-Kutta chain
-    const int gid = (blockIdx.x * RW + warp) * 32 + lane;
-    const int q = gid & 3, blk = q >> 1, half = q & 1;
-    const long long slot = gid >> 2;
-    const bool inrange = slot < (long long)a.nrows * a.B;
-    const int b = inrange ? (int)(slot / a.nrows) : 0;
-    const int i0 = inrange ? a.row0 + (int)(slot % a.nrows) : a.row0;
-    const bool active = inrange && i0 < (a.nb ? a.nb[b] : a.N);
-    const int i = active ? i0 : a.row0;
-    double* __restrict__ Pb = a.psi + (size_t)b * 24 * a.ld;
-#define LSEL(f) (blk ? LB.f : LA.f)
-    int map[3];
-    map[0] = half ? LSEL(map[2]) : LSEL(map[0]);
-    map[1] = half ? LSEL(map[4]) : LSEL(map[1]);
-    map[2] = half ? LSEL(map[5]) : LSEL(map[3]);
-    const double hc10 = h * LSEL(c10), hc20 = h * LSEL(c20), hc13 = h * LSEL(c13), hc14 = h * LSEL(c14), hc25 = h * LSEL(c25);
-    const double gam1 = LSEL(gam1), gam2 = LSEL(gam2);
-    Lane4H H;
-    H.hg0 = half ? 0.5 * h * gam2 : 0.0; H.hg1 = half ? 0.0 : 0.5 * h * gam1;
-    H.G0 = half ? h * gam2 : 0.0; H.G1 = half ? 0.0 : h * gam1;
-    H.Gr0 = half ? 0.0 : h * gam2; H.Gr1 = half ? h * gam1 : 0.0;
-    H.a02 = half ? hc25 : 0.0; H.b00 = hc20; H.a12 = half ? 0.0 : hc13; H.b11 = hc14;
-    H.a21 = half ? 0.0 : hc13; H.a20 = half ? hc25 : 0.0;
-    H.a01r = hc10; H.a01i = 0.0; H.a10r = hc10; H.a10i = 0.0;
-    const double k1 = half ? -C.kick_dp * LSEL(gD[0]) : C.kick_sp * LSEL(gA);
-    const double k2 = half ? 0.0 : C.kick_dp * LSEL(gD[1]);
-    const double k3 = half ? -C.kick_sp * LSEL(gB) : 0.0;
-    const double k4 = half ? -C.kick_dp * LSEL(gD[2]) : 0.0;
-    const double k5 = half ? -C.kick_dp * LSEL(gD[3]) : 0.0;
-#undef LSEL
-    const int me = warp * 32 + lane;           // this lane's R -> S slots
-    const Chunk* hsrc0 = &c_h[0][warp * 8 + (lane >> 2)][0];
-    const Chunk* hsrc1 = &c_h[1][warp * 8 + (lane >> 2)][0];
-    pdl_wait();
-    if (lane == 0) stamp_time(a.stamp, 0);
-    cplx y[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { y[k].re = Pb[(size_t)(2 * map[k]) * a.ld + i]; y[k].im = Pb[(size_t)(2 * map[k] + 1) * a.ld + i]; }
-    if (q < 3) {  // the ion's force: quad lanes 0, 1, 2 fetch (and, from partials, add up) x, y, z
-      const double f = load_force1_impl(a.fpart, a.Fw, a.F, a.nb ? a.nb[b] : a.N, a.fp_jlen, a.B, a.ld, b, i, q, active ? 1 : 0);
-      chunk_put(&c_f[me], f, 1ull);
-    }
-    // populations and kick partials of y(s), for S's jump test and kick of substep s
-    auto publish = [&](int s) {
-      const double pn = half ? cnorm(y[0]) : cnorm(y[1]);
-      const cplx r0 = {__shfl_xor_sync(0xffffffffu, y[0].re, 1), __shfl_xor_sync(0xffffffffu, y[0].im, 1)};
-      const cplx r1 = {__shfl_xor_sync(0xffffffffu, y[1].re, 1), __shfl_xor_sync(0xffffffffu, y[1].im, 1)};
-      double kick = __dmul_rn(k1, im_acb(y[0], y[1]));
-      kick = fma(k2, im_acb(y[2], y[1]), kick); kick = fma(k3, im_acb(r0, y[0]), kick);
-      kick = fma(k4, im_acb(y[2], y[0]), kick); kick = fma(k5, im_acb(y[1], r1), kick);
-      chunk_put(&c_pn[s & 1][me], pn, (unsigned long long)(s + 1));
-      chunk_put(&c_kp[s & 1][me], kick, (unsigned long long)(s + 1));
-    };
-    // {H(s), outcome of substep s-1} from S: the five chunks of this lane's type. S writes them a whole RK step ahead, so they
-    // are FETCHED during stage 3 of the step before (no waiting) and only validated here; polled if a tag is not there yet.
-    double v0, v1, v2, v3, v4;
-    unsigned long long m0, m1, m2, m3, m4;
-    auto fetch = [&](int s) {
-      const Chunk* hs = (s & 1) ? hsrc1 : hsrc0;
-      m0 = chunk_get(hs + half * 3 + 0, v0); m1 = chunk_get(hs + half * 3 + 1, v1); m2 = chunk_get(hs + half * 3 + 2, v2);
-      m3 = chunk_get(hs + 6 + blk * 2, v3); m4 = chunk_get(hs + 7 + blk * 2, v4);
-    };
-    fetch(0);
-    for (int s = 0; s <= a.nsub; s++) {
-      {
-        const unsigned tag = (unsigned)(s + 1);
-        while (!__all_sync(0xffffffffu, (unsigned)m0 == tag && (unsigned)m1 == tag && (unsigned)m2 == tag && (unsigned)m3 == tag &&
-                                            (unsigned)m4 == tag))
-          fetch(s);
-      }
-      K2TRACE(warp, 0)
-      const int dest = (int)(m4 >> 32) - 1;
-      if (dest >= 0) {  // substep s-1 jumped (SU:573-703): all four lanes of the quad take the same destination
-#pragma unroll
-        for (int k = 0; k < 3; k++) { y[k].re = (map[k] == dest) ? 1.0 : 0.0; y[k].im = 0.0; }
-      }
-      if (s == a.nsub) break;
-      H.hE1 = v1; H.hE2 = v2;
-      if (half) { H.a01r = v3; H.a01i = -v4; H.a10r = v3; H.a10i = v4; }
-      publish(s);
-      // hE0 is taken again from its chunk AFTER the publishing stores (volatile accesses keep their order), so that the stages
-      // depend on something behind those stores: ptxas otherwise sinks them below stage 3 (they have no consumer in this warp)
-      // and S gets its input three stages late
-      chunk_get(((s & 1) ? hsrc1 : hsrc0) + half * 3 + 0, v0);
-      H.hE0 = v0;
-      {
-        cplx w[3], g[3], acc[3];
-        stage4(H, y, g);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { acc[k] = g[k]; w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im); }
-        stage4(H, w, g);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
-          w[k].re = fma(0.5, g[k].re, y[k].re); w[k].im = fma(0.5, g[k].im, y[k].im);
-        }
-        stage4(H, w, g);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          acc[k].re = fma(3.0, g[k].re, acc[k].re); acc[k].im = fma(3.0, g[k].im, acc[k].im);
-          w[k].re = y[k].re + g[k].re; w[k].im = y[k].im + g[k].im;
-        }
-        fetch(s + 1);
-        stage4(H, w, g);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          y[k].re = fma(0.125, acc[k].re + g[k].re, y[k].re);
-          y[k].im = fma(0.125, acc[k].im + g[k].im, y[k].im);
-        }
-      }
-      if (a.renorm) {
-        double own = cnorm(y[0]) + cnorm(y[1]) + cnorm(y[2]);
-        own += __shfl_xor_sync(0xffffffffu, own, 1);
-        own += __shfl_xor_sync(0xffffffffu, own, 2);
-        const double nn = sqrt(own);
-#pragma unroll
-        for (int k = 0; k < 3; k++) { y[k].re /= nn; y[k].im /= nn; }
-      }
-      K2TRACE(warp, 1)
-    }
-    pdl_launch_dependents();
-    if (lane == 0) stamp_time(a.stamp, 1);
-    if (!active) return;
-#pragma unroll
-    for (int k = 0; k < 3; k++) { Pb[(size_t)(2 * map[k]) * a.ld + i] = y[k].re; Pb[(size_t)(2 * map[k] + 1) * a.ld + i] = y[k].im; }
-    return;
-  }
-
-  // ------------------------------------------------------------------ warp S: the per-ion scalar recurrence, one lane per ion
-  const int rw = lane >> 3;  // the R warp this lane serves, and its ion there
-  if (rw >= RW) return;
-  const unsigned smask = RW >= 4 ? 0xffffffffu : ((1u << (8 * RW)) - 1u);  // the lanes of this warp that stay
-  const long long slot = (long long)(blockIdx.x * RW + rw) * 8 + (lane & 7);
-  const bool inrange = slot < (long long)a.nrows * a.B;
-  const int b = inrange ? (int)(slot / a.nrows) : 0;
-  const int i0 = inrange ? a.row0 + (int)(slot % a.nrows) : a.row0;
-  const bool active = inrange && i0 < (a.nb ? a.nb[b] : a.N);
-  const int i = active ? i0 : a.row0;
-  const uint64_t seed = a.seeds ? a.seeds[b] : a.seed;
-  double* __restrict__ Rb = a.R + (size_t)b * 3 * a.ld;
-  double* __restrict__ Vb = a.V + (size_t)b * 3 * a.ld;
-  const double hrotA = h * LA.rot, hrotB = h * LB.rot;
-  const double dEDP = -a.detuning + a.detuningDP;
-  // energies as e0 + e1 * (vq + expDetuning) (SU:506-510), pre-multiplied by h; [half][local row]
-  const double e0[2][3] = {{0.0, -h * a.detuning, h * dEDP}, {-h * a.detuning, h * dEDP, h * dEDP}};
-  const double e1[2][3] = {{0.0, -h, h * (a.kRat - 1)}, {h, -h * (1 + a.kRat), h * (1 - a.kRat)}};
-  const double hG0 = h * C.gam[0], hG1 = h * C.gam[1], hG2 = h * C.gam[2], hG3 = h * C.gam[3];
-  PrepC pc = {};
-  pc.pv2qv = a.pv2qv; pc.two_kr = 2. * (1 + a.kRat); pc.g2E = a.g2E;
-  pc.ed_num = 0.0126 * a.fracOfSig * a.Te; pc.ed_den = sqrt(a.density) * a.sig0;
-  pc.ed_c = 0.00014314 * a.Te / (a.density * a.sig0 * a.sig0); pc.expand = a.fracOfSig != 0.0;
-  pdl_wait();
-  double r[3], v[3], f[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) { r[k] = Rb[(size_t)k * a.ld + i]; v[k] = Vb[(size_t)k * a.ld + i]; }
-  double tp = a.tPart[(size_t)b * a.ld + i];
-  double t = a.clock ? a.clock[0] : a.t0;
-  const uint64_t substep0 = a.clock ? *reinterpret_cast<const unsigned long long*>(a.clock + 1) : a.substep0;
-  const double DT = 0.5 * a.dtq;
-  const int quad = rw * 32 + 4 * (lane & 7);  // first R lane of this ion
-#pragma unroll
-  for (int k = 0; k < 3; k++)
-    while ((unsigned)chunk_get(&c_f[quad + k], f[k]) != 1u) {}
-  Chunk* const hdst0 = &c_h[0][rw * 8 + (lane & 7)][0];
-  Chunk* const hdst1 = &c_h[1][rw * 8 + (lane & 7)][0];
-  int dest_prev = -1;
-  for (int s = 0; s < a.nsub; s++) {
-    {  // step() (SU:356-430)
-      const bool started = t > 0;
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          if (started) r[k] = __dadd_rn(r[k], __dmul_rn(DT, v[k]));
-          else r[k] = __dadd_rn(r[k], __dadd_rn(__dmul_rn(DT, v[k]), __dmul_rn(__dmul_rn(DT, DT), f[k])));
-          if (r[k] < 0) r[k] = __dadd_rn(r[k], a.L);
-          if (r[k] > a.L) r[k] = __dadd_rn(r[k], -a.L);
-          if (hf == 0) v[k] = __dadd_rn(v[k], __dmul_rn(a.dtq, f[k]));
-        }
-      }
-    }
-    tp = __dadd_rn(tp, a.dtq);
-    {  // Doppler shift, rotating phase, coefficients (prep4's expressions) for the four lane types of this ion
-      const double uu = prep_uu(pc, v[0], t);
-      const double phi = __dmul_rn(__dmul_rn(__dmul_rn(pc.two_kr, uu), tp), pc.g2E);
-      double sn, cs;
-      sincos_fast(phi, sn, cs);
-      const unsigned long long meta = ((unsigned long long)(unsigned)(dest_prev + 1) << 32) | (unsigned long long)(unsigned)(s + 1);
-      Chunk* hd = (s & 1) ? hdst1 : hdst0;
-#pragma unroll
-      for (int hf = 0; hf < 2; hf++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) chunk_put(hd + hf * 3 + k, fma(e1[hf][k], uu, e0[hf][k]), meta);
-      chunk_put(hd + 6, __dmul_rn(hrotA, cs), meta); chunk_put(hd + 7, __dmul_rn(hrotA, sn), meta);
-      chunk_put(hd + 8, __dmul_rn(hrotB, cs), meta); chunk_put(hd + 9, __dmul_rn(hrotB, sn), meta);
-    }
-    K2TRACE(rw, 3)
-    // this substep's uniforms -- all five, also the three only a jump consumes: straight-line integer work that overlaps, and the
-    // jump branch (taken whenever ANY of the warp's ions jumps) stays short. R needs nothing from here for a whole RK step.
-    const uint64_t sidx = substep0 + (uint64_t)s;
-    double u0, u1, u2, u3, u4;
-    if (FORCED) {
-      const double* up = a.forced_u + ((size_t)s * a.N + i) * 5;
-      u0 = up[0]; u1 = up[1]; u2 = up[2]; u3 = up[3]; u4 = up[4];
-    } else {
-      const uint4 o0 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 0);
-      const uint4 o1 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 1);
-      const uint4 o2 = philox_call(seed, (unsigned)(a.traj0 + b), (unsigned)i, sidx, 2);
-      u0 = u52(o0.x, o0.y); u1 = u52(o0.z, o0.w); u2 = u52(o1.x, o1.y); u3 = u52(o1.z, o1.w); u4 = u52(o2.x, o2.y);
-    }
-    // P populations of the quad in the reference's state order 2,3,4,5: lanes hold P1(A)=3, P2(A)=5, P1(B)=2, P2(B)=4
-    double n3, n5, n2, n4, kick;
-    {  // every lane takes its quad's chunks every substep; warp-uniform spin (a per-lane, divergent spin here hung intermittently on B200)
-      const unsigned tag = (unsigned)(s + 1);
-      const Chunk* cp = &c_pn[s & 1][quad];
-      const Chunk* ck = &c_kp[s & 1][quad];
-      double ka, kb, kc, kd;
-      for (;;) {
-        const unsigned long long md = chunk_get(ck + 3, kd);  // the last chunk the quad writes ...
-        if (!__all_sync(smask, (unsigned)md == tag)) continue;
-        const unsigned long long q0 = chunk_get(cp + 0, n3), q1 = chunk_get(cp + 1, n5), q2 = chunk_get(cp + 2, n2), q3 = chunk_get(cp + 3, n4);
-        const unsigned long long q4 = chunk_get(ck + 0, ka), q5 = chunk_get(ck + 1, kb), q6 = chunk_get(ck + 2, kc);
-        const bool ok = (unsigned)q0 == tag && (unsigned)q1 == tag && (unsigned)q2 == tag && (unsigned)q3 == tag && (unsigned)q4 == tag &&
-                        (unsigned)q5 == tag && (unsigned)q6 == tag;
-        if (__all_sync(smask, ok)) break;  // ... then the others, each validated by its own tag
-      }
-      kick = ka + kb;   // the quad's total in the order of k_substeps4's shuffle tree: (own + neighbour) + (the other pair's sum)
-      kick += kc + kd;
-    }
-    K2TRACE(rw, 4)
-    const double dp0 = hG0 * n2 + hG1 * n3 + hG2 * n4 + hG3 * n5;
-    const bool jump = !(u0 > dp0);
-    if (!jump) {
-      dest_prev = -1;
-    } else {  // quantum jump (SU:573-703)
-      tp = 0.0;
-      const double tot = n2 + n3 + n4 + n5;
-      const double p3 = n2 / tot, p4 = n3 / tot, p5 = n4 / tot;
-      const bool sDecay = !(u2 < C.dfrac);
-      const double mag = sDecay ? a.vKick : a.vKickDP;
-      kick = (u3 < 0.5) ? mag : -mag;
-      int dest;
-      if (u1 < p3) dest = sDecay ? 1 : (u4 < C.tD[0] ? 11 : (u4 < C.tD[1] ? 10 : 9));
-      else if (u1 < p3 + p4) dest = sDecay ? (u4 < C.tS[0] ? 0 : 1) : (u4 < C.tD[2] ? 10 : (u4 < C.tD[3] ? 9 : 8));
-      else if (u1 < p3 + p4 + p5) dest = sDecay ? (u4 < C.tS[1] ? 1 : 0) : (u4 < C.tD[4] ? 9 : (u4 < C.tD[5] ? 8 : 7));
-      else dest = sDecay ? 0 : (u4 < C.tD[6] ? 8 : (u4 < C.tD[7] ? 7 : 6));
-      dest_prev = dest;
-    }
-    v[0] = __dadd_rn(v[0], kick);  // SU:705
-    t = __dadd_rn(t, a.dtq);       // SU:716
-    K2TRACE(rw, 5)
-  }
-  {  // the outcome of the last substep
-    const unsigned long long meta = ((unsigned long long)(unsigned)(dest_prev + 1) << 32) | (unsigned long long)(unsigned)(a.nsub + 1);
-    Chunk* hd = (a.nsub & 1) ? hdst1 : hdst0;
-#pragma unroll
-    for (int k = 0; k < 10; k++) chunk_put(hd + k, 0.0, meta);
-  }
-  if (lane == 0) stamp_time(a.stamp, 1);
-  if (!active) return;
-  long long* __restrict__ Xf = a.Rfix + (size_t)b * 3 * a.ld;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    Rb[(size_t)k * a.ld + i] = r[k];
-    Xf[(size_t)k * a.ld + i] = to_fixed(r[k], a.invL, a.invL_lo);
-    Vb[(size_t)k * a.ld + i] = v[k];
-  }
-  a.tPart[(size_t)b * a.ld + i] = tp;
-}
-
 void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_t s) {
   long long threads = 2LL * a.nrows * a.B;
   int block = threads >= 148LL * 4 * 128 ? 128 : 64;
@@ -1248,20 +893,8 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   if (four) {
     long long th = 4LL * a.nrows * a.B;
     int g4 = (int)((th + 31) / 32);
-    // warp-specialised form (Runge-Kutta warp + scalar-recurrence warp per 8 ions) unless MDQT_K2_WS=0 (A/B, variant tests)
-    static const bool ws = [] { const char* e = getenv("MDQT_K2_WS"); return e && e[0] == '1'; }();  // experiment: opt-in
-    if (ws) {
-      // Runge-Kutta warps per CTA (+ one scalar warp): three -- one per sub-partition, the fourth left to the scalar warp -- while
-      // that puts the launch on one CTA per SM, else four
-      static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-      const int rw = g4 <= 3 * sms ? 3 : kWsMaxR;
-      const int gw = (g4 + rw - 1) / rw;
-      if (forced) launch_kernel(k_substeps4ws<true>, dim3(gw), dim3(32 * (rw + 1)), s, false, a, C);
-      else launch_kernel(k_substeps4ws<false>, dim3(gw), dim3(32 * (rw + 1)), s, pdl_enabled(), a, C);
-    } else {
-      if (forced) launch_kernel(k_substeps4<true>, dim3(g4), dim3(32), s, false, a, C);
-      else launch_kernel(k_substeps4<false>, dim3(g4), dim3(32), s, pdl_enabled(), a, C);
-    }
+    if (forced) launch_kernel(k_substeps4<true>, dim3(g4), dim3(32), s, false, a, C);
+    else launch_kernel(k_substeps4<false>, dim3(g4), dim3(32), s, pdl_enabled(), a, C);
     return;
   }
   if (scheme == 12) {
@@ -1421,15 +1054,3 @@ void launch_lf(const LFArgs& a, cudaStream_t s) {
 }
 
 }  // namespace mdqt
-
-#ifdef MDQT_K2_TRACE
-extern "C" int mdqt_debug_read_k2trace(long long* out, int n) {
-  return (int)cudaMemcpyFromSymbol(out, mdqt::g_k2trace, sizeof(long long) * (size_t)n);
-}
-#endif
-
-#ifdef MDQT_K2_WATCHDOG
-extern "C" int mdqt_debug_read_k2dog(unsigned long long* out, int n) {
-  return (int)cudaMemcpyFromSymbol(out, mdqt::g_k2dog, sizeof(unsigned long long) * (size_t)n);
-}
-#endif
