@@ -122,14 +122,15 @@ void launch_forces(const ForceArgs& a, cudaStream_t s, bool finalize = true);
 inline bool forces_are_partial(const ForceArgs& a) { return a.items && a.nsplit > 1; }
 #ifdef __CUDACC__
 // sum of `nch` partials src[0], src[stride], ... in ascending order, fetched as batches of 12 independent L2 loads
+template <int BATCH = 12>
 __device__ __forceinline__ double sum_partials(const double* __restrict__ src, size_t stride, int nch) {
   double sum = 0.0;
-  for (int s0 = 0; s0 < nch; s0 += 12) {
-    double v[12];
+  for (int s0 = 0; s0 < nch; s0 += BATCH) {
+    double v[BATCH];
 #pragma unroll
-    for (int q = 0; q < 12; q++) v[q] = (s0 + q < nch) ? __ldcg(src + (size_t)(s0 + q) * stride) : 0.0;
+    for (int q = 0; q < BATCH; q++) v[q] = (s0 + q < nch) ? __ldcg(src + (size_t)(s0 + q) * stride) : 0.0;
 #pragma unroll
-    for (int q = 0; q < 12; q++) sum += v[q];  // + 0.0 for absent chunks: exact
+    for (int q = 0; q < BATCH; q++) sum += v[q];  // + 0.0 for absent chunks: exact
   }
   return sum;
 }
