@@ -142,6 +142,7 @@ static void plan_force(mdqt_handle* h) {
   // same plan whatever their environments, or the rank-count-independent bits are gone
   auto knob = [h](const char* name) -> const char* { return h->nrows == h->N ? getenv(name) : nullptr; };
   h->items = 0;
+  h->pdl = pdl_mode() == 1 ? 1 : 0;
   {
     const int np = h->p.plan_n > 0 ? h->p.plan_n : h->N;
     const char* e = knob("MDQT_K1_ITEMS");  // developer knob (A/B runs): 0 = CTA-tile kernel everywhere
@@ -154,6 +155,9 @@ static void plan_force(mdqt_handle* h) {
       h->nsplit = (h->N + h->jlen - 1) / h->jlen;
       h->ipt = 1; h->jsub = 1; h->rg = 32;
       h->itiles = (h->nrows + 31) / 32;
+      // one trajectory whose items fit ONE round of the resident warps: all force warps finish together, which is when programmatic
+      // dependent launch pays (pdl_mode)
+      if (pdl_mode() < 0) h->pdl = (h->B == 1 && h->nrows == h->N && (long long)h->itiles * h->nsplit <= 148LL * 2 * 8) ? 1 : 0;
       return;
     }
   }
@@ -463,7 +467,7 @@ extern "C++" ForceArgs mdqt_force_args(mdqt_handle* h) {
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
-  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb;
+  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb; a.pdl = h->pdl;
   a.mg_chunk = ((1ULL << 40) + h->nsplit - 1) / h->nsplit; a.mg_gcap = ((1ULL << 40) + a.gcap - 1) / a.gcap;
   { const int g2 = (h->nrows + 63) / 64; a.mg_gcap2 = ((1ULL << 40) + g2 - 1) / g2; }
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
@@ -498,6 +502,7 @@ extern "C++" QTArgs mdqt_qt_args(mdqt_handle* h, int nsub, int do_step, int do_k
   a.nsub = nsub; a.do_step = do_step; a.do_kick = do_kick; a.do_tpart = do_kick;  // tPart lives where the kick does (SU, TS)
   a.scheme = h->S; a.S = h->S; a.renorm = p.renormalize; a.quad = p.quad;
   a.nb = h->nb; a.seeds = h->seeds;
+  a.pdl = h->pdl;
   a.lanes = 0;  // lanes per ion by (N, B): the two- and four-lane kernels give the same bits (tests/test_gpu_variants.py)
   a.t0 = h->t; a.substep0 = h->substep; a.seed = p.seed;
   a.L = p.L; a.dtq = p.dtq;
@@ -1254,7 +1259,9 @@ int mdqt_time_forces(mdqt_handle* h, int reps, double* ms_per_launch) {
   cudaGraph_t graph;
   cudaGraphExec_t exec = nullptr;
   CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  for (int k = 0; k < reps; k++) launch_forces(force_args(h), h->stream, false);  // the force kernel alone
+  ForceArgs fa = force_args(h);
+  fa.pdl = 0;  // plain stream order: with programmatic dependent launch successive force launches would overlap, and this is a kernel time
+  for (int k = 0; k < reps; k++) launch_forces(fa, h->stream, false);  // the force kernel alone
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (e != cudaSuccess) return fail(MDQT_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
   e = cudaGraphInstantiate(&exec, graph, 0);

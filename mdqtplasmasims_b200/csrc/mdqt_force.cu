@@ -63,14 +63,15 @@ static_assert(kExpTable == 128 || kExpTable == 1024, "exp table must have 128 or
 
 __device__ double c_exp2tab[kExpTable];  // global (L2-resident), not __constant__: the CTA prologue reads it with a per-thread index
 
-bool pdl_enabled() {
-  // Programmatic dependent launch between the force and substep kernels: opt-in (MDQT_PDL=1). With the persistent item kernel it
-  // hides the dependent's launch latency and prologue behind the tail when all warps finish together (N = 3500: 54.4 -> 53.5 us per
-  // MD step) -- but whenever the force kernel's warps finish at different times (N = 3653 planned for 3500: two item rounds) the
-  // dependent's CTAs pile onto the SMs that free up first and the substep kernel runs unbalanced: 79.9 instead of 67.6 us. With the
-  // round-1 CTA-tile kernel it was slower everywhere (114 vs 74 us).
-  static const bool on = [] { const char* e = getenv("MDQT_PDL"); return e && e[0] == '1'; }();
-  return on;
+int pdl_mode() {
+  // Programmatic dependent launch between the force and substep kernels. With the persistent item kernel it hides the dependent's
+  // launch latency and prologue behind the tail WHEN ALL WARPS FINISH TOGETHER (one trajectory whose items fill one round of the
+  // resident warps; N = 3500: 54.4 -> 53.5 us per MD step) -- but whenever the force kernel's warps finish at different times
+  // (N = 3653 planned for 3500: two item rounds; batches) the dependent's CTAs pile onto the SMs that free up first and the substep
+  // kernel runs unbalanced: 79.9 instead of 67.6 us; with the CTA-tile kernel it was slower everywhere (114 vs 74 us). So the
+  // default is decided per handle from the plan (plan_force); MDQT_PDL=1 / 0 forces it on / off.
+  static const int mode = [] { const char* e = getenv("MDQT_PDL"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+  return mode;
 }
 
 bool cluster_enabled() {
@@ -700,7 +701,7 @@ static void launch_items_nw(const ForceArgs& a, double* partials, cudaStream_t s
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NW * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
   int n = 0;
-  if (!EPOT && pdl_enabled()) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; n++; }
+  if (!EPOT && a.pdl) { at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[n].val.programmaticStreamSerializationAllowed = 1; n++; }
   cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kern, a, partials);
 }
@@ -763,7 +764,7 @@ static void launch_pairs(const ForceArgs& a, double* partials, cudaStream_t s) {
   const int ipt = (rg == 32) ? 1 : (a.ipt == 2 ? 2 : 1);
   const int jsub = (rg == 32) ? (a.jsub == 8 ? 8 : 4) : ((a.jsub == 2 || a.jsub == 4) ? a.jsub : 1);
   dim3 grid((a.nrows + rg * ipt - 1) / (rg * ipt), a.js_count > 0 ? a.js_count : a.nsplit, a.B);
-  const bool pdl = !EPOT && pdl_enabled();
+  const bool pdl = !EPOT && a.pdl;
   if (a.half_l && MDQT_VALID_INT) launch_pairs_hl<EPOT, true>(a, partials, s, grid, ipt, jsub, pdl);
   else launch_pairs_hl<EPOT, false>(a, partials, s, grid, ipt, jsub, pdl);
 }

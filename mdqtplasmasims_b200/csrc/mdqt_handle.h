@@ -35,6 +35,7 @@ struct mdqt_handle {
   mdqt::QTConsts qc;
   double t; uint64_t substep, vv_step;
   int nsplit, jlen, itiles, ipt, jsub, rg, items;
+  int pdl;  // programmatic dependent launch between the force and substep kernels (plan_force)
   int* nb;              // [B] per-trajectory ion counts on the device (ensembles with unequal N) or null
   std::vector<int> nb_host;
   uint64_t* seeds;      // [B] per-trajectory Philox keys or null

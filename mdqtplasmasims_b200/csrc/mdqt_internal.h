@@ -40,6 +40,7 @@ struct ForceArgs {
   // item-walking kernel (small and medium systems, any batch size): every warp of a persistent grid walks a static list of
   // (trajectory, 32-row group, j chunk) items. items = 1 selects it; gcap = row groups per trajectory (at capacity)
   int items, gcap;
+  int pdl;                                // launch with programmatic stream serialisation (pdl_for)
   unsigned long long mg_chunk, mg_gcap, mg_gcap2;  // ceil(2^40 / nsplit), ceil(2^40 / groups of 32 rows), ... of 64 rows: item index -> (b, g, chunk) without division
   const int* nb;     // [B] ions per trajectory (ensembles whose jobs drew different N, SU:299-337) or null: all N
   unsigned long long* stamp;  // {min start, max end} of this launch in %globaltimer ns (in-graph kernel timing) or null
@@ -60,6 +61,7 @@ struct QTArgs {
   int do_tpart;                           // 1: tPart tracked (+= dtq, reset on a jump; SU:482, TS:155)
   int renorm, quad;
   int lanes;                              // lanes per ion of the 12-level kernel: 0 = by (N, B), 2 or 4 = pinned
+  int pdl;                                // launch with programmatic stream serialisation (pdl_for)
   double t0; uint64_t substep0; uint64_t seed;
   const int* nb;                          // [B] ions per trajectory or null (all N)
   const double* fpart; double* Fw;        // item-kernel partials [chunk][B][3][ld] to add up (then written to Fw), or null: F is complete
@@ -90,7 +92,7 @@ struct VVArgs {
 // Programmatic dependent launch (sm_90+): the hot kernels of an MD step call griddepcontrol.launch_dependents at
 // their start and griddepcontrol.wait before touching data of their predecessor, so the next kernel's launch latency
 // and prologue overlap the current kernel's tail. `pdl` = launch with the programmatic-serialization attribute.
-bool pdl_enabled();
+int pdl_mode();  // MDQT_PDL: 1 = always, 0 = never, unset = -1: where the plan says the kernels' warps finish together (mdqt_capi.cu)
 bool cluster_enabled();
 // cluster_y > 0: the grid's y dimension is launched as thread-block clusters of (1, cluster_y, 1)
 template <typename... KArgs, typename A0, typename A1>

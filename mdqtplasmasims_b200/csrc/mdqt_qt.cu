@@ -918,12 +918,12 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
     long long th = 4LL * a.nrows * a.B;
     int g4 = (int)((th + 31) / 32);
     if (forced) launch_kernel(k_substeps4<true>, dim3(g4), dim3(32), s, false, a, C);
-    else launch_kernel(k_substeps4<false>, dim3(g4), dim3(32), s, pdl_enabled(), a, C);
+    else launch_kernel(k_substeps4<false>, dim3(g4), dim3(32), s, a.pdl != 0, a, C);
     return;
   }
   if (scheme == 12) {
     if (forced) launch_kernel(k_substeps<6, true>, dim3(grid), dim3(block), s, false, a, C);
-    else launch_kernel(k_substeps<6, false>, dim3(grid), dim3(block), s, pdl_enabled(), a, C);
+    else launch_kernel(k_substeps<6, false>, dim3(grid), dim3(block), s, a.pdl != 0, a, C);
   } else {
     if (forced) k_substeps<4, true><<<grid, block, 0, s>>>(a, C);
     else k_substeps<4, false><<<grid, block, 0, s>>>(a, C);

@@ -51,6 +51,11 @@ e = Engine(su_params(n_ions=256, N0=256))
 print("fp64 peak TFLOP/s:", e.fp64_peak_tflops(), flush=True)
 e.close()
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
+if which == "pdl":  # run once with MDQT_PDL=0 and once without (the mode is read once per process)
+    for N in (1000, 2048, 3000, 3500, 4096):
+        run("items", N)
+    run("items", 3653, plan_n=3500)
+    run("items", 3500, B=8, nmd=4)
 if which == "k1ab":
     run("items", 3500)
     run("items", 3653, plan_n=3500)
