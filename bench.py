@@ -235,7 +235,7 @@ def run_ours(args):
         # every reference job draws its own N ~ Binomial(729 N0, 1/729) (SU:299-337): unequal ion counts in one handle
         counts = np.random.default_rng(4321 + rank).binomial(729 * N0, 1.0 / 729, size=Be).astype(np.int32)
         cap = int(counts.max())
-        pe = su_params(n_ions=cap, N0=N0, n_traj=Be, traj0=1000 + rank * Be, seed=12345, device=local, plan_n=N0)
+        pe = su_params(n_ions=cap, N0=N0, n_traj=Be, traj0=1000 + rank * Be, seed=12345, device=local, plan_n=0)
         ee = Engine(pe)
         ee.set_ion_counts(counts)
         ee.set_traj_seeds(np.arange(Be, dtype=np.uint64) + 777 + rank * Be)

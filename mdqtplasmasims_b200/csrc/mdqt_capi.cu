@@ -317,6 +317,7 @@ int mdqt_destroy(mdqt_handle* h) {
   if (h->tagged) cudaFree(h->tagged);
   if (h->clock) cudaFree(h->clock);
   if (h->nb) cudaFree(h->nb);
+  if (h->jl) cudaFree(h->jl);
   if (h->tags) cudaFree(h->tags);
   if (h->moments) cudaFree(h->moments);
   if (h->stamps) cudaFree(h->stamps);
@@ -435,6 +436,37 @@ int mdqt_set_ion_counts(mdqt_handle* h, const int32_t* n_ions) {
     CU(cudaMemcpy(h->nb, n_ions, sizeof(int) * (size_t)h->B, cudaMemcpyHostToDevice));
     h->nb_host.assign(n_ions, n_ions + h->B);
   }
+  // The chunk length of the item force kernel is a function of each trajectory's OWN ion count (plan_n == 0; a non-zero plan_n fixes one
+  // length for all): a job sums its forces in the same order alone (n_ions = its N) and in any batch, and every job gets the plan
+  // that fits its N (a nominal plan spills into a second round of items for the third of the jobs above N0 + 0.5 sigma).
+  {
+    const int old_nsplit = h->nsplit;
+    if (h->jl) { cudaFree(h->jl); h->jl = nullptr; }
+    plan_force(h);  // the uniform plan for N = n_ions (or plan_n)
+    if (n_ions && h->p.plan_n == 0) {
+      std::vector<int> jl(h->B);
+      int jmax = 8, nsmax = 1;
+      for (int b = 0; b < h->B; b++) {
+        jl[b] = plan_items_jlen(n_ions[b]);
+        jmax = std::max(jmax, jl[b]);
+        nsmax = std::max(nsmax, (n_ions[b] + jl[b] - 1) / jl[b]);
+      }
+      CU(cudaMalloc((void**)&h->jl, sizeof(int) * (size_t)h->B));
+      CU(cudaMemcpy(h->jl, jl.data(), sizeof(int) * (size_t)h->B, cudaMemcpyHostToDevice));
+      h->jlen = jmax; h->nsplit = nsmax;  // tile capacity and chunk-slot capacity of the batch
+      if (pdl_mode() < 0) h->pdl = (h->B == 1 && (long long)((n_ions[0] + 31) / 32) * h->nsplit <= 148LL * 2 * 8) ? 1 : 0;
+    }
+    if (h->nsplit != old_nsplit) {  // the partial-sum buffers are sized by the number of chunk slots
+      cudaFree(h->Fpart); cudaFree(h->epot_partials);
+      h->Fpart = h->epot_partials = nullptr;
+      const size_t n1 = std::max<size_t>(h->nsplit > 1 ? (size_t)h->nsplit * state_elems(h) : 1, 1);
+      const size_t n2 = std::max<size_t>((size_t)h->itiles * h->nsplit * h->B, 1);
+      CU(cudaMalloc((void**)&h->Fpart, n1 * sizeof(double)));
+      CU(cudaMalloc((void**)&h->epot_partials, n2 * sizeof(double)));
+      CU(cudaMemset(h->Fpart, 0, n1 * sizeof(double)));
+      CU(cudaMemset(h->epot_partials, 0, n2 * sizeof(double)));
+    }
+  }
   for (GraphEntry& g : h->graphs) cudaGraphExecDestroy(g.exec);  // captured arguments carried the old pointer
   h->graphs.clear();
   return MDQT_OK;
@@ -467,7 +499,7 @@ extern "C++" ForceArgs mdqt_force_args(mdqt_handle* h) {
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
-  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb; a.pdl = h->pdl;
+  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb; a.jl = h->jl; a.pdl = h->pdl;
   a.mg_chunk = ((1ULL << 40) + h->nsplit - 1) / h->nsplit; a.mg_gcap = ((1ULL << 40) + a.gcap - 1) / a.gcap;
   { const int g2 = (h->nrows + 63) / 64; a.mg_gcap2 = ((1ULL << 40) + g2 - 1) / g2; }
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;
@@ -524,7 +556,7 @@ static cudaEvent_t next_event(mdqt_handle* h) {
 extern "C++" int mdqt_enqueue_substeps(mdqt_handle* h, int nsub, int do_step, int do_kick, bool forces_partial) {
   if (h->forced_u && h->forced_cursor + nsub > h->forced_nsub) return fail(MDQT_ESTATE, "forced uniforms exhausted");
   QTArgs a = qt_args(h, nsub, do_step, do_kick);
-  if (forces_partial && forces_are_partial(force_args(h))) { a.fpart = h->Fpart; a.Fw = h->F; a.fp_jlen = h->jlen; }
+  if (forces_partial && forces_are_partial(force_args(h))) { a.fpart = h->Fpart; a.Fw = h->F; a.fp_jlen = h->jlen; a.jl = h->jl; }
   launch_substeps(a, h->qc, h->S, h->stream);
   if (h->forced_u) h->forced_cursor += nsub;
   h->substep += (uint64_t)nsub;
@@ -584,7 +616,7 @@ static int md_steps_graph(mdqt_handle* h, int nsteps) {
   fa.clock = h->clock; fa.clock_dtq = h->p.dtq; fa.clock_advance = 0;
   QTArgs qa = qt_args(h, ratio, 1, 1);
   qa.clock = h->clock; qa.t0 = 0.0; qa.substep0 = 0;
-  if (forces_are_partial(fa)) { qa.fpart = h->Fpart; qa.Fw = h->F; qa.fp_jlen = h->jlen; }
+  if (forces_are_partial(fa)) { qa.fpart = h->Fpart; qa.Fw = h->F; qa.fp_jlen = h->jlen; qa.jl = h->jl; }
   const bool stamp = h->timing == 2;
   if (stamp) {
     const size_t need = (size_t)nsteps * 2;

@@ -15,10 +15,9 @@
 //            [--Om 1] [--OmDP 1] [--saveDirectory dataLaserCool/] [--newRun 1] [--c0 0] [--tmax 30]
 //            [--reNormalizewvFns 0] [--sampleFreq 40] [--seed n] [--device 0] [--writers n] [--fast-single] [--quiet]
 //
-// A job gives the same bits whether it runs alone or inside any batch: the force summation plan is fixed by N0
-// (mdqt_params.plan_n), not by the batch, and the substep kernel's lane mappings are bitwise equivalent. --fast-single lifts the
-// former for a lone job (the plan is then made for the job's own N: faster when N exceeds what the N0 plan fits in one round of
-// items, e.g. N = 3653 at N0 = 3500; results differ in the last bits).
+// A job gives the same bits whether it runs alone or inside any batch: the force summation order of a trajectory follows from
+// its own ion count (mdqt_set_ion_counts with plan_n = 0), not from the batch, and the substep kernel's lane mappings are
+// bitwise equivalent. (--fast-single is accepted and ignored: it used to lift a nominal-N0 plan for lone jobs.)
 #include "../../include/mdqt.h"
 #include "../../include/mdqt_io.h"
 #include <math.h>
@@ -179,7 +178,7 @@ static BatchResult run_batch(const Options& o, unsigned job0, int B, int device,
   CKB(mdqt_params_su(&p, o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning, o.detuningDP, o.Om, o.OmDP, o.N0, Ncap));
   p.n_traj = B; p.traj0 = (int)job0; p.seed = (uint64_t)seeds[0]; p.device = device;
   p.renormalize = o.renorm;
-  p.plan_n = (B == 1 && o.fast_single) ? 0 : o.N0;
+  p.plan_n = 0;  // every trajectory's summation order follows from its own ion count: the same bits alone and in any batch
   CKB(mdqt_create(&p, &h));
   if (B > 1) {
     std::vector<uint64_t> s64(seeds.begin(), seeds.end());
@@ -321,7 +320,7 @@ static int run_rows(const Options& o, unsigned job, int G, std::vector<std::uniq
     CKR(mdqt_params_su(&p, o.Ge, o.density, o.sig0, o.Te, o.fracOfSig, o.detuning, o.detuningDP, o.Om, o.OmDP, o.N0, N));
     p.traj0 = (int)job; p.seed = (uint64_t)seed; p.device = o.device + g; p.renormalize = o.renorm;
     p.row0 = g * rows; p.n_rows = std::min(rows, N - g * rows);
-    p.plan_n = o.fast_single ? 0 : o.N0;  // the same bits as the one-GPU run of this job
+    p.plan_n = 0;  // the same bits as the one-GPU run of this job
     CKR(mdqt_create(&p, &h));
     CKR(mdqt_comm_init(h, uid, g, G));
     CKR(mdqt_upload_state(h, R.data(), V.data(), psi.data(), tPart.data(), ld));

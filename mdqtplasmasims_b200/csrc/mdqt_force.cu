@@ -514,7 +514,7 @@ constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-struct Item { int b, g, ch, Nb; };
+struct Item { int b, g, ch, Nb, jl; };
 
 #ifdef MDQT_K1_TRACE  // developer build: per-WARP phase time stamps of the item kernel (scripts/k1_items_trace.py)
 #define WTRACE(slot)                                                                                             \
@@ -536,6 +536,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8192) double stab_mem[kExpTable];  // 8 KB-aligned: see pair_core<.., TAB32>
   __shared__ int snb[kItemMaxB];  // the trajectories' ion counts: read at every item decode, so not from L2
+  __shared__ int sjl[kItemMaxB];  // and their chunk lengths (a function of each trajectory's own ion count: plan_items_jlen)
   constexpr int RPG = 32 * IPT;  // rows per group
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tj = a.jlen;  // tile capacity (a multiple of 8, <= kItemMaxJ)
@@ -548,7 +549,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
   WTRACE(0)
   for (int k = tid; k < kExpTable; k += NW * 32) cp_async8(&stab_mem[k], &c_exp2tab[k]);
   const bool nb_smem = a.nb && a.B <= kItemMaxB;
-  if (nb_smem) for (int k = tid; k < a.B; k += NW * 32) snb[k] = a.nb[k];  // constant for the handle's lifetime
+  if (nb_smem) for (int k = tid; k < a.B; k += NW * 32) { snb[k] = a.nb[k]; sjl[k] = a.jl ? a.jl[k] : a.jlen; }  // constant for the handle's lifetime
   __syncthreads();
   pdl_wait();  // positions (Rfix) come from the previous kernel in the stream
   if (!EPOT && tid == 0 && blockIdx.x == 0) advance_clock(a);
@@ -565,8 +566,9 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
     it.b = (int)(((unsigned long long)t * mg_g) >> 40);
     it.g = (int)t - it.b * gcap;
     it.Nb = nb_smem ? snb[it.b] : (a.nb ? a.nb[it.b] : a.N);
+    it.jl = nb_smem ? sjl[it.b] : (a.jl ? a.jl[it.b] : a.jlen);
     // empty when the group or the chunk lies beyond the trajectory's ions
-    return (a.row0 + it.g * RPG < min(rowend_cap, it.Nb)) && (it.ch * a.jlen < it.Nb);
+    return (a.row0 + it.g * RPG < min(rowend_cap, it.Nb)) && (it.ch * it.jl < it.Nb);
   };
   auto next_valid = [&](int k, Item& it) {
     while (k < total && !decode(k, it)) {
@@ -583,7 +585,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
     longlong2* sxy = reinterpret_cast<longlong2*>(base);
     long long* sz = reinterpret_cast<long long*>(base + 16u * (unsigned)tj);
     long long* srow = reinterpret_cast<long long*>(base + 24u * (unsigned)tj);
-    const int jbeg = it.ch * a.jlen, cnt = min(a.jlen, it.Nb - jbeg);
+    const int jbeg = it.ch * it.jl, cnt = min(it.jl, it.Nb - jbeg);
     for (int q = lane; q < cnt; q += 32) {
       cp_async8(&sxy[q].x, X + jbeg + q); cp_async8(&sxy[q].y, Y + jbeg + q); cp_async8(&sz[q], Z + jbeg + q);
     }
@@ -620,7 +622,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
       xi[r] = srow[r * 32 + lane]; yi[r] = srow[RPG + r * 32 + lane]; zi[r] = srow[2 * RPG + r * 32 + lane];
       ax[r] = ay[r] = az[r] = 0.0;
     }
-    const int cnt = min(a.jlen, cur.Nb - cur.ch * a.jlen);
+    const int cnt = min(cur.jl, cur.Nb - cur.ch * cur.jl);
     WTRACE(2)
 #pragma unroll(IPT == 2 ? 4 : 8)
     for (int jj = 0; jj < cnt; jj++) {
@@ -725,7 +727,8 @@ __global__ void k_sum_partials(ForceArgs a) {
   const int bc = (int)(gidx / a.nrows), b = bc / 3;
   const int Nb = a.nb ? a.nb[b] : a.N;
   if (i >= Nb) return;
-  const int nch = (Nb + a.jlen - 1) / a.jlen;
+  const int jl = a.jl ? a.jl[b] : a.jlen;
+  const int nch = (Nb + jl - 1) / jl;
   const size_t stride = (size_t)a.B * 3 * a.ld;
   const double* src = a.Fpart + (size_t)bc * a.ld + i;
   a.F[(size_t)bc * a.ld + i] = sum_partials(src, stride, nch);

@@ -40,7 +40,8 @@ struct ForceArgs {
   // item-walking kernel (small and medium systems, any batch size): every warp of a persistent grid walks a static list of
   // (trajectory, 32-row group, j chunk) items. items = 1 selects it; gcap = row groups per trajectory (at capacity)
   int items, gcap;
-  int pdl;                                // launch with programmatic stream serialisation (pdl_for)
+  const int* jl;                          // item kernel: [B] chunk length of every trajectory, or null (all jlen); jlen = the largest
+  int pdl;                                // launch with programmatic stream serialisation (pdl_mode)
   unsigned long long mg_chunk, mg_gcap, mg_gcap2;  // ceil(2^40 / nsplit), ceil(2^40 / groups of 32 rows), ... of 64 rows: item index -> (b, g, chunk) without division
   const int* nb;     // [B] ions per trajectory (ensembles whose jobs drew different N, SU:299-337) or null: all N
   unsigned long long* stamp;  // {min start, max end} of this launch in %globaltimer ns (in-graph kernel timing) or null
@@ -61,11 +62,12 @@ struct QTArgs {
   int do_tpart;                           // 1: tPart tracked (+= dtq, reset on a jump; SU:482, TS:155)
   int renorm, quad;
   int lanes;                              // lanes per ion of the 12-level kernel: 0 = by (N, B), 2 or 4 = pinned
-  int pdl;                                // launch with programmatic stream serialisation (pdl_for)
+  int pdl;                                // launch with programmatic stream serialisation (pdl_mode)
   double t0; uint64_t substep0; uint64_t seed;
   const int* nb;                          // [B] ions per trajectory or null (all N)
   const double* fpart; double* Fw;        // item-kernel partials [chunk][B][3][ld] to add up (then written to Fw), or null: F is complete
-  int fp_jlen;                            // chunk length of those partials
+  int fp_jlen;                            // chunk length of those partials ...
+  const int* jl;                          // ... or [B], one per trajectory (per-trajectory ion counts)
   const uint64_t* seeds;                  // [B] Philox key per trajectory or null (all `seed`)
   unsigned long long* stamp;              // {min start, max end} of this launch in %globaltimer ns, or null
   const double* clock;                    // {t, substep index (as uint64 bits)} in device memory: overrides t0/substep0 when non-null

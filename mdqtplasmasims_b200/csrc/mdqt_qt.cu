@@ -184,7 +184,7 @@ double2 load_forces_impl(const double* __restrict__ fpart, double* __restrict__ 
 }
 #define load_forces(a, b, i, c2, store_x, store_2, fx, f2)                                                                       \
   do {                                                                                                                           \
-    const double2 f_ = load_forces_impl((a).fpart, (a).Fw, (a).F, (a).nb ? (a).nb[b] : (a).N, (a).fp_jlen, (a).B, (a).ld, b, i,  \
+    const double2 f_ = load_forces_impl((a).fpart, (a).Fw, (a).F, (a).nb ? (a).nb[b] : (a).N, (a).jl ? (a).jl[b] : (a).fp_jlen, (a).B, (a).ld, b, i,  \
                                         c2, ((store_x) ? 1 : 0) | ((store_2) ? 2 : 0));                                          \
     fx = f_.x; f2 = f_.y;                                                                                                        \
   } while (0)
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
 #if MDQT_K2_FLOAD1
   {
     double fown = 0.0;
-    if (q < 3) fown = load_force1_impl(a.fpart, a.Fw, a.F, a.nb ? a.nb[b] : a.N, a.fp_jlen, a.B, a.ld, b, i, q, active ? 1 : 0);
+    if (q < 3) fown = load_force1_impl(a.fpart, a.Fw, a.F, a.nb ? a.nb[b] : a.N, a.jl ? a.jl[b] : a.fp_jlen, a.B, a.ld, b, i, q, active ? 1 : 0);
     const double fy = __shfl_sync(0xffffffffu, fown, base + 1), fz = __shfl_sync(0xffffffffu, fown, base + 2);
     fx_ = __shfl_sync(0xffffffffu, fown, base);
     f2_ = (q == 1) ? fz : fy;

@@ -55,6 +55,7 @@ if which == "pdl":  # run once with MDQT_PDL=0 and once without (the mode is rea
     for N in (1000, 2048, 3000, 3500, 4096):
         run("items", N)
     run("items", 3653, plan_n=3500)
+    run("items", 3653)
     run("items", 3500, B=8, nmd=4)
 if which == "k1ab":
     run("items", 3500)

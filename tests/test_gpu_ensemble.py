@@ -20,14 +20,18 @@ def _job_state(n, L, seed):
             synthetic.random_full_state(n, 12, seed=seed + 2), np.zeros(n))
 
 
-@pytest.mark.parametrize("N0,counts", [(600, (571, 640, 600, 613, 588)), (3500, (3487, 3561, 3440))])
-def test_variable_n_batch_equals_single_trajectories_bitwise(N0, counts):
+@pytest.mark.parametrize("N0,counts,nominal", [(600, (571, 640, 600, 613, 588), False), (3500, (3487, 3561, 3440), False),
+                                              (3500, (3487, 3653, 3440, 3529), False), (600, (571, 640, 600, 613, 588), True),
+                                              (3500, (3487, 3561, 3440), True)])
+def test_variable_n_batch_equals_single_trajectories_bitwise(N0, counts, nominal):
     """B jobs with different N in one handle (mdqt_set_ion_counts + per-job Philox keys) against B single-trajectory
-    handles with the same plan_n: forces, potential energy, observables and the state after 3 MD steps (quantum jumps
-    included) are bitwise identical."""
+    handles: forces, potential energy, observables and the state after 3 MD steps (quantum jumps included) are bitwise
+    identical. plan_n = 0 (what mdqt_run uses): every trajectory's summation order follows from its own ion count, so the
+    lone job is simply a handle of its own size; plan_n = N0 (`nominal`): one order for all, fixed by the nominal N0."""
     B, cap, traj0 = len(counts), max(counts), 11
+    plan_n = N0 if nominal else 0
     seeds = np.array([1000 + 7 * b for b in range(B)], dtype=np.uint64)
-    pb = su_params(n_ions=cap, N0=N0, n_traj=B, traj0=traj0, plan_n=N0, seed=int(seeds[0]))
+    pb = su_params(n_ions=cap, N0=N0, n_traj=B, traj0=traj0, plan_n=plan_n, seed=int(seeds[0]))
     L = pb.L
     R, V, psi, tp = (np.zeros((B, 3, cap)), np.zeros((B, 3, cap)), np.zeros((B, cap, 12, 2)), np.zeros((B, cap)))
     psi[:, :, 0, 0] = 1.0
@@ -50,7 +54,7 @@ def test_variable_n_batch_equals_single_trajectories_bitwise(N0, counts):
     pv_b = eb.vel_dist()
     jumped = 0
     for b, n in enumerate(counts):
-        e1 = Engine(su_params(n_ions=n, N0=N0, traj0=traj0 + b, plan_n=N0, seed=int(seeds[b])))
+        e1 = Engine(su_params(n_ions=n, N0=N0, traj0=traj0 + b, plan_n=plan_n, seed=int(seeds[b])))
         e1.upload(R=jobs[b][0], V=jobs[b][1], psi=jobs[b][2], tPart=jobs[b][3], t=0.0, substep=0)
         e1.forces()
         assert np.array_equal(e1.download_forces(), Fb[b][:, :n])
