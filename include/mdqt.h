@@ -57,10 +57,11 @@ typedef struct mdqt_params {
   int32_t substeps_per_md; /* plasmaToQuantumTimestepRatio (SU:83) */
   int32_t renormalize;  /* reNormalizewvFns (SU:74) */
   int32_t quad;         /* 7-level only: circular-pump coupling mask of MC408Q:596 */
-  int32_t plan_n;       /* 0, or the NOMINAL ion number (the reference's N0) that fixes the summation order of the force
-                           kernel: handles created with the same plan_n give the same bits for a trajectory whether it runs
-                           alone or batched with others (n_traj > 1), whatever each trajectory's actual ion count. 0: the
-                           order is planned from n_ions (the lane mappings of the substep kernel give identical bits anyway). */
+  int32_t plan_n;       /* 0 (recommended): the summation order of the force kernel for a trajectory follows from that
+                           trajectory's OWN ion count -- n_ions, or its entry in mdqt_set_ion_counts -- so a job gives the
+                           same bits alone (a handle of its size) and inside any batch, and gets the plan that fits its N.
+                           > 0: one order for every trajectory, planned for this NOMINAL ion number (the reference's N0);
+                           handles created with the same plan_n agree bit for bit whatever else they hold. */
   double L;             /* box length (SU:297, MD:73) */
   double kappa;         /* 1/lDeb = sqrt(3 Ge) (SU:295) or kappa (MD:67) */
   double rcut;          /* L/2 (SU:195, MD:74) */

@@ -119,7 +119,8 @@ int mdqt_params_ts(mdqt_params* p, int n_ions, double detuning, double Om) {
 // j-chunks in the same order (bitwise identical forces for any GPU count).
 // Item-walking kernel (k_pairs_items): chunk length for `np` ions, chosen for ONE trajectory on the chip's 148 x 2 x 8
 // resident warps -- the latency-critical case; a batch walks B times as many equal items whatever the choice. A function of
-// np alone (mdqt_params.plan_n, else n_ions): not of the batch size, the row range or the environment.
+// np alone (a trajectory's own ion count -- n_ions, or its entry in mdqt_set_ion_counts -- or the nominal mdqt_params.plan_n): not of
+// the batch size, the row range or the environment.
 static int plan_items_jlen(int np) {
   const long long W = 148LL * 2 * 8;
   const long long G = (np + 31) / 32;

@@ -496,9 +496,10 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 // items, two rows per lane (fewer shared-memory reads and index instructions per pair).
 // Every item writes ONE partial sum and the kernel ends there: no fence, no counter, no reduction. The consumer adds the
 // partials of a row in ascending chunk order -- the substep kernel while it loads its ion (mdqt_qt.cu), k_sum_partials for
-// everybody else. The summation order of a row is therefore a function of jlen alone -- i.e. of mdqt_params.plan_n, not of
+// everybody else. The summation order of a row is therefore a function of the trajectory's chunk length alone -- which follows
+// from the trajectory's OWN ion count (jl[b] = plan_items_jlen(nb[b]); or one nominal length, mdqt_params.plan_n > 0) -- not of
 // the batch size, of the rows per lane, of the trajectory's position in the batch, or of the number of row-owning ranks:
-// a job gives the same bits alone or batched. Trajectories of an ensemble may hold different ion counts nb[b] (SU:299-337).
+// a job gives the same bits alone or batched. Trajectories of an ensemble hold different ion counts nb[b] (SU:299-337).
 // ------------------------------------------------------------------------------------------------------------
 // MDQT_TAB32 1: 8 KB-aligned table addressed as base | offset in one logic instruction (saves the base add the compiler emits inside
 // the per-warp item loop: 44.6 -> 43.6 instructions per pair) -- measured on B200: no gain (28.98 vs 28.66 us at N = 3500), so off

@@ -911,7 +911,7 @@ void launch_substeps(const QTArgs& a, const QTConsts& C, int scheme, cudaStream_
   // MDQT_QT_LANES=2|4 forces one mapping (both stay parity-tested, tests/test_gpu_variants.py).
   static const int lanes_override = [] { const char* e = getenv("MDQT_QT_LANES"); return e ? atoi(e) : 0; }();
   const bool small = 4LL * a.N * a.B <= 148LL * 4 * 32;  // four-lane warps fit one per sub-partition
-  // a.lanes (mdqt_params.plan_n != 0: batch-reproducible mode) pins the mapping so that a job gives the same bits alone or batched
+  // a.lanes pins a mapping (unused: the two mappings give the same bits, so the choice may follow N and B)
   const int want = lanes_override ? lanes_override : a.lanes;
   const bool four = scheme == 12 && a.do_step && (want == 4 || (want != 2 && small));
   if (four) {
