@@ -1,8 +1,10 @@
 set -x
-python bench.py --steps 20 --warmup 5 > gpurun_out/r02m_bench_gpu1.json 2> gpurun_out/r02m_bench_gpu1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02m_bench_reference.json 2> gpurun_out/r02m_bench_reference.err
+timeout 1500 python -m pytest tests -q -m gpu -x > gpurun_out/r02q_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02q_pytest_gpu.log
+python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/r02q_smoke.log 2>&1; tail -2 gpurun_out/r02q_smoke.log
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02q_bench_gpu1.json 2> gpurun_out/r02q_bench_gpu1.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02q_bench_reference.json 2> gpurun_out/r02q_bench_reference.err
 # launch list of one bench command (per-launch times are cold-cache and serialised: the kernels' SHARE of the step is what counts)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02m_launches_mdstep_N3500.csv python bench.py --steps 2 --warmup 3 --ensemble 0 --large-n 0 --large-n2 0 --no-md-family --no-cpu-baseline > gpurun_out/r02m_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02q_launches_mdstep_N3500.csv python bench.py --steps 2 --warmup 3 --ensemble 0 --large-n 0 --large-n2 0 --no-md-family --no-cpu-baseline > gpurun_out/r02q_ncu_launches.log 2>&1
 # full captures of the two hot kernels at the thesis shape and of the pair kernel at large N
 cat > /tmp/prof_small.py <<'PY'
 import sys, numpy as np
@@ -15,16 +17,16 @@ e.upload(R=synthetic.random_positions(N, p.L), V=np.zeros((3, N)), psi=synthetic
 for _ in range(3): e.md_steps(nmd)
 e.sync()
 PY
-ncu --set full --clock-control none --import-source on -k regex:k_pairs_items -s 20 -c 1 -o gpurun_out/r02m_pairs_small -f python /tmp/prof_small.py 3500 10 > gpurun_out/r02m_ncu_pairs_small.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_substeps4 -s 20 -c 1 -o gpurun_out/r02m_sub_small -f python /tmp/prof_small.py 3500 10 > gpurun_out/r02m_ncu_sub_small.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_pairs -s 2 -c 1 -o gpurun_out/r02m_pairs_large -f python /tmp/prof_small.py 100000 1 > gpurun_out/r02m_ncu_pairs_large.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pairs_items -s 20 -c 1 -o gpurun_out/r02q_pairs_small -f python /tmp/prof_small.py 3500 10 > gpurun_out/r02q_ncu_pairs_small.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_substeps4 -s 20 -c 1 -o gpurun_out/r02q_sub_small -f python /tmp/prof_small.py 3500 10 > gpurun_out/r02q_ncu_sub_small.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_pairs -s 2 -c 1 -o gpurun_out/r02q_pairs_large -f python /tmp/prof_small.py 100000 1 > gpurun_out/r02q_ncu_pairs_large.log 2>&1
 ls -la gpurun_out/ | tail -12
-tail -c 600 gpurun_out/r02m_bench_gpu1.err
+tail -c 600 gpurun_out/r02q_bench_gpu1.err
 D=/tmp/mdqt_one; rm -rf $D; mkdir -p $D
-( time ./mdqtplasmasims_b200/mdqt_run 1 --tmax 30 --seed 7 --saveDirectory $D/a/ ) > gpurun_out/r02m_thesis_run.log 2>&1
-( time ./mdqtplasmasims_b200/mdqt_run 1 --tmax 30 --seed 7 --fast-single --saveDirectory $D/b/ ) >> gpurun_out/r02m_thesis_run.log 2>&1
-( time ./mdqtplasmasims_b200/mdqt_run 2 --tmax 30 --seed 7 --saveDirectory $D/c/ ) >> gpurun_out/r02m_thesis_run.log 2>&1
-grep -v "^[0-9]*$" gpurun_out/r02m_thesis_run.log | tail -16
+( time ./mdqtplasmasims_b200/mdqt_run 1 --tmax 30 --seed 7 --saveDirectory $D/a/ ) > gpurun_out/r02q_thesis_run.log 2>&1
+( time ./mdqtplasmasims_b200/mdqt_run 1 --tmax 30 --seed 7 --saveDirectory $D/b/ ) >> gpurun_out/r02q_thesis_run.log 2>&1
+( time ./mdqtplasmasims_b200/mdqt_run 2 --tmax 30 --seed 7 --saveDirectory $D/c/ ) >> gpurun_out/r02q_thesis_run.log 2>&1
+grep -v "^[0-9]*$" gpurun_out/r02q_thesis_run.log | tail -16
 rm -rf $D
-python scripts/quick2.py small > gpurun_out/r02m_quick.log 2>&1; python scripts/quick2.py batch >> gpurun_out/r02m_quick.log 2>&1; python scripts/quick2.py large >> gpurun_out/r02m_quick.log 2>&1
-cat gpurun_out/r02m_quick.log
+python scripts/quick2.py small > gpurun_out/r02q_quick.log 2>&1; python scripts/quick2.py batch >> gpurun_out/r02q_quick.log 2>&1; python scripts/quick2.py large >> gpurun_out/r02q_quick.log 2>&1
+cat gpurun_out/r02q_quick.log

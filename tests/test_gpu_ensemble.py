@@ -139,3 +139,33 @@ def test_mdqt_run_array_reproduces_single_jobs(tmp_path):
         pop = np.loadtxt(os.path.join(da, "statePopulationsVsVTime000001.dat"))
         assert pop[:, 2].mean() > 0.05  # lasers on: P population present, so jumps happened
     assert len(ns) > 1  # the jobs really had different ion numbers
+
+
+def test_ion_counts_can_be_changed_and_reset():
+    """mdqt_set_ion_counts re-plans the item kernel (per-trajectory chunk lengths, partial-sum buffers): setting counts, changing
+    them and clearing them again leaves a handle that gives the bits of a fresh one."""
+    n, B = 1400, 3
+    p = su_params(n_ions=n, N0=n, n_traj=B)
+    R = np.stack([synthetic.random_positions(n, p.L, seed=70 + b) for b in range(B)])
+    fresh = Engine(p)
+    fresh.upload(R=R)
+    fresh.forces()
+    F0, E0 = fresh.download_forces(), fresh.Epotential()
+    e = Engine(p)
+    e.upload(R=R)
+    e.set_ion_counts((700, 1400, 333))   # small trajectories need MORE chunk slots than the uniform plan holds
+    e.forces()
+    F1 = e.download_forces()
+    for b, nb in enumerate((700, 1400, 333)):
+        one = Engine(su_params(n_ions=nb, N0=n))
+        one.upload(R=np.ascontiguousarray(R[b][:, :nb]))
+        one.forces()
+        assert np.array_equal(one.download_forces(), F1[b][:, :nb]), b
+        one.close()
+    e.set_ion_counts((1399, 5, 1400))
+    e.forces()
+    assert np.all(np.isfinite(e.download_forces()))
+    e.set_ion_counts(None)
+    e.forces()
+    assert np.array_equal(e.download_forces(), F0) and np.array_equal(e.Epotential(), E0)
+    e.close(); fresh.close()

@@ -134,7 +134,7 @@ def test_vel_dist_tagged_vs_numpy():
     vt = V[0][(tags & 1).astype(bool)]
     want = np.exp(-(vel[:, None] - vt[None, :]) ** 2 / (2 * 0.002 ** 2)).sum(axis=1) / (6.0 * np.sqrt(2 * np.pi * 0.002 ** 2))
     big = want > 1e-250  # deep in the tails the sums are subnormal: exp() implementations differ there
-    assert big.sum() > 1000 and np.allclose(pv[big], want[big], rtol=1e-11) and np.all(pv[~big] < 1e-240)
+    assert big.sum() > 500 and np.allclose(pv[big], want[big], rtol=1e-11) and np.all(pv[~big] < 1e-240)
     e.close()
 
 
