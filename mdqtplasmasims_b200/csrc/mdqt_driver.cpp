@@ -401,7 +401,7 @@ static int run_rows(const Options& o, unsigned job, int G, std::vector<std::uniq
 }
 
 static void usage() {
-  fprintf(stderr, "usage: mdqt_run [--program su|md|fz408l|mc408l] <job> | --jobs a-b [--batch n] [--gpus n]\n"
+  fprintf(stderr, "usage: mdqt_run [--program su|md|fz408l|mc408l|mc422l] <job> | --jobs a-b [--batch n] [--gpus n]\n"
                   "       [--Ge x] [--density x] [--sig0 x] [--Te x] [--fracOfSig x] [--N0 n] [--detuning x] [--detuningDP x] [--Om x]\n"
                   "       [--OmDP x] [--saveDirectory dir/] [--newRun 0|1] [--c0 n] [--tmax x] [--reNormalizewvFns 0|1] [--sampleFreq n]\n"
                   "       [--seed n] [--device n] [--writers n] [--fast-single] [--quiet]\n");
@@ -410,6 +410,7 @@ static void usage() {
 int mdqt_program_md(int argc, char** argv);      // mdqt_programs.cpp
 int mdqt_program_fz408l(int argc, char** argv);
 int mdqt_program_mc408l(int argc, char** argv);
+int mdqt_program_mc422l(int argc, char** argv);
 
 int main(int argc, char** argv) {
   if (argc < 2) { usage(); return 2; }
@@ -421,7 +422,8 @@ int main(int argc, char** argv) {
     if (!strcmp(argv[2], "md")) return mdqt_program_md((int)av.size(), av.data());
     if (!strcmp(argv[2], "fz408l")) return mdqt_program_fz408l((int)av.size(), av.data());
     if (!strcmp(argv[2], "mc408l")) return mdqt_program_mc408l((int)av.size(), av.data());
-    if (strcmp(argv[2], "su")) { fprintf(stderr, "mdqt_run: unknown program %s (su, md, fz408l, mc408l)\n", argv[2]); return 2; }
+    if (!strcmp(argv[2], "mc422l")) return mdqt_program_mc422l((int)av.size(), av.data());
+    if (strcmp(argv[2], "su")) { fprintf(stderr, "mdqt_run: unknown program %s (su, md, fz408l, mc408l, mc422l)\n", argv[2]); return 2; }
     argc = (int)av.size();
     static std::vector<char*> keep;
     keep = av;

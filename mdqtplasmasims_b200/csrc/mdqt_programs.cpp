@@ -6,7 +6,7 @@
 //            autocorrelations, the instantaneous-anisotropy stage, re-equilibration, and the laser-force anisotropy stages.
 //   fz408l   randomFrozenStartTag408Linear.cpp main() (FZ408L:981-1076): frozen random start, leap-frog time loop with the
 //            408 nm pump window, spin measurement and the tagged velocity autocorrelation.
-//   mc408l   MonteCarloFollowedByQTTagging408Linear.cpp main() (MC408L:1140-1254), stages 1, 4-7: collisional MD, the pump stage
+//   mc408l, mc422l   MonteCarloFollowedByQTTagging408Linear.cpp / ...422Linear.cpp main() (MC408L:1140-1254, MC422L:1100-1222), stages 1, 4-7: collisional MD, the pump stage
 //            (62 x 7-level qstep() per MDStep), the projective spin measurement, the recording stage with the tagged ions' moments
 //            and velocity distribution, the autocorrelations.
 //
@@ -422,12 +422,16 @@ int mdqt_program_fz408l(int argc, char** argv) {
 // { ratio x qstep(); MDStep(k) } x pumpMDTimeSteps, tagParticles() (projective spin measurement), then the collisionless
 // recording stage -- taggedMoments.dat and vel_distX_timestep%06d.dat every step (MC408L:1069-1137), g(r) every 100 steps,
 // temperature.dat -- and the four autocorrelation files.
-int mdqt_program_mc408l(int argc, char** argv) {
+// The same main() serves MonteCarloFollowedByQTTagging422Linear.cpp (MC422L:1100-1222; `ca5`): the 5-level 422 nm pump scheme with
+// its own unit conversions (mdqt_params_md, MC422L:113-122) and defaults (tpumpreal 5e-8, detuning -1, Om 1.3: MC422L:85-87), the
+// same init() draws (MC422L:196-238) into a 5-state wavefunction, and a "Date%m%d%y" suffix on the run directory (MC422L:1127-1134).
+static int program_mc_tagging(int argc, char** argv, bool ca5) {
   OptMap opt = {{"N", "4096"}, {"Gamma", "3"}, {"kappa", "0.5"}, {"density", "2"}, {"timeStep", "0.005"}, {"collisionFreq", "0.25"},
-                {"preSteps", "200"}, {"recordSteps", "1500"}, {"pumpSteps", "-1"}, {"tpumpreal", "0.0000002"}, {"detuning", "-2.5"}, {"Om", "0.7"},
-                {"quad", "0"}, {"pairPairStep", "0.05"}, {"seed", ""}, {"saveDirectory", "data/"}, {"device", "0"}, {"program", "mc408l"}};
+                {"preSteps", "200"}, {"recordSteps", "1500"}, {"pumpSteps", "-1"}, {"tpumpreal", ca5 ? "0.00000005" : "0.0000002"},
+                {"detuning", ca5 ? "-1" : "-2.5"}, {"Om", ca5 ? "1.3" : "0.7"}, {"quad", "0"}, {"pairPairStep", "0.05"}, {"seed", ""},
+                {"saveDirectory", "data/"}, {"device", "0"}, {"program", ca5 ? "mc422l" : "mc408l"}, {"dateSuffix", ca5 ? "1" : "0"}};
   bool quiet = false;
-  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program mc408l <job> [--N n] [--density x] [--tpumpreal x] ...\n"); return 2; }
+  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program mc408l|mc422l <job> [--N n] [--density x] [--tpumpreal x] ...\n"); return 2; }
   const unsigned job = (unsigned)atof(argv[1]);
   if (!parse_opts(argc, argv, 2, opt, &quiet)) return 2;
   const int N = atoi(opt["N"].c_str());
@@ -448,20 +452,28 @@ int mdqt_program_mc408l(int argc, char** argv) {
            as_unsigned_printed(kappa * 100), N, as_unsigned_printed(1000000000. * tpumpreal), as_unsigned_printed(100. * fabs(detuning)),
            as_unsigned_printed(100. * Om), as_unsigned_printed(10. * n));  // MC408L:1153
   dir += namebuf;
+  if (atoi(opt["dateSuffix"].c_str())) {  // MC422L:1127-1134 (--dateSuffix 0 for a reproducible path)
+    time_t rawtime;
+    time(&rawtime);
+    char st[80];
+    strftime(st, sizeof(st), "Date%m%d%y", localtime(&rawtime));
+    dir += st;
+  }
   mkdir(dir.c_str(), 0777);
   snprintf(namebuf, sizeof(namebuf), "/job%d/", (int)job);
   dir += namebuf;
   mkdir(dir.c_str(), 0777);
 
   mdqt_params p;
-  CKP(mdqt_params_md(&p, MDQT_SCHEME_SR7, N, kappa, n, timeStep, detuning, Om, atoi(opt["quad"].c_str())));
+  CKP(mdqt_params_md(&p, ca5 ? MDQT_SCHEME_CA5 : MDQT_SCHEME_SR7, N, kappa, n, timeStep, detuning, Om, atoi(opt["quad"].c_str())));
+  const int S2 = ca5 ? 10 : 14;  // doubles per ion of the wavefunction: 5 or 7 states x (re, im)
   p.traj0 = (int)job; p.seed = seed; p.device = atoi(opt["device"].c_str());
   const double L = p.L;
   // init() (MC408L:196-250): per lattice site three normal draws (mt19937), then rand1..rand4 from drand48 in its default state
   std::mt19937 rng(seed);
   std::normal_distribution<double> velocityDistribution(0, sqrt(1 / Gamma));
   unsigned short xs[3] = {0x330E, 0xABCD, 0x1234};  // the initial state of an unseeded drand48 (the reference never calls srand48, Q14)
-  std::vector<double> R((size_t)3 * N, 0.0), V((size_t)3 * N, 0.0), psi((size_t)N * 14, 0.0);
+  std::vector<double> R((size_t)3 * N, 0.0), V((size_t)3 * N, 0.0), psi((size_t)N * S2, 0.0);
   {
     int N0 = 0;
     const int side = (int)round(pow(N, 1. / 3));
@@ -475,7 +487,7 @@ int mdqt_program_mc408l(int argc, char** argv) {
           const double sign = rand3 < 0.5 ? -1 : 1;
           const double rand4 = erand48(xs);
           const double sign2 = rand4 < 0.5 ? -1 : 1;
-          double* w = &psi[(size_t)N0 * 14];
+          double* w = &psi[(size_t)N0 * S2];  // sqrt(rand1) |1> + (sign2 sqrt(..) + i sign sqrt(..)) |2>  (MC408L:232-236, MC422L:232-236)
           w[0] = sqrt(rand1); w[2] = sign2 * sqrt(1 - rand1) * sqrt(rand2); w[3] = sign * sqrt(1 - rand1) * sqrt(1 - rand2);
           N0++;
         }
@@ -535,8 +547,10 @@ int mdqt_program_mc408l(int argc, char** argv) {
   CKP(mdqt_sync(h));
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
   if (!quiet)
-    fprintf(stderr, "mdqt_run: program mc408l, job %u, N=%d: %d collisional + %d pump (x %d qstep) + %d recorded MD steps, %d of %d ions tagged, %.3f s; files in %s\n",
-            job, N, preSteps, pumpSteps, p.substeps_per_md, recSteps, (int)nup, N, wall, dir.c_str());
+    fprintf(stderr, "mdqt_run: program %s, job %u, N=%d: %d collisional + %d pump (x %d qstep) + %d recorded MD steps, %d of %d ions tagged, %.3f s; files in %s\n",
+            ca5 ? "mc422l" : "mc408l", job, N, preSteps, pumpSteps, p.substeps_per_md, recSteps, (int)nup, N, wall, dir.c_str());
   mdqt_destroy(h);
   return 0;
 }
+int mdqt_program_mc408l(int argc, char** argv) { return program_mc_tagging(argc, argv, false); }
+int mdqt_program_mc422l(int argc, char** argv) { return program_mc_tagging(argc, argv, true); }

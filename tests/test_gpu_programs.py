@@ -138,15 +138,20 @@ def test_vel_dist_tagged_vs_numpy():
     e.close()
 
 
-def test_mc408l_program_writes_consistent_files(tmp_path):
-    """`mdqt_run --program mc408l` (collisional MD, pump, spin measurement, recording stage): the files exist in the reference's
-    shapes, and the two things it writes about the tagged ions agree with each other -- the integral of vel_distX_timestep k is
-    numTagged / 6, and its first and second moments are the taggedMoments.dat row k."""
+@pytest.mark.parametrize("program,prefix", [("mc408l", "Gamma300Kappa50NumIons512PumpTime200Det250Om70Density20"),
+                                            ("mc422l", "Gamma300Kappa50NumIons512PumpTime")])
+def test_mc_tagging_programs_write_consistent_files(tmp_path, program, prefix):
+    """`mdqt_run --program mc408l | mc422l` (collisional MD, pump with the 7- resp. 5-level scheme, spin measurement, recording
+    stage): the files exist in the reference's shapes, and the two things it writes about the tagged ions agree with each other --
+    the integral of vel_distX_timestep k is numTagged / 6, and its first and second moments are the taggedMoments.dat row k."""
     save = str(tmp_path) + "/"
-    r = subprocess.run([DRIVER, "--program", "mc408l", "3", "--N", "512", "--seed", "17", "--preSteps", "20", "--pumpSteps", "6", "--recordSteps", "12",
+    r = subprocess.run([DRIVER, "--program", program, "3", "--N", "512", "--seed", "17", "--preSteps", "20", "--pumpSteps", "6", "--recordSteps", "12",
                         "--saveDirectory", save, "--quiet"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
-    d = os.path.join(save, "Gamma300Kappa50NumIons512PumpTime200Det250Om70Density20", "job3")
+    runs = [x for x in os.listdir(save) if x.startswith(prefix)]
+    assert len(runs) == 1, os.listdir(save)
+    assert ("Date" in runs[0]) == (program == "mc422l")   # MC422L:1127-1134 appends the date to the run directory
+    d = os.path.join(save, runs[0], "job3")
     assert os.path.isdir(d), os.listdir(save)
     tm = _table(open(os.path.join(d, "taggedMoments.dat")).read())
     assert tm.shape == (12, 5) and np.allclose(tm[:, 0], np.arange(12) * 0.005)
@@ -158,7 +163,7 @@ def test_mc408l_program_writes_consistent_files(tmp_path):
         pv = _table(open(os.path.join(d, "vel_distX_timestep%06d.dat" % k)).read())
         assert pv.shape == (4001, 2)
         ntag = pv[:, 1].sum() * 0.0025 * 6
-        assert abs(ntag - round(ntag)) < 1e-3 and 0.2 * 512 < ntag < 0.8 * 512     # an integer number of spin-up ions, roughly half
+        assert abs(ntag - round(ntag)) < 1e-3 and 0.05 * 512 < ntag < 0.95 * 512   # an integer number of tagged ions, a sizeable fraction
         m1 = (pv[:, 0] * pv[:, 1]).sum() / pv[:, 1].sum()
         m2 = (pv[:, 0] ** 2 * pv[:, 1]).sum() / pv[:, 1].sum() - 0.002 ** 2         # minus the kernel's own variance
         assert abs(m1 - tm[k, 1]) < 2e-5 and abs(m2 - tm[k, 2]) < 2e-5 * max(1.0, tm[k, 2])
