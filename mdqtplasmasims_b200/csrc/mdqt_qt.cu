@@ -592,7 +592,9 @@ struct Lane4H {
 //   MDQT_K2_PIPE    1: the next substep's Doppler shift, rotating phase, sin/cos and coefficients are computed right after
 //                      this substep's optical-force kick is known, overlapping the Runge-Kutta chains; recomputed on a jump
 #ifndef MDQT_K2_DPLOCAL
-#define MDQT_K2_DPLOCAL 1  // measured on B200, N = 3500, 25 substeps in the replayed graph: 23.6 us (0: 28.2; DPSTAGE 24.3; PIPE 24.9; all three 28.6)
+#define MDQT_K2_DPLOCAL 0  // measured on B200, N = 3500, 25 substeps in the replayed graph, with __launch_bounds__(32): 21.9 us (1: 22.1). With
+                           // __launch_bounds__(128) it was the other way round (1: 23.6 -> 22.6 with the one-round-trip force prologue; 0: 28.2):
+                           // the variants differ in ptxas' schedule of the loop, not in work (DPSTAGE 23.6; PIPE 22.6-23.5; PHILOX4 22.1-31.2)
 #endif
 #ifndef MDQT_K2_DPSTAGE
 #define MDQT_K2_DPSTAGE 0
@@ -646,8 +648,16 @@ __device__ __forceinline__ double stage4(const Lane4H& H, const cplx* w, cplx* g
   return own;
 }
 
+// the kernel is launched as one-warp CTAs; telling ptxas so (instead of 128) gives a schedule that is 0.4 us faster
+#ifndef MDQT_K2_LB
+#define MDQT_K2_LB 32
+#endif
+#ifndef MDQT_K2_UNROLL
+#define MDQT_K2_UNROLL 1
+#endif
+constexpr int kK2Unroll = MDQT_K2_UNROLL;
 template <bool FORCED>
-__global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
+__global__ void __launch_bounds__(MDQT_K2_LB) k_substeps4(QTArgs a, QTConsts C) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int q = gid & 3, blk = q >> 1, half = q & 1;
   const long long slot = gid >> 2;
@@ -737,6 +747,7 @@ __global__ void __launch_bounds__(128) k_substeps4(QTArgs a, QTConsts C) {
   double uq0 = 0.0, uq1 = 0.0;
 #endif
 
+#pragma unroll(kK2Unroll)
   for (int s = 0; s < a.nsub; s++) {
     {  // step() (SU:356-430)
       const bool started = t > 0;
