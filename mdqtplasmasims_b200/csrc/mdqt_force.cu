@@ -508,6 +508,13 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 #endif
 // 16 resident warps per SM either way: two CTAs of 8 warps, or -- for batches (two rows per lane), where it is 4 % faster
 // (5.08e11 vs 4.88e11 pairs/s at 64 x 3500) -- one CTA of 16; the bits do not depend on it
+#ifndef MDQT_K1_UNR1
+#define MDQT_K1_UNR1 8
+#endif
+#ifndef MDQT_K1_UNR2
+#define MDQT_K1_UNR2 4
+#endif
+constexpr int kItemUnroll1 = MDQT_K1_UNR1, kItemUnroll2 = MDQT_K1_UNR2;  // j-loop unroll with one / two rows per lane (A/B knobs)
 constexpr int kItemResidentWarps = 16;
 constexpr int kItemMaxB = 512;   // per-trajectory ion counts cached in shared memory up to this batch size
 constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps = 120 KB per CTA at most
@@ -625,7 +632,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
     }
     const int cnt = min(cur.jl, cur.Nb - cur.ch * cur.jl);
     WTRACE(2)
-#pragma unroll(IPT == 2 ? 4 : 8)
+#pragma unroll(IPT == 2 ? kItemUnroll2 : kItemUnroll1)
     for (int jj = 0; jj < cnt; jj++) {
       const longlong2 pxy = sxy[jj];
       const long long pz = sz[jj];
