@@ -488,6 +488,56 @@ def gen_su_coupled(procs=7):
            np.mean([r["pops"][-1, 1] for r in res])))
 
 
+# ---- the MC-tagging programs' own stages 4-6, statistically -------------------------------------------
+MCPROG = dict(npre=200, nrec=200, seeds=list(range(301, 309)))
+
+
+def mc_program_worker(job):
+    """One run of main()'s stages 4-6 of MC408L (MC408L:1211-1244) or MC422L (MC422L:1178-1211) by the reference's own functions
+    (ref_mc_run_stages / ref_m422_run_stages: collisional MD, the pump stage with the reference's pumpMDTimeSteps and ratio,
+    tagParticles(), the recording stage), after init() under `seed`, 1 thread, its own mt19937 + drand48 streams. The Metropolis
+    stage is skipped exactly as `mdqt_run --program mc408l|mc422l` skips it. Returns the parsed
+    taggedMoments.dat and temperature.dat, the number of tagged ions and the mean level populations after the pump."""
+    import shutil
+    import tempfile
+    which, seed = job
+    ref = po.RefMC408L() if which == "mc408l" else po.RefMC422L()
+    pre = "ref_mc" if which == "mc408l" else "ref_m422"
+    getattr(ref.lib, pre + "_init")(ctypes.c_uint(seed))
+    run = getattr(ref.lib, pre + "_run_stages")
+    run.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double]
+    d = tempfile.mkdtemp() + "/"
+    npump = int(ref.consts["pumpMDTimeSteps"])
+    ntag = run(d.encode(), MCPROG["npre"], npump, MCPROG["nrec"], 0.25)
+    tm = np.loadtxt(os.path.join(d, "taggedMoments.dat"), ndmin=2)
+    temp = np.loadtxt(os.path.join(d, "temperature.dat"), ndmin=1)
+    vd0 = np.loadtxt(os.path.join(d, "vel_distX_timestep%06d.dat" % 0), ndmin=2)[:, 1]
+    psi = ref.get_state()["psi"]
+    shutil.rmtree(d, ignore_errors=True)
+    return dict(which=which, seed=seed, ntag=ntag, npump=npump, ratio=int(ref.consts["ratio"]), moments=tm, temperature=temp,
+                vel_dist0=vd0, pops=(psi ** 2).sum(axis=2).mean(axis=0))
+
+
+def gen_mc_programs(procs=8):
+    import multiprocessing as mp
+    jobs = [(w, s) for s in MCPROG["seeds"] for w in ("mc408l", "mc422l")]
+    with mp.get_context("spawn").Pool(procs) as pool:
+        res = pool.map(mc_program_worker, jobs, chunksize=1)
+    out = dict(npre=MCPROG["npre"], nrec=MCPROG["nrec"], seeds=np.array(MCPROG["seeds"]))
+    for w in ("mc408l", "mc422l"):
+        rs = [r for r in res if r["which"] == w]
+        out[w + "_ntag"] = np.array([r["ntag"] for r in rs])
+        out[w + "_npump"] = rs[0]["npump"]
+        out[w + "_ratio"] = rs[0]["ratio"]
+        out[w + "_moments"] = np.stack([r["moments"] for r in rs])
+        out[w + "_temperature"] = np.stack([r["temperature"] for r in rs])
+        out[w + "_vel_dist0"] = np.stack([r["vel_dist0"] for r in rs]).astype(np.float32)
+        out[w + "_pops"] = np.stack([r["pops"] for r in rs])
+        print(w, "ntag", out[w + "_ntag"], "npump", rs[0]["npump"], "m1(0)", out[w + "_moments"][:, 0, 1].mean(),
+              "m1(end)", out[w + "_moments"][:, -1, 1].mean(), "T(0)", out[w + "_temperature"][:, 0].mean(), "pops", out[w + "_pops"].mean(axis=0))
+    np.savez_compressed(os.path.join(OUT, "mc_programs.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     po.build()
@@ -511,6 +561,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if "--coupled" in sys.argv:
         gen_su_coupled()
+        sys.exit(0)
+    if "--mcprograms" in sys.argv:
+        gen_mc_programs()
         sys.exit(0)
     gen_su_forces()
     gen_su_nojump()

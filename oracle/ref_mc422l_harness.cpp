@@ -89,4 +89,32 @@ void ref_m422_qstep() { qstep(); }
 void ref_m422_tag(int* out) { tagParticles(); for (int i = 0; i < N; i++) out[i] = tagged[i] ? 1 : 0; }
 void ref_m422_accelerations() { calculateAccelerations(0); }
 void ref_m422_mdstep() { MDStep(0); }
+// init() again under a chosen seed (its mt19937 draws and, for the wavefunctions, drand48), then main()'s stages 4-6
+// (MC422L:1178-1211) with run-time step counts (the reference's are compile-time constants): every call the reference's own function in
+// the reference's order -- collisional MD, collisionFreq = 0, pump {ratio x qstep(); MDStep(k)}, tagParticles(), then per recorded
+// step recordTaggedParticleMoments(k); k % 100 == 0 -> recordPairPairCorr(k); recordTemperature(); MDStep(k);
+// recordVelsForAutocorrelations(k). Files go to `dir` (trailing '/'). Returns the number of tagged ions.
+void ref_m422_init(unsigned s) { rng.seed(s); velocityDistribution.reset(); uni.reset(); srand48(s); init(); memset(A, 0, sizeof(A)); }
+int ref_m422_run_stages(const char* dir, int npre, int npump, int nrec, double collFreq) {
+  ::mkdir(dir, 0777);
+  strcpy(saveDirectory, dir);
+  collisionFreq = collFreq;
+  for (int k = 0; k < npre; k++) MDStep(k);
+  collisionFreq = 0;
+  for (int k = 0; k < npump; k++) {
+    for (int l = 0; l < plasmaToQuantumTimestepRatio; l++) qstep();
+    MDStep(k);
+  }
+  tagParticles();
+  int ntag = 0;
+  for (int i = 0; i < N; i++) ntag += tagged[i] ? 1 : 0;
+  for (int k = 0; k < nrec; k++) {
+    recordTaggedParticleMoments(k);
+    if (k % 100 == 0) recordPairPairCorr(k);
+    recordTemperature();
+    MDStep(k);
+    recordVelsForAutocorrelations(k);
+  }
+  return ntag;
+}
 }
