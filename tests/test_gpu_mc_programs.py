@@ -51,6 +51,7 @@ def test_mc_program_runs_match_the_reference_runs_statistically(tmp_path, golden
     obs, names = mc_stats.observables(np.array(frac), np.stack(mom), np.stack(temp))
     # the default pump length is the reference's pumpMDTimeSteps (MC408L:119-120): nothing is passed on the command line
     ok, rows = mc_stats.compare(obs, fx["obs"], names, tmax=6.0, rel=dict(default=0.05, m1=0.25, T=0.03))
+    print("\n".join("%-18s ours %.6g  reference %.6g  t %+.2f  %s" % r for r in rows))
     assert ok, rows
     # the tagged ions' velocity distribution at the first recorded step, pooled over the runs: Kolmogorov-Smirnov distance of
     # the two cumulative distributions (16 x ~2000 against 8 x ~2000 ions: D(alpha = 1e-3) = 0.017)
