@@ -163,6 +163,9 @@ int mdqt_advance_time(mdqt_handle* h, int nsub);
 int mdqt_tag_particles(mdqt_handle* h, int32_t* tagged, int32_t* n_tagged);
 /* Zfunc() (FZ408L:938-961): velocity autocorrelation <v_x(t0) v_x(t)>; start != 0 stores v_x(t0) first. vaf[n_traj]. */
 int mdqt_vaf(mdqt_handle* h, int start, double* vaf);
+/* Zfunc() of the Quad program (randomFrozenStartTag408Quad.cpp:942-967): the v_x^2 autocorrelation "LongKin"
+ * sum_j (1/N) (v_x(t0)^2 - a)(v_x(t)^2 - a) with a = <v_x(t)^2>; start != 0 stores v_x(t0) first. out[n_traj]. */
+int mdqt_vsq_autocorr(mdqt_handle* h, int start, double* out);
 
 /* Test hook: replace the Philox stream by caller-supplied uniforms u[nsub][n_ions][5] (rand, rand2, randDOrS,
  * randDir, rand3) for the next substeps/qsteps calls (n_traj must be 1). NULL restores Philox. */

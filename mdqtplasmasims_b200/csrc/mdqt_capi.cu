@@ -1029,7 +1029,7 @@ int mdqt_set_forced_tag_uniforms(mdqt_handle* h, const double* u) {
   return MDQT_OK;
 }
 
-int mdqt_vaf(mdqt_handle* h, int start, double* vaf) {
+static int vaf_impl(mdqt_handle* h, int start, double* vaf, int squares) {
   if (!h || !vaf) return fail(MDQT_EINVAL, "null argument");
   NEED_UNIFORM_N(h);
   if (h->nrows != h->N) return fail(MDQT_ESTATE, "mdqt_vaf: a row-decomposed handle holds the velocities of its own rows only");
@@ -1040,12 +1040,15 @@ int mdqt_vaf(mdqt_handle* h, int start, double* vaf) {
   }
   if (start)  // Vholder[j] = V[0][j] (FZ408L:949-954)
     CU(cudaMemcpy2DAsync(h->vhold, (size_t)h->ld * 8, h->V, (size_t)3 * h->ld * 8, (size_t)h->ld * 8, h->B, cudaMemcpyDeviceToDevice, h->stream));
-  launch_vaf(h->V, h->vhold, h->N, h->ld, h->B, h->scalars, h->stream);
+  launch_vaf(h->V, h->vhold, h->N, h->ld, h->B, h->scalars, h->stream, squares);
   CU(cudaMemcpyAsync(vaf, h->scalars, (size_t)h->B * 8, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaGetLastError());
   return MDQT_OK;
 }
+
+int mdqt_vaf(mdqt_handle* h, int start, double* vaf) { return vaf_impl(h, start, vaf, 0); }
+int mdqt_vsq_autocorr(mdqt_handle* h, int start, double* out) { return vaf_impl(h, start, out, 1); }
 
 int mdqt_pair_correlation(mdqt_handle* h, double step, double rmax, int nbins, double* g, uint64_t* counts) {
   if (!h || (!g && !counts)) return fail(MDQT_EINVAL, "null argument");

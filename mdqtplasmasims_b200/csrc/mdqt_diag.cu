@@ -126,8 +126,29 @@ __global__ void __launch_bounds__(1024) k_vaf(const double* __restrict__ V, cons
   s = block_sum_1024(s, sred);
   if (threadIdx.x == 0) out[b] = s;
 }
-void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s) {
-  k_vaf<<<B, 1024, 0, s>>>(V, Vhold, N, ld, out);
+// Zfunc() of the Quad program (FZ408Q:942-967): the v_x^2 ("longitudinal stress") autocorrelation
+// out[b] = sum_j (1/N) (Vhold_x[j]^2 - a) (V_x[j]^2 - a), a = <V_x^2> NOW (FZ408Q:947-952); two fixed-order block reductions
+__global__ void __launch_bounds__(1024) k_vsq_autocorr(const double* __restrict__ V, const double* __restrict__ Vhold, int N, int ld,
+                                                       double* __restrict__ out) {
+  __shared__ double sred[32];
+  __shared__ double savg;
+  const int b = blockIdx.x;
+  const double* vx = V + (size_t)b * 3 * ld;
+  const double* v0 = Vhold + (size_t)b * ld;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += vx[i] * vx[i];
+  s = block_sum_1024(s, sred);
+  if (threadIdx.x == 0) savg = s / N;
+  __syncthreads();
+  const double a = savg, invN = 1 / ((double)N);
+  s = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s += invN * (v0[i] * v0[i] - a) * (vx[i] * vx[i] - a);
+  s = block_sum_1024(s, sred);
+  if (threadIdx.x == 0) out[b] = s;
+}
+void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s, int squares) {
+  if (squares) k_vsq_autocorr<<<B, 1024, 0, s>>>(V, Vhold, N, ld, out);
+  else k_vaf<<<B, 1024, 0, s>>>(V, Vhold, N, ld, out);
 }
 
 // ------------------------------------------------------------------------------------------------------------

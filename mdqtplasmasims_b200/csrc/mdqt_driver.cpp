@@ -409,21 +409,27 @@ static void usage() {
 
 int mdqt_program_md(int argc, char** argv);      // mdqt_programs.cpp
 int mdqt_program_fz408l(int argc, char** argv);
+int mdqt_program_fz408q(int argc, char** argv);
+int mdqt_program_fz422l(int argc, char** argv);
+int mdqt_program_ts(int argc, char** argv);
 int mdqt_program_mc408l(int argc, char** argv);
 int mdqt_program_mc422l(int argc, char** argv);
 
 int main(int argc, char** argv) {
   if (argc < 2) { usage(); return 2; }
-  // mdqt_run --program md|fz408l <job> [options]: the host loops of the reference's other programs (mdqt_programs.cpp)
+  // mdqt_run --program md|fz408l|fz408q|fz422l|mc408l|mc422l|ts <job> [options]: the host loops of the reference's other programs (mdqt_programs.cpp)
   if (argc >= 3 && !strcmp(argv[1], "--program")) {
     std::vector<char*> av;
     av.push_back(argv[0]);
     for (int i = 3; i < argc; i++) av.push_back(argv[i]);
     if (!strcmp(argv[2], "md")) return mdqt_program_md((int)av.size(), av.data());
     if (!strcmp(argv[2], "fz408l")) return mdqt_program_fz408l((int)av.size(), av.data());
+    if (!strcmp(argv[2], "fz408q")) return mdqt_program_fz408q((int)av.size(), av.data());
+    if (!strcmp(argv[2], "fz422l")) return mdqt_program_fz422l((int)av.size(), av.data());
+    if (!strcmp(argv[2], "ts")) return mdqt_program_ts((int)av.size(), av.data());
     if (!strcmp(argv[2], "mc408l")) return mdqt_program_mc408l((int)av.size(), av.data());
     if (!strcmp(argv[2], "mc422l")) return mdqt_program_mc422l((int)av.size(), av.data());
-    if (strcmp(argv[2], "su")) { fprintf(stderr, "mdqt_run: unknown program %s (su, md, fz408l, mc408l, mc422l)\n", argv[2]); return 2; }
+    if (strcmp(argv[2], "su")) { fprintf(stderr, "mdqt_run: unknown program %s (su, md, fz408l, fz408q, fz422l, mc408l, mc422l, ts)\n", argv[2]); return 2; }
     argc = (int)av.size();
     static std::vector<char*> keep;
     keep = av;

@@ -170,7 +170,7 @@ struct LFArgs {
 };
 void launch_lf(const LFArgs& a, cudaStream_t s);
 // Zfunc (FZ408L:938-961): vaf[B] = 1/N sum_j Vhold_x[j] V_x[j]
-void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s);
+void launch_vaf(const double* V, const double* Vhold, int N, int ld, int B, double* out, cudaStream_t s, int squares = 0);
 void launch_transpose_psi_in(const double* psi_aos, double* psi_soa, int S, int N, int ld, int B, cudaStream_t s);
 void launch_transpose_psi_out(const double* psi_soa, double* psi_aos, int S, int N, int ld, int B, cudaStream_t s);
 // recordPairPairCorr (MD:584-625): counts[B][nbins] of ordered pairs per distance bin (nbins <= gr_max_bins())

@@ -290,19 +290,28 @@ void fz_output(FzOut& o, double t, int c0) {
   fclose(fa);
   o.counter++;
 }
-void fz_print_vaf(const FzOut& o, double t, double vaf) {
-  FILE* fa = open_in(o.dir, "VAF.dat", "a");
+void fz_print_vaf(const FzOut& o, double t, double vaf, const char* file = "VAF.dat") {
+  FILE* fa = open_in(o.dir, file, "a");
   fprintf(fa, "%lg\t%lg\n", t, vaf);  // :971
   fclose(fa);
 }
 }  // namespace
 
-int mdqt_program_fz408l(int argc, char** argv) {
-  OptMap opt = {{"Ge", "0.1"}, {"density", "2"}, {"N0", "3500"}, {"detuning", "-2.5"}, {"Om", "0.7"}, {"tpumpreal", "0.0000002"},
-                {"tstartV0", "15"}, {"tmax", "25"}, {"sampleFreq", "40"}, {"seed", ""}, {"saveDirectory", "dataTag408/"}, {"device", "0"},
-                {"program", "fz408l"}, {"quad", "0"}};
+// The same main() serves the two sibling programs (`variant`):
+//   fz408q  randomFrozenStartTag408Quad.cpp: ONE circularly polarised resonant 408 nm laser -- the coupling keeps two of its four
+//           terms (FZ408Q:441: the `quad` mask of the 7-level kernel), defaults detuning 0, Om 2, tpumpreal 1e-7 (FZ408Q:58-60), and
+//           Zfunc() is the v_x^2 autocorrelation "LongKin" written to vSquareAutoCorr.dat (FZ408Q:942-979).
+//   fz422l  randomFrozenStartTag422Linear.cpp: the 5-level 422 nm pump with its unit conversions (FZ422L:66-74: g2E x 0.894,
+//           ratio = round(34.81 x 0.894 / sqrt(n)), velocity x 0.967, decayRatio 0.0754, vKick 0.001257), defaults detuning -1,
+//           Om 1.3, tpumpreal 1e-7 (FZ422L:55-57), and NO output() at the measurement (FZ422L:1000-1005).
+static int program_fz(int argc, char** argv, int variant) {
+  const bool quadv = variant == 1, ca5 = variant == 2;
+  const char* pname = quadv ? "fz408q" : ca5 ? "fz422l" : "fz408l";
+  OptMap opt = {{"Ge", "0.1"}, {"density", "2"}, {"N0", "3500"}, {"detuning", quadv ? "0" : ca5 ? "-1" : "-2.5"}, {"Om", quadv ? "2" : ca5 ? "1.3" : "0.7"},
+                {"tpumpreal", variant ? "0.0000001" : "0.0000002"}, {"tstartV0", "15"}, {"tmax", "25"}, {"sampleFreq", "40"}, {"seed", ""},
+                {"saveDirectory", quadv ? "data/" : ca5 ? "data422/" : "dataTag408/"}, {"device", "0"}, {"program", pname}, {"quad", quadv ? "1" : "0"}};
   bool quiet = false;
-  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program fz408l <job> [--Ge x] [--density x] [--N0 n] ...\n"); return 2; }
+  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program fz408l|fz408q|fz422l <job> [--Ge x] [--density x] [--N0 n] ...\n"); return 2; }
   const unsigned job = (unsigned)atof(argv[1]);
   if (!parse_opts(argc, argv, 2, opt, &quiet)) return 2;
   const double Ge = atof(opt["Ge"].c_str()), density = atof(opt["density"].c_str()), detuning = atof(opt["detuning"].c_str());
@@ -331,14 +340,22 @@ int mdqt_program_fz408l(int argc, char** argv) {
   const int N = mdqt_io_init_su(seed, N0, Ge, ld, R.data(), V.data(), psi12.data(), tp.data(), &L, &lDeb);
   if (N < 0) { fprintf(stderr, "mdqt_run: more than N0+1000 ions drawn\n"); return 1; }
   printf("%i\n", N);  // FZ408L:301
-  std::vector<double> psi((size_t)N * 14, 0.0);
+  const int S2 = ca5 ? 10 : 14;  // doubles per ion of the wavefunction: 5 or 7 states x (re, im)
+  std::vector<double> psi((size_t)N * S2, 0.0);
   for (int i = 0; i < N; i++)
-    for (int k = 0; k < 4; k++) psi[(size_t)i * 14 + k] = psi12[(size_t)i * 24 + k];  // S(-1/2), S(+1/2): the only non-zero amplitudes
+    for (int k = 0; k < 4; k++) psi[(size_t)i * S2 + k] = psi12[(size_t)i * 24 + k];  // S(-1/2), S(+1/2): the only non-zero amplitudes
 
   mdqt_params p;
   CKP(mdqt_params_su(&p, Ge, density, 4, 19, 0, detuning, 0, Om, 0, N0, N));
-  p.scheme = MDQT_SCHEME_SR7; p.quad = atoi(opt["quad"].c_str());
+  p.scheme = ca5 ? MDQT_SCHEME_CA5 : MDQT_SCHEME_SR7; p.quad = atoi(opt["quad"].c_str());
   p.substeps_per_md = (int)round(34.81 / sqrt(density));  // FZ408L:73 rounds where SU takes the ceiling
+  if (ca5) {                                              // FZ422L:66-74, 116-117
+    p.g2E = 174.07 * .894 / sqrt(density);
+    p.substeps_per_md = (int)round(34.81 * .894 / sqrt(density));
+    p.pv2qv = 1.1821 * pow(density, 1. / 6) * .967;
+    p.dR = 0.0754;
+    p.vKick = 0.001257 / p.pv2qv;
+  }
   p.dtq = 0.002 / p.substeps_per_md;
   p.traj0 = (int)job; p.seed = (uint64_t)seed; p.device = atoi(opt["device"].c_str());
   mdqt_handle* h = NULL;
@@ -358,6 +375,7 @@ int mdqt_program_fz408l(int argc, char** argv) {
     if (pend_q) { CKP(mdqt_qsteps(h, (int)pend_q)); pend_q = 0; }
     if (pend_t) { CKP(mdqt_advance_time(h, (int)pend_t)); pend_t = 0; }
   };
+  const char* acfile = quadv ? "vSquareAutoCorr.dat" : "VAF.dat";  // printLongKin (FZ408Q:969-979) / printVAF (FZ408L:963-973)
   auto wall0 = std::chrono::steady_clock::now();
   while (t <= tmax + 0.0009) {  // FZ408L:1040
     if (!recorded && t >= tendV0) {
@@ -365,15 +383,15 @@ int mdqt_program_fz408l(int argc, char** argv) {
       int32_t nup = 0;
       CKP(mdqt_tag_particles(h, o.spin.data(), &nup));  // measureSpinUps()
       recorded = 1;
-      fz_output(o, t, c0);
-      CKP(mdqt_vaf(h, 1, &vaf));                          // Zfunc(0)
-      fz_print_vaf(o, t, vaf);
+      if (!ca5) fz_output(o, t, c0);                      // FZ408L:1045; the 422 nm program has no output() here (FZ422L:1000-1005)
+      CKP(quadv ? mdqt_vsq_autocorr(h, 1, &vaf) : mdqt_vaf(h, 1, &vaf));  // Zfunc(0)
+      fz_print_vaf(o, t, vaf, acfile);
     }
     if ((c0 + 1) % sampleFreq == 0 && tsc == 1 && recorded) {
       flush();
       fz_output(o, t, c0);
-      CKP(mdqt_vaf(h, 0, &vaf));                          // Zfunc(1)
-      fz_print_vaf(o, t, vaf);
+      CKP(quadv ? mdqt_vsq_autocorr(h, 0, &vaf) : mdqt_vaf(h, 0, &vaf));  // Zfunc(1)
+      fz_print_vaf(o, t, vaf, acfile);
     }
     if (tsc == ratio) {
       flush();                                            // step() tests the clock (2nd-order start while t <= 0, FZ408L:321)
@@ -410,8 +428,98 @@ int mdqt_program_fz408l(int argc, char** argv) {
   }
   const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
   if (!quiet)
-    fprintf(stderr, "mdqt_run: program fz408l, job %u, N=%d, t=%.6f, c0=%d: %ld loop iterations, %u outputs in %.3f s; files in %s\n", job, N, t, c0,
+    fprintf(stderr, "mdqt_run: program %s, job %u, N=%d, t=%.6f, c0=%d: %ld loop iterations, %u outputs in %.3f s; files in %s\n", pname, job, N, t, c0,
             iters, o.counter, wall, dir.c_str());
+  mdqt_destroy(h);
+  return 0;
+}
+int mdqt_program_fz408l(int argc, char** argv) { return program_fz(argc, argv, 0); }
+int mdqt_program_fz408q(int argc, char** argv) { return program_fz(argc, argv, 1); }
+int mdqt_program_fz422l(int argc, char** argv) { return program_fz(argc, argv, 2); }
+
+// ---- laserCoolNoPlasmaThreeState.cpp --------------------------------------------------------------------------------------------
+// main() (TS:352-409): N0 non-interacting ions with Maxwellian velocities (std::mt19937 + normal_distribution, sigma = 1.0508
+// sqrt(T[K]), TS:83, 115-131) in the ground state of a J = 0 -> J = 1 transition lit by two counter-propagating sigma+/sigma- beams;
+// the loop is { t += dt; every sampleFreq-th iteration output(); qstep(); c0++ } until t > tmax, and output() appends
+// "t <tab> <v_x^2>/2" to energies.dat (TS:296-322). No plasma forces at all: the whole run is the 3-level substep kernel, sampleFreq
+// sweeps fused per launch. Directory: <save>/Om%d/Det%dNumIons%dInitialTemp%duK/job%d/ (TS:371-382; the (unsigned) cast of a
+// negative detuning is printed as the reference prints it on x86-64).
+int mdqt_program_ts(int argc, char** argv) {
+  OptMap opt = {{"N0", "1000"}, {"detuning", "-0.5"}, {"Om", "0.5"}, {"tmax", "45000"}, {"sampleFreq", "1000"}, {"temperature", "0.01"},
+                {"seed", ""}, {"saveDirectory", "dataLaserCoolTestDoppShift/"}, {"device", "0"}, {"program", "ts"}};
+  bool quiet = false;
+  if (argc < 2 || argv[1][0] == '-') { fprintf(stderr, "usage: mdqt_run --program ts <job> [--N0 n] [--detuning x] [--Om x] [--tmax x] ...\n"); return 2; }
+  const unsigned job = (unsigned)atof(argv[1]);
+  if (!parse_opts(argc, argv, 2, opt, &quiet)) return 2;
+  const int N0 = atoi(opt["N0"].c_str()), sampleFreq = atoi(opt["sampleFreq"].c_str());
+  const double detuning = atof(opt["detuning"].c_str()), Om = atof(opt["Om"].c_str()), tmax = atof(opt["tmax"].c_str());
+  const double temperature = atof(opt["temperature"].c_str());
+  const unsigned seed = opt["seed"].empty() ? (unsigned)time(NULL) + job : (unsigned)atol(opt["seed"].c_str());  // TS:388
+  if (N0 < 1 || sampleFreq < 1) { fprintf(stderr, "mdqt_run: N0 and sampleFreq must be positive\n"); return 2; }
+
+  std::string dir = opt["saveDirectory"];
+  mkdir(dir.c_str(), 0777);
+  char namebuf[256];
+  snprintf(namebuf, sizeof(namebuf), "Om%d/", as_unsigned_printed(Om * 100));
+  dir += namebuf;
+  mkdir(dir.c_str(), 0777);
+  snprintf(namebuf, sizeof(namebuf), "Det%dNumIons%dInitialTemp%duK", (int)(unsigned)(long long)(detuning * 100), N0, as_unsigned_printed(temperature * 1000000));
+  dir += namebuf;
+  mkdir(dir.c_str(), 0777);
+  snprintf(namebuf, sizeof(namebuf), "/job%d/", (int)job);
+  dir += namebuf;
+  mkdir(dir.c_str(), 0777);
+
+  // init() (TS:115-131)
+  std::mt19937 rng(seed);
+  std::normal_distribution<double> velocityDistribution(0, 1.0508 * sqrt(temperature));
+  std::vector<double> V((size_t)3 * N0), R((size_t)3 * N0, 0.0), psi((size_t)N0 * 6, 0.0), tp(N0, 0.0);
+  for (int i = 0; i < N0; i++) {
+    V[i] = velocityDistribution(rng); V[(size_t)N0 + i] = velocityDistribution(rng); V[(size_t)2 * N0 + i] = velocityDistribution(rng);
+    psi[(size_t)i * 6] = 1.0;
+  }
+  mdqt_params p;
+  CKP(mdqt_params_ts(&p, N0, detuning, Om));
+  p.traj0 = (int)job; p.seed = seed; p.device = atoi(opt["device"].c_str());
+  mdqt_handle* h = NULL;
+  CKP(mdqt_create(&p, &h));
+  CKP(mdqt_upload_state(h, R.data(), V.data(), psi.data(), tp.data(), N0));
+  CKP(mdqt_set_time(h, 0.0, 0));
+  const double dt = 0.01;  // TS:390
+  // the loop's schedule first (the reference's repeated addition t += dt decides where it ends), then the launches: every output()
+  // is one reduction kernel appending sum v_x^2 to a device log -- nothing synchronises until the log is read back at the end
+  std::vector<double> tout;
+  std::vector<long> sweeps_before;  // qstep() sweeps between the previous output() and this one
+  long c0 = 0, pend = 0;
+  {
+    double t = 0.0;
+    while (t <= tmax) {  // TS:392
+      t += dt;
+      if ((c0 + 1) % sampleFreq == 0) { tout.push_back(t); sweeps_before.push_back(pend); pend = 0; }  // output() (TS:296-322)
+      pend++;  // qstep()
+      c0++;
+    }
+  }
+  const long outputs = (long)tout.size();
+  if (outputs > (1 << 22)) { fprintf(stderr, "mdqt_run: more than 2^22 outputs; raise --sampleFreq\n"); return 2; }
+  auto wall0 = std::chrono::steady_clock::now();
+  if (outputs) CKP(mdqt_moments_begin(h, (int)outputs));
+  for (long k = 0; k < outputs; k++) {
+    if (sweeps_before[k]) CKP(mdqt_qsteps(h, (int)sweeps_before[k]));
+    CKP(mdqt_moments_record(h, (int)k));
+  }
+  if (pend) CKP(mdqt_qsteps(h, (int)pend));
+  if (outputs) {
+    std::vector<double> rec((size_t)outputs * 23);
+    CKP(mdqt_moments_download(h, rec.data(), (int)outputs));
+    FILE* fe = open_in(dir, "energies.dat", "a");
+    for (long k = 0; k < outputs; k++) fprintf(fe, "%lg\t%lg\n", tout[k], 0.5 * rec[(size_t)k * 23] / (double)N0);  // TS:318: t, EkinX
+    fclose(fe);
+  }
+  CKP(mdqt_sync(h));
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+  if (!quiet)
+    fprintf(stderr, "mdqt_run: program ts, job %u, N0=%d: %ld sweeps, %ld outputs in %.3f s; files in %s\n", job, N0, c0, outputs, wall, dir.c_str());
   mdqt_destroy(h);
   return 0;
 }

@@ -5,7 +5,7 @@ the reference and stay in Python: they only sequence calls that run on the GPU.
 """
 
 
-def fz_main_loop(eng, tmax, tstartV0, tendV0, c0=-1, sampleFreq=40, new_run=True, on_measure=None, on_sample=None):
+def fz_main_loop(eng, tmax, tstartV0, tendV0, c0=-1, sampleFreq=40, new_run=True, on_measure=None, on_sample=None, zfunc=None):
     """The time loop of randomFrozenStartTag408Linear.cpp (FZ408L:1040-1072) on an :class:`Engine` created with the
     7-level scheme, the SU box and ``substeps_per_md = plasmaToQuantumTimestepRatio``:
 
@@ -20,8 +20,11 @@ def fz_main_loop(eng, tmax, tstartV0, tendV0, c0=-1, sampleFreq=40, new_run=True
     File output is the caller's business: ``on_measure(t, tagged, n_up, vaf)`` and ``on_sample(t, c0, vaf)`` are invoked
     where the reference calls ``output()``/``printVAF``. Consecutive pump-window ``qstep()`` calls between two events are
     fused into one launch; ``t`` advances by the reference's repeated addition on host and device alike.
+    ``zfunc`` replaces ``eng.Zfunc`` -- the Quad program correlates v_x^2 instead (``eng.ZfuncLongKin``, FZ408Q:942-967); the
+    422 nm program is the same loop on an engine with the 5-level scheme (its main() only omits the output() at the measurement).
     Returns ``dict(c0, iters, tagged, n_up, vaf_measure, vaf_last, t)``.
     """
+    zfunc = zfunc or eng.Zfunc
     p = eng.params
     ratio, dtq = int(p.substeps_per_md), float(p.dtq)
     t = eng.time()[0]
@@ -46,13 +49,13 @@ def fz_main_loop(eng, tmax, tstartV0, tendV0, c0=-1, sampleFreq=40, new_run=True
             flush()
             tagged, n_up = eng.measureSpinUps()
             recorded = True
-            vaf = eng.Zfunc(0)
+            vaf = zfunc(0)
             out.update(tagged=tagged, n_up=n_up, vaf_measure=vaf)
             if on_measure:
                 on_measure(t, tagged, n_up, vaf)
         if (c0 + 1) % sampleFreq == 0 and tsc == 1 and recorded:
             flush()
-            vaf = eng.Zfunc(1)
+            vaf = zfunc(1)
             out["vaf_last"] = vaf
             if on_sample:
                 on_sample(t, c0, vaf)

@@ -45,7 +45,7 @@ ABI_SYMBOLS = [
     "mdqt_qsteps", "mdqt_set_forced_uniforms", "mdqt_set_forced_collisions", "mdqt_philox_uniforms", "mdqt_device_ptr",
     "mdqt_device_ld", "mdqt_stream", "mdqt_mark_wrapped", "mdqt_force_plan", "mdqt_enable_timing",
     "mdqt_kernel_time_ms", "mdqt_fp64_peak", "mdqt_params_ts", "mdqt_leapfrog_step", "mdqt_advance_time",
-    "mdqt_tag_particles", "mdqt_vaf", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
+    "mdqt_tag_particles", "mdqt_vaf", "mdqt_vsq_autocorr", "mdqt_set_forced_tag_uniforms", "mdqt_pair_correlation", "mdqt_vstore_begin",
     "mdqt_vstore_record", "mdqt_vstore_upload", "mdqt_autocorrelations", "mdqt_diag_partial", "mdqt_vel_dist_partial",
     "mdqt_vv_steps", "mdqt_set_ion_counts", "mdqt_set_traj_seeds", "mdqt_time_forces", "mdqt_comm_unique_id", "mdqt_comm_init", "mdqt_comm_destroy",
     "mdqt_comm_exchange_positions", "mdqt_comm_allreduce", "mdqt_populations_rows", "mdqt_download_rows", "mdqt_set_tags", "mdqt_moments_begin", "mdqt_moments_record",
@@ -105,6 +105,7 @@ def load_library():
     L.mdqt_advance_time.argtypes = [vp, ctypes.c_int]
     L.mdqt_tag_particles.argtypes = [vp, vp, vp]
     L.mdqt_vaf.argtypes = [vp, ctypes.c_int, c_double_p]
+    L.mdqt_vsq_autocorr.argtypes = [vp, ctypes.c_int, c_double_p]
     L.mdqt_set_forced_tag_uniforms.argtypes = [vp, vp]
     L.mdqt_pair_correlation.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, vp, vp]
     L.mdqt_vstore_begin.argtypes = [vp, ctypes.c_int]
@@ -384,6 +385,12 @@ class Engine:
         """Zfunc() FZ408L:938-961: VAF against the velocities stored when c1V == 0."""
         v = np.empty(self.B)
         self._ck(self.lib.mdqt_vaf(self.h, 1 if c1V == 0 else 0, v.ctypes.data_as(c_double_p)))
+        return v if self.B > 1 else float(v[0])
+
+    def ZfuncLongKin(self, c1V):
+        """Zfunc() of the Quad program (FZ408Q:942-967): the v_x^2 autocorrelation against the velocities stored when c1V == 0."""
+        v = np.empty(self.B)
+        self._ck(self.lib.mdqt_vsq_autocorr(self.h, 1 if c1V == 0 else 0, v.ctypes.data_as(c_double_p)))
         return v if self.B > 1 else float(v[0])
 
     def recordPairPairCorr(self, pairPairStep=0.05, pairPairMax=None):
