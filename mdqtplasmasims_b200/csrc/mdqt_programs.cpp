@@ -6,6 +6,9 @@
 //            autocorrelations, the instantaneous-anisotropy stage, re-equilibration, and the laser-force anisotropy stages.
 //   fz408l   randomFrozenStartTag408Linear.cpp main() (FZ408L:981-1076): frozen random start, leap-frog time loop with the
 //            408 nm pump window, spin measurement and the tagged velocity autocorrelation.
+//   fz408q, fz422l   its siblings randomFrozenStartTag408Quad.cpp (circular resonant pump, v_x^2 autocorrelation) and
+//            randomFrozenStartTag422Linear.cpp (5-level 422 nm scheme): the same main() with their defaults and differences.
+//   ts       laserCoolNoPlasmaThreeState.cpp main() (TS:352-409): free ions in a J = 0 -> J = 1 molasses, energies.dat.
 //   mc408l, mc422l   MonteCarloFollowedByQTTagging408Linear.cpp / ...422Linear.cpp main() (MC408L:1140-1254, MC422L:1100-1222), stages 1, 4-7: collisional MD, the pump stage
 //            (62 x 7-level qstep() per MDStep), the projective spin measurement, the recording stage with the tagged ions' moments
 //            and velocity distribution, the autocorrelations.
