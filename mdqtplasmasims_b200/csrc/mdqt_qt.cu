@@ -191,6 +191,9 @@ double2 load_forces_impl(const double* __restrict__ fpart, double* __restrict__ 
 
 // One force component of ion i (the four-lane kernel: quad lanes 0, 1, 2 take x, y, z and share them by shuffle, so a lane has
 // 21 partial loads in flight in ONE L2 round trip instead of 2 x 21 in four). Same ascending sum, same bits.
+#ifndef MDQT_K2_TRIGGER
+#define MDQT_K2_TRIGGER 0  // 1: the four-lane substep kernel releases its dependent (the force kernel) at its START (A/B knob)
+#endif
 #ifndef MDQT_K2_FLOAD1
 #define MDQT_K2_FLOAD1 1
 #endif
@@ -708,6 +711,13 @@ __global__ void __launch_bounds__(MDQT_K2_LB) k_substeps4(QTArgs a, QTConsts C) 
   const int base = threadIdx.x & 28;  // first lane of this ion's quad within the warp
 
   pdl_wait();
+#if MDQT_K2_TRIGGER == 1
+  // Every CTA of this kernel is resident from the start (one warp per scheduler at most), so the dependent force kernel may be
+  // launched NOW: one of its two CTAs per SM fits beside these warps (226 x 32 x 4 + 126 x 256 registers), loads its exp table and
+  // waits at its griddepcontrol.wait -- which returns only when this grid has completed and flushed -- so launch latency and prologue
+  // hide behind the 25 substeps instead of following them
+  pdl_launch_dependents();
+#endif
   if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 0);
   cplx y[3];
 #pragma unroll
@@ -910,7 +920,9 @@ __global__ void __launch_bounds__(MDQT_K2_LB) k_substeps4(QTArgs a, QTConsts C) 
   }
 
 #undef prep
+#if MDQT_K2_TRIGGER != 1
   pdl_launch_dependents();  // the force kernel's launch and prologue may overlap the stores below (it waits before reading)
+#endif
   if ((threadIdx.x & 31) == 0) stamp_time(a.stamp, 1);
   if (!active) return;
 #pragma unroll
