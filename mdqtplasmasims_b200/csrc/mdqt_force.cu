@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(RG * JS, (RG == 32 && JS == 8) ? MDQT_K1_MINB3
 #endif
 constexpr int kItemUnroll1 = MDQT_K1_UNR1, kItemUnroll2 = MDQT_K1_UNR2;  // j-loop unroll with one / two rows per lane (A/B knobs)
 constexpr int kItemResidentWarps = 16;
+constexpr int kItemUnrollFat = 8;  // j-loop unroll of the one-CTA-per-SM instantiation (two rows per lane): 12 and 16 measured slower
 constexpr int kItemMaxB = 512;   // per-trajectory ion counts cached in shared memory up to this batch size
 constexpr int kItemMaxJ = 256;  // positions per chunk: 2 buffers x (24 B x 256 + rows) x 8 warps = 120 KB per CTA at most
 
@@ -539,8 +540,8 @@ struct Item { int b, g, ch, Nb, jl; };
 #define WTRACE(slot)
 #endif
 
-template <int NW, int IPT, bool EPOT, bool HL>
-__global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
+template <int NW, int IPT, bool EPOT, bool HL, int RW = kItemResidentWarps>  // RW = resident warps per SM (register budget 65536 / (32 RW))
+__global__ void __launch_bounds__(NW * 32, RW / NW) k_pairs_items(ForceArgs a, double* __restrict__ item_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8192) double stab_mem[kExpTable];  // 8 KB-aligned: see pair_core<.., TAB32>
   __shared__ int snb[kItemMaxB];  // the trajectories' ion counts: read at every item decode, so not from L2
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(NW * 32, kItemResidentWarps / NW) k_pairs_item
     }
     const int cnt = min(cur.jl, cur.Nb - cur.ch * cur.jl);
     WTRACE(2)
-#pragma unroll(IPT == 2 ? kItemUnroll2 : kItemUnroll1)
+#pragma unroll(IPT == 2 ? (RW == 8 ? kItemUnrollFat : kItemUnroll2) : kItemUnroll1)
     for (int jj = 0; jj < cnt; jj++) {
       const longlong2 pxy = sxy[jj];
       const long long pz = sz[jj];
@@ -689,13 +690,13 @@ static int items_ipt(const ForceArgs& a) {
   return items1 >= 4LL * 148 * kItemResidentWarps ? 2 : 1;
 }
 
-template <int NW, int IPT, bool EPOT>
+template <int NW, int IPT, bool EPOT, int RW = kItemResidentWarps>
 static void launch_items_nw(const ForceArgs& a, double* partials, cudaStream_t s) {
   const size_t smem = (size_t)NW * 2 * (24 * (size_t)a.jlen + 24 * 32 * IPT);
   const long long total = (long long)a.B * ((a.nrows + 32 * IPT - 1) / (32 * IPT)) * a.nsplit;
-  const int grid = (int)std::min<long long>(148LL * (kItemResidentWarps / NW), (total + NW - 1) / NW);
+  const int grid = (int)std::min<long long>(148LL * (RW / NW), (total + NW - 1) / NW);
   const bool hl = a.half_l && MDQT_VALID_INT;
-  void (*kern)(ForceArgs, double*) = hl ? k_pairs_items<NW, IPT, EPOT, true> : k_pairs_items<NW, IPT, EPOT, false>;
+  void (*kern)(ForceArgs, double*) = hl ? k_pairs_items<NW, IPT, EPOT, true, RW> : k_pairs_items<NW, IPT, EPOT, false, RW>;
   // function attributes are per DEVICE (one process may drive several GPUs from several threads: mdqt_run --gpus): set them once
   // on every device this instantiation is launched on
   static std::atomic<bool> attr_done[64][2];
@@ -720,6 +721,17 @@ template <bool EPOT>
 static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
   const int ipt = EPOT ? 1 : items_ipt(a);  // the potential energy is a diagnostic: one instantiation
   if (EPOT) { launch_items_nw<8, 1, EPOT>(a, partials, s); return; }
+  // One trajectory whose items fit ONE round of 148 x 8 warps at two rows per lane: ONE 8-warp CTA per SM with the whole register
+  // file (156 registers, 16 independent pair chains per warp) instead of two CTAs of 8 one-row warps. Two co-resident CTAs do not
+  // share the issue ports evenly -- the one that arrived first has strict priority, finishes early and leaves the other alone on ports
+  // that two 8-chain warps per scheduler fill to 67 % only -- whereas here the two warps of a scheduler are equals
+  // and each carries twice the chains: 28.6 -> 27.5 us at N = 3500, 31.0 -> 29.8 at N = 3653 (profiles/r02y_fat_ab2.log). Same items,
+  // same chunk order, same bits. MDQT_K1_FAT=0 switches it off (A/B runs).
+  {
+    static const bool fat = [] { const char* e = getenv("MDQT_K1_FAT"); return !(e && e[0] == '0'); }();
+    const long long items2 = (long long)((a.nrows + 63) / 64) * a.nsplit;
+    if (fat && a.B == 1 && items2 <= 148LL * 8) { launch_items_nw<8, 2, false, 8>(a, partials, s); return; }
+  }
   if (ipt == 1) { launch_items_nw<8, 1, false>(a, partials, s); return; }
   // two rows per lane (batches): one 16-warp CTA per SM when its tiles fit (chunks of up to 192 positions), else two of 8
   if ((size_t)16 * 2 * (24 * (size_t)a.jlen + 24 * 64) + 12 * 1024 <= (size_t)227 * 1024) launch_items_nw<16, 2, false>(a, partials, s);
