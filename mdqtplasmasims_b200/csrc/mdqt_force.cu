@@ -728,9 +728,9 @@ static void launch_items(const ForceArgs& a, double* partials, cudaStream_t s) {
   // and each carries twice the chains: 28.6 -> 27.5 us at N = 3500, 31.0 -> 29.8 at N = 3653 (profiles/r02y_fat_ab2.log). Same items,
   // same chunk order, same bits. MDQT_K1_FAT=0 switches it off (A/B runs).
   {
-    static const bool fat = [] { const char* e = getenv("MDQT_K1_FAT"); return !(e && e[0] == '0'); }();
+    static const int fat = [] { const char* e = getenv("MDQT_K1_FAT"); return e ? atoi(e) : 1; }();  // 2: also for batches (A/B: slower)
     const long long items2 = (long long)((a.nrows + 63) / 64) * a.nsplit;
-    if (fat && a.B == 1 && items2 <= 148LL * 8) { launch_items_nw<8, 2, false, 8>(a, partials, s); return; }
+    if (fat == 2 || (fat && a.B == 1 && items2 <= 148LL * 8)) { launch_items_nw<8, 2, false, 8>(a, partials, s); return; }
   }
   if (ipt == 1) { launch_items_nw<8, 1, false>(a, partials, s); return; }
   // two rows per lane (batches): one 16-warp CTA per SM when its tiles fit (chunks of up to 192 positions), else two of 8
