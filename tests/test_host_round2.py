@@ -86,3 +86,31 @@ def test_reference_arm_prints_the_contract_line():
     assert d["config"]["md_steps_per_step"] >= 1 and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert abs(d["ms_per_step"] * 1e-3 * d["value"] - d["config"]["n_ions"] * 25.0 * d["config"]["md_steps_per_step"]) < 1e-6 * d["value"] * d["ms_per_step"]
+
+
+@pytest.mark.parametrize("program,args,tree", [
+    ("md", ["--N", "512"], "Gamma300Kappa50NumIons512/job3"),                                                        # MD:1037-1058
+    ("mc408l", ["--N", "512"], "Gamma300Kappa50NumIons512PumpTime200Det250Om70Density20/job3"),                      # MC408L:1153
+    ("fz408l", ["--N0", "700"], "PumpTime200PumpStart15Det250Om70Density20Ge100NumIons700/job3"),                    # FZ408L:990
+    ("fz408q", ["--N0", "700"], "PumpTime100PumpStart15Det0Om200Density20Ge100NumIons700/job3"),                     # FZ408Q:58-60, 999
+    ("fz422l", ["--N0", "700"], "PumpTime100PumpStart15Det100Om130Density20Ge100NumIons700/job3"),                   # FZ422L:55-57, 955
+    ("ts", ["--N0", "100"], "Om50/Det-50NumIons100InitialTemp10000uK/job3"),                                         # TS:371-382
+])
+def test_program_drivers_build_the_reference_tree_and_fail_loudly_without_a_gpu(tmp_path, program, args, tree):
+    """`mdqt_run --program <p>`: every host loop first makes the reference's directory tree from the reference's DEFAULT inputs
+    (so the names below are what the reference's own main() would create; TS prints its negative detuning through an (unsigned)
+    cast as -50 on x86-64) and then needs a CUDA device -- without one it must stop with the library's error, never compute on the CPU."""
+    from mdqtplasmasims_b200 import load_library
+    if load_library().mdqt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    save = str(tmp_path) + "/"
+    r = subprocess.run([os.path.join(ROOT, "mdqtplasmasims_b200", "mdqt_run"), "--program", program, "3", "--seed", "1", "--saveDirectory", save,
+                        "--quiet"] + args, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in r.stderr, (r.returncode, r.stderr[-500:])
+    assert os.path.isdir(os.path.join(save, tree)), [os.path.join(dp, d) for dp, ds, _ in os.walk(save) for d in ds]
+    assert not any(fs for _, _, fs in os.walk(save))          # nothing was written
+
+
+def test_unknown_program_is_a_usage_error():
+    r = subprocess.run([os.path.join(ROOT, "mdqtplasmasims_b200", "mdqt_run"), "--program", "nosuch", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "unknown program" in r.stderr
