@@ -267,7 +267,7 @@ int mdqt_create(const mdqt_params* p, mdqt_handle** out) {
   h->forced_u = nullptr; h->forced_nsub = 0; h->forced_cursor = 0; h->forced_cu = h->forced_cn = nullptr;
   h->vhold = nullptr; h->forced_tag = nullptr; h->tagged = nullptr;
   h->gr_counts = nullptr; h->vstore = h->ac_partials = h->ac_out = nullptr; h->vstore_T = 0;
-  h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr; h->comm = nullptr;
+  h->clock = nullptr; h->nb = nullptr; h->seeds = nullptr; h->comm = nullptr; h->ilist = nullptr; h->icount = 0;
   h->tags = nullptr; h->moments = nullptr; h->moments_slots = 0;
   h->timing = 0; h->ev_used = 0; h->stamps = nullptr; h->stamps_cap = 0;
   for (int k = 0; k < 4; k++) { h->time_ms[k] = 0; h->time_n[k] = 0; }
@@ -319,6 +319,7 @@ int mdqt_destroy(mdqt_handle* h) {
   if (h->clock) cudaFree(h->clock);
   if (h->nb) cudaFree(h->nb);
   if (h->jl) cudaFree(h->jl);
+  if (h->ilist) cudaFree(h->ilist);
   if (h->tags) cudaFree(h->tags);
   if (h->moments) cudaFree(h->moments);
   if (h->stamps) cudaFree(h->stamps);
@@ -457,6 +458,23 @@ int mdqt_set_ion_counts(mdqt_handle* h, const int32_t* n_ions) {
       h->jlen = jmax; h->nsplit = nsmax;  // tile capacity and chunk-slot capacity of the batch
       if (pdl_mode() < 0) h->pdl = (h->B == 1 && (long long)((n_ions[0] + 31) / 32) * h->nsplit <= 148LL * 2 * 8) ? 1 : 0;
     }
+    // unequal ion counts leave ~8 % of the (trajectory, row group, chunk) slots empty, and a static walk over slots then gives the warps
+    // 29-34 real items each: hand the kernel the packed list of the non-empty items (two rows per lane: the batch instantiations)
+    if (h->ilist) { cudaFree(h->ilist); h->ilist = nullptr; h->icount = 0; }
+    static const bool use_list = [] { const char* e = getenv("MDQT_K1_ILIST"); return !(e && e[0] == '0'); }();  // A/B knob
+    if (n_ions && h->items && h->B > 1 && h->B < (1 << 14) && h->nsplit <= 1024 && h->N <= 64 * 256 && use_list) {
+      std::vector<unsigned> list;
+      list.reserve((size_t)h->B * ((h->N + 63) / 64) * h->nsplit);
+      for (int b = 0; b < h->B; b++) {
+        const int jlb = (h->p.plan_n == 0) ? plan_items_jlen(n_ions[b]) : h->jlen;
+        const int groups = (n_ions[b] + 63) / 64, nch = (n_ions[b] + jlb - 1) / jlb;
+        for (int g = 0; g < groups; g++)
+          for (int ch = 0; ch < nch; ch++) list.push_back((unsigned)b << 18 | (unsigned)g << 10 | (unsigned)ch);
+      }
+      CU(cudaMalloc((void**)&h->ilist, sizeof(unsigned) * list.size()));
+      CU(cudaMemcpy(h->ilist, list.data(), sizeof(unsigned) * list.size(), cudaMemcpyHostToDevice));
+      h->icount = (int)list.size();
+    }
     if (h->nsplit != old_nsplit) {  // the partial-sum buffers are sized by the number of chunk slots
       cudaFree(h->Fpart); cudaFree(h->epot_partials);
       h->Fpart = h->epot_partials = nullptr;
@@ -500,7 +518,7 @@ extern "C++" ForceArgs mdqt_force_args(mdqt_handle* h) {
   a.R = h->R; a.F = h->F; a.Fpart = h->Fpart; a.counters = h->counters;
   a.N = h->N; a.ld = h->ld; a.B = h->B; a.row0 = h->row0; a.nrows = h->nrows;
   a.nsplit = h->nsplit; a.jlen = h->jlen; a.ipt = h->ipt; a.jsub = h->jsub; a.rg = h->rg; a.Rfix = h->Rfix;
-  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb; a.jl = h->jl; a.pdl = h->pdl;
+  a.items = h->items; a.gcap = (h->nrows + 31) / 32; a.nb = h->nb; a.jl = h->jl; a.pdl = h->pdl; a.ilist = h->ilist; a.icount = h->icount;
   a.mg_chunk = ((1ULL << 40) + h->nsplit - 1) / h->nsplit; a.mg_gcap = ((1ULL << 40) + a.gcap - 1) / a.gcap;
   { const int g2 = (h->nrows + 63) / 64; a.mg_gcap2 = ((1ULL << 40) + g2 - 1) / g2; }
   a.L = h->p.L; a.halfL = h->p.L / 2.; a.invL = 1.0 / h->p.L; a.kappa = h->p.kappa; a.rc2 = h->p.rcut * h->p.rcut;

@@ -565,15 +565,21 @@ __global__ void __launch_bounds__(NW * 32, RW / NW) k_pairs_items(ForceArgs a, d
 
   const int gcap = (a.nrows + RPG - 1) / RPG;
   const int W = gridDim.x * NW;
-  const int total = a.B * gcap * a.nsplit;
+  const bool listed = !EPOT && IPT == 2 && a.ilist != nullptr;  // walk the packed list of non-empty items instead of all slots
+  const int total = listed ? a.icount : a.B * gcap * a.nsplit;
   const int rowend_cap = a.row0 + a.nrows;
   const unsigned long long mg_g = (IPT == 2) ? a.mg_gcap2 : a.mg_gcap;
   // item k -> (b, g, ch) by multiplication with host-made reciprocals (k < 2^24, divisors < 2^16: exact)
   auto decode = [&](int k, Item& it) {
-    const unsigned t = (unsigned)(((unsigned long long)(unsigned)k * a.mg_chunk) >> 40);
-    it.ch = k - (int)t * a.nsplit;
-    it.b = (int)(((unsigned long long)t * mg_g) >> 40);
-    it.g = (int)t - it.b * gcap;
+    if (listed) {
+      const unsigned v = __ldg(a.ilist + k);
+      it.b = (int)(v >> 18); it.g = (int)((v >> 10) & 255u); it.ch = (int)(v & 1023u);
+    } else {
+      const unsigned t = (unsigned)(((unsigned long long)(unsigned)k * a.mg_chunk) >> 40);
+      it.ch = k - (int)t * a.nsplit;
+      it.b = (int)(((unsigned long long)t * mg_g) >> 40);
+      it.g = (int)t - it.b * gcap;
+    }
     it.Nb = nb_smem ? snb[it.b] : (a.nb ? a.nb[it.b] : a.N);
     it.jl = nb_smem ? sjl[it.b] : (a.jl ? a.jl[it.b] : a.jlen);
     // empty when the group or the chunk lies beyond the trajectory's ions
@@ -693,7 +699,7 @@ static int items_ipt(const ForceArgs& a) {
 template <int NW, int IPT, bool EPOT, int RW = kItemResidentWarps>
 static void launch_items_nw(const ForceArgs& a, double* partials, cudaStream_t s) {
   const size_t smem = (size_t)NW * 2 * (24 * (size_t)a.jlen + 24 * 32 * IPT);
-  const long long total = (long long)a.B * ((a.nrows + 32 * IPT - 1) / (32 * IPT)) * a.nsplit;
+  const long long total = (!EPOT && IPT == 2 && a.ilist) ? a.icount : (long long)a.B * ((a.nrows + 32 * IPT - 1) / (32 * IPT)) * a.nsplit;
   const int grid = (int)std::min<long long>(148LL * (RW / NW), (total + NW - 1) / NW);
   const bool hl = a.half_l && MDQT_VALID_INT;
   void (*kern)(ForceArgs, double*) = hl ? k_pairs_items<NW, IPT, EPOT, true, RW> : k_pairs_items<NW, IPT, EPOT, false, RW>;

@@ -44,6 +44,9 @@ struct ForceArgs {
   int pdl;                                // launch with programmatic stream serialisation (pdl_mode)
   unsigned long long mg_chunk, mg_gcap, mg_gcap2;  // ceil(2^40 / nsplit), ceil(2^40 / groups of 32 rows), ... of 64 rows: item index -> (b, g, chunk) without division
   const int* nb;     // [B] ions per trajectory (ensembles whose jobs drew different N, SU:299-337) or null: all N
+  // batches with unequal ion counts: the NON-EMPTY items at two rows per lane, packed b << 18 | 64-row group << 10 | chunk in slot
+  // order, so that the warps walk equal numbers of real items (the slot walk leaves them 29-34 each when 8 % of the slots are empty)
+  const unsigned* ilist; int icount;
   unsigned long long* stamp;  // {min start, max end} of this launch in %globaltimer ns (in-graph kernel timing) or null
 };
 
